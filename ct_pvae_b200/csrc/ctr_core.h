@@ -1,0 +1,303 @@
+// ctr_core.h -- per-thread arithmetic of the Radon kernels, written once as
+// __host__ __device__ so the exact same code runs inside the sm_100a kernels
+// (ctr_kernels.cu) and inside the CPU emulation harness under tests/emu/ that
+// checks the geometry logic without a GPU.  Nothing here touches memory spaces,
+// barriers or TMA; that glue lives in ctr_kernels.cu.
+//
+// Semantics restated (reference file:line in /root/reference):
+//   ctvae/forward_functions.py:113   tfa.image.rotate(imgs, -theta)  -> ImageProjectiveTransformV3
+//   ctvae/forward_functions.py:114   tf.reduce_sum(imgs_rot, 1)
+// Sample coordinates follow TF's ProjectiveGenerator bit for bit: float32,
+// ((t0*x_out) + (t1*y_out)) + t2, no FMA contraction (CTR_MUL/CTR_ADD).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define CTR_HD __host__ __device__ __forceinline__
+#else
+#define CTR_HD inline
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define CTR_MUL(a, b) __fmul_rn((a), (b))
+#define CTR_ADD(a, b) __fadd_rn((a), (b))
+#define CTR_SUB(a, b) __fsub_rn((a), (b))
+#else  // host: translation units are compiled with -ffp-contract=off
+#define CTR_MUL(a, b) ((a) * (b))
+#define CTR_ADD(a, b) ((a) + (b))
+#define CTR_SUB(a, b) ((a) - (b))
+#endif
+
+enum { CTR_NEAREST = 0, CTR_BILINEAR = 1 };
+enum { CTR_ADJ_EXACT = 0, CTR_ADJ_TF = 1, CTR_ADJ_FBP = 2 };
+
+// Per-angle ray coefficients, normalised to the packed-image orientation the angle
+// is served from ("class"):
+//   u(j,i) = (u0*j + u1*i) + u2   coordinate along a packed row (contiguous axis)
+//   v(j,i) = (v0*j + v1*i) + v2   coordinate across packed rows (the strip axis)
+// class 0 (|cos| >= |sin|): u = x_in, v = y_in, served from the row-major pack;
+// class 1 (|sin| >  |cos|): u = y_in, v = x_in, served from the transposed pack.
+// Either way |v1| >= 0.707, so every ray crosses the strips at a steady rate.
+struct CtrRay {
+    float u0, u1, u2;
+    float v0, v1, v2;
+    int angle;  // row of the sinogram this ray set writes
+    int cls;
+};
+
+// Packed-image geometry of one class (frame coordinates -> packed indices).
+// A sample is inside the image's footprint iff ulo < u < uhi and vlo < v < vhi.
+struct CtrClassGeom {
+    float ulo, uhi, vlo, vhi;
+    int offu, offv;  // packed index = (int)floor(coord) - off   (off = pad - 1: one halo pixel)
+    int Up, Vp;      // packed row length (pixels) and row count, halos included
+};
+
+// NB interleaved floats -> registers (128-bit shared-memory loads on the device).
+template <int NB>
+CTR_HD void ctr_ldv(const float* __restrict__ p, float* __restrict__ out)
+{
+#if defined(__CUDA_ARCH__)
+    static_assert(NB % 4 == 0, "NB must be a multiple of 4 (16-byte vectors)");
+#pragma unroll
+    for (int q = 0; q < NB / 4; ++q) {
+        const float4 t = reinterpret_cast<const float4*>(p)[q];
+        out[4 * q + 0] = t.x; out[4 * q + 1] = t.y; out[4 * q + 2] = t.z; out[4 * q + 3] = t.w;
+    }
+#else
+    for (int q = 0; q < NB; ++q) out[q] = p[q];
+#endif
+}
+
+CTR_HD float ctr_coord(float p0j, float c1, float fi, float c2)
+{
+    return CTR_ADD(CTR_ADD(p0j, CTR_MUL(c1, fi)), c2);
+}
+
+// std::round (half away from zero), exact for every float (no v+0.5 double rounding).
+CTR_HD float ctr_round(float v)
+{
+    float r = rintf(v);          // nearest-even
+    float d = CTR_SUB(v, r);     // exact
+    if (d == 0.5f && v > 0.f) r += 1.f;
+    if (d == -0.5f && v < 0.f) r -= 1.f;
+    return r;
+}
+
+// Smallest i in [0,H] with sgn*coord(i) > bound (strict) or >= bound.  float32
+// rounding is monotone, so coord(i) is monotone in i and the predicate flips once.
+CTR_HD int ctr_search(float p0j, float c1, float c2, float sgn, float bound, bool strict, int H)
+{
+    int lo = 0, hi = H;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        float g = sgn * ctr_coord(p0j, c1, (float)mid, c2);
+        bool p = strict ? (g > bound) : (g >= bound);
+        if (p) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+// [ib, ie): the steps i of ray j whose sample lies strictly inside the footprint
+// (everything outside contributes exactly zero to the row sum).
+CTR_HD void ctr_ray_interval(const CtrRay& r, const CtrClassGeom& g, int j, int H, int& ib, int& ie)
+{
+    const float pu = CTR_MUL(r.u0, (float)j), pv = CTR_MUL(r.v0, (float)j);
+    const float su = (r.u1 >= 0.f) ? 1.f : -1.f;
+    const float sv = (r.v1 >= 0.f) ? 1.f : -1.f;
+    const int ib_u = ctr_search(pu, r.u1, r.u2, su, su > 0.f ? g.ulo : -g.uhi, true, H);
+    const int ie_u = ctr_search(pu, r.u1, r.u2, su, su > 0.f ? g.uhi : -g.ulo, false, H);
+    const int ib_v = ctr_search(pv, r.v1, r.v2, sv, sv > 0.f ? g.vlo : -g.vhi, true, H);
+    const int ie_v = ctr_search(pv, r.v1, r.v2, sv, sv > 0.f ? g.vhi : -g.vlo, false, H);
+    ib = ib_u > ib_v ? ib_u : ib_v;
+    ie = ie_u < ie_v ? ie_u : ie_v;
+    if (ie < ib) ie = ib;
+}
+
+// A ray in flight: next step, steps left, direction of travel (towards larger v).
+struct CtrRayState {
+    float pu, pv;  // u0*j, v0*j
+    int i, n, di;
+};
+
+CTR_HD void ctr_ray_begin(const CtrRay& r, const CtrClassGeom& g, int j, int H, CtrRayState& s)
+{
+    int ib, ie;
+    ctr_ray_interval(r, g, j, H, ib, ie);
+    s.pu = CTR_MUL(r.u0, (float)j);
+    s.pv = CTR_MUL(r.v0, (float)j);
+    s.n = ie - ib;
+    s.di = (r.v1 >= 0.f) ? 1 : -1;
+    s.i = (s.di > 0) ? ib : ie - 1;
+}
+
+// March one ray through one strip.  `strip` holds packed rows [row0p, row0p+rows)
+// as [row][Up][NB] floats; this call consumes every remaining sample whose key row
+// (floor(v) for bilinear, round(v) for nearest) is < vend.  Keys only grow along
+// the march, so successive strips partition the ray exactly.
+//   vend  = (float)(row0p + R + offv)   first key row that belongs to the next strip
+//   rbase = row0p + offv                key row of strip row 0
+template <int NB, int INTERP>
+CTR_HD void ctr_march(const float* __restrict__ strip, int Up, float vend, int rbase, int offu,
+                      const CtrRay& r, CtrRayState& s, float* __restrict__ acc)
+{
+    while (s.n > 0) {
+        const float fi = (float)s.i;
+        const float u = ctr_coord(s.pu, r.u1, fi, r.u2);
+        const float v = ctr_coord(s.pv, r.v1, fi, r.v2);
+        if (INTERP == CTR_NEAREST) {
+            const float kv = ctr_round(v);
+            if (kv >= vend) break;
+            const float ku = ctr_round(u);
+            float a[NB];
+            ctr_ldv<NB>(strip + ((size_t)((int)kv - rbase) * Up + ((int)ku - offu)) * NB, a);
+#pragma unroll
+            for (int q = 0; q < NB; ++q) acc[q] += a[q];
+        } else {
+            const float kv = floorf(v);
+            if (kv >= vend) break;
+            const float ku = floorf(u);
+            const float fu = CTR_SUB(u, ku), gu = CTR_SUB(CTR_ADD(ku, 1.f), u);
+            const float fv = CTR_SUB(v, kv), gv = CTR_SUB(CTR_ADD(kv, 1.f), v);
+            const float w00 = gv * gu, w01 = gv * fu, w10 = fv * gu, w11 = fv * fu;
+            const float* p0 = strip + ((size_t)((int)kv - rbase) * Up + ((int)ku - offu)) * NB;
+            const float* p1 = p0 + (size_t)Up * NB;
+            float a00[NB], a01[NB], a10[NB], a11[NB];
+            ctr_ldv<NB>(p0, a00); ctr_ldv<NB>(p0 + NB, a01);
+            ctr_ldv<NB>(p1, a10); ctr_ldv<NB>(p1 + NB, a11);
+#pragma unroll
+            for (int q = 0; q < NB; ++q)
+                acc[q] += w00 * a00[q] + w01 * a01[q] + w10 * a10[q] + w11 * a11[q];
+        }
+        s.i += s.di;
+        --s.n;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pixel-driven back-projections.  t[] is one row of the [A,8] transform table
+// (forward table for EXACT, inverted table for TF).  (px,py) are the pixel's frame
+// coordinates as floats.  ywin holds sinogram bins [jbase_p, jbase_p+wlen) of the
+// halo-padded row (packed bin index = j + 1; bins -1 and W are zero), NB images
+// interleaved: ywin[(jp - jbase_p)*NB + n].
+
+// First-order inverse of the forward rotation: which (j,i) lattice point samples closest to (px,py).
+CTR_HD void ctr_adj_centre(const float* t, float px, float py, float& uj, float& vi)
+{
+    const float dx = px - t[2], dy = py - t[5];
+    uj = t[0] * dx + t[3] * dy;
+    vi = t[1] * dx + t[4] * dy;
+}
+
+// Exact transpose of the forward operator (north_star: <Ax,y> == <x,A^T y>).
+// Every (j,i) whose sample can touch pixel (px,py) lies in the 3x3 lattice window
+// around round(M^-1 p) (rotated 2x2 footprint, half-diagonal 1.414 < 1.5); the
+// forward's float32 coordinates and tap weights are re-evaluated for each of them,
+// so a superset window is harmless (weight exactly 0).
+template <int NB, int INTERP>
+CTR_HD void ctr_adj_exact(const float* t, int H, int W, float px, float py,
+                          const float* __restrict__ ywin, int jbase_p, float* __restrict__ acc)
+{
+    float uj, vi;
+    ctr_adj_centre(t, px, py, uj, vi);
+    // clamp in float first: uj/vi can be far outside for pad=False corners
+    uj = fminf(fmaxf(uj, 0.f), (float)(W - 1));
+    vi = fminf(fmaxf(vi, 0.f), (float)(H - 1));
+    const int j0 = (int)rintf(uj), i0 = (int)rintf(vi);
+#pragma unroll
+    for (int dj = -1; dj <= 1; ++dj) {
+        const int j = j0 + dj;
+        const float fj = (float)j;
+        const float p0x = CTR_MUL(t[0], fj), p0y = CTR_MUL(t[3], fj);
+        float wsum = 0.f;
+#pragma unroll
+        for (int di = -1; di <= 1; ++di) {
+            const int i = i0 + di;
+            const float fi = (float)i;
+            const float x = ctr_coord(p0x, t[1], fi, t[2]);
+            const float y = ctr_coord(p0y, t[4], fi, t[5]);
+            float w;
+            if (INTERP == CTR_NEAREST) {
+                w = (ctr_round(x) == px && ctr_round(y) == py) ? 1.f : 0.f;
+            } else {
+                const float wx = fmaxf(0.f, CTR_SUB(1.f, fabsf(CTR_SUB(x, px))));
+                const float wy = fmaxf(0.f, CTR_SUB(1.f, fabsf(CTR_SUB(y, py))));
+                w = wx * wy;
+            }
+            if (i >= 0 && i < H) wsum += w;
+        }
+        float yv[NB];
+        ctr_ldv<NB>(ywin + (size_t)(j + 1 - jbase_p) * NB, yv);
+#pragma unroll
+        for (int q = 0; q < NB; ++q) acc[q] += wsum * yv[q];
+    }
+}
+
+// TensorFlow's registered gradient (ImageProjectiveTransformV3 applied to the
+// row-broadcast cotangent with the inverted transforms; main_ct_vae.py:471-481).
+template <int NB, int INTERP>
+CTR_HD void ctr_adj_tf(const float* ti, int H, int W, float px, float py,
+                       const float* __restrict__ ywin, int jbase_p, float* __restrict__ acc)
+{
+    const float x = CTR_ADD(CTR_ADD(CTR_MUL(ti[0], px), CTR_MUL(ti[1], py)), ti[2]);
+    const float y = CTR_ADD(CTR_ADD(CTR_MUL(ti[3], px), CTR_MUL(ti[4], py)), ti[5]);
+    if (INTERP == CTR_NEAREST) {
+        const float jj = ctr_round(x), ii = ctr_round(y);
+        if (ii >= 0.f && ii < (float)H && jj >= 0.f && jj < (float)W) {
+            const float* yp = ywin + (size_t)((int)jj + 1 - jbase_p) * NB;
+#pragma unroll
+            for (int q = 0; q < NB; ++q) acc[q] += yp[q];
+        }
+    } else {
+        const float xf = floorf(x), yf = floorf(y);
+        if (xf >= -1.f && xf <= (float)(W - 1)) {  // else both column taps are fill
+            const float wxf = CTR_SUB(CTR_ADD(xf, 1.f), x), wxc = CTR_SUB(x, xf);
+            const float wyf = (yf >= 0.f && yf < (float)H) ? CTR_SUB(CTR_ADD(yf, 1.f), y) : 0.f;
+            const float wyc = (yf >= -1.f && yf < (float)(H - 1)) ? CTR_SUB(y, yf) : 0.f;
+            const float* yp = ywin + (size_t)((int)xf + 1 - jbase_p) * NB;
+#pragma unroll
+            for (int q = 0; q < NB; ++q) {
+                const float vrow = CTR_ADD(CTR_MUL(wxf, yp[q]), CTR_MUL(wxc, yp[NB + q]));
+                acc[q] += CTR_ADD(CTR_MUL(wyf, vrow), CTR_MUL(wyc, vrow));
+            }
+        }
+    }
+}
+
+// Back-projection stage of iradon (ctvae/fbp_tensorflow.py:52-71): geometry in
+// float64 like the reference, interpolation weights applied in float32.
+//   cs[0]=cos(theta), cs[1]=sin(theta); xpr = row - x_size/2, ypr = col - y_size/2.
+// tfp's constant_extension clamps the fractional index to [0, P-1], so the halo
+// bins of the packed row (packed index = j + 1) are never read here.
+template <int NB>
+CTR_HD void ctr_adj_fbp(const double* cs, int P, double xpr, double ypr,
+                        const float* __restrict__ ywin, int jbase_p, float* __restrict__ acc)
+{
+    const double tt = ypr * cs[0] - xpr * cs[1];
+    double idx = tt + 0.5 * (double)P;   // (t - x_ref_min)/(x_ref_max - x_ref_min)*(P-1)
+    idx = fmin(fmax(idx, 0.0), (double)(P - 1));
+    double below = floor(idx);
+    double above = fmin(below + 1.0, (double)(P - 1));
+    below = fmax(above - 1.0, 0.0);
+    const float alpha = (float)(idx - below);
+    const float* yb = ywin + (size_t)((int)below + 1 - jbase_p) * NB;
+    const float* ya = ywin + (size_t)((int)above + 1 - jbase_p) * NB;
+#pragma unroll
+    for (int q = 0; q < NB; ++q) acc[q] += (1.f - alpha) * yb[q] + alpha * ya[q];
+}
+
+// Sinogram-bin window a pixel tile needs for one angle: packed start bin so that
+// [start, start+win) covers every bin any of the tile's pixels can touch.
+//   u(px,py) is linear, so its extremes over the tile sit at the 4 corners.
+CTR_HD int ctr_window_start(float ua, float ub, float uc, float ud, int Wp2, int win)
+{
+    float umin = fminf(fminf(ua, ub), fminf(uc, ud));
+    // keep the float->int conversion in range for far-out corners (pad=False)
+    umin = fminf(fmaxf(umin, -4.f), (float)Wp2);
+    int start = (int)floorf(umin) - 2 + 1;  // two bins of slack, +1: packed index
+    const int maxs = Wp2 - win;
+    if (start > maxs) start = maxs;
+    if (start < 0) start = 0;
+    return start;
+}

@@ -1,0 +1,168 @@
+// ctr_emu.cpp -- CPU emulation of the kernels' per-thread logic (tests only).
+//
+// Runs the SAME ctr_core.h / ctr_host.h code the sm_100a kernels run, with the CTA
+// structure (packed layouts, strips, angle chunks, pixel tiles, bin windows)
+// replayed by plain loops.  It exists so the geometry logic can be checked against
+// the oracle in this GPU-less container; it is not shipped, not imported by
+// ct_pvae_b200/, and is no fallback for anything.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../ct_pvae_b200/csrc/ctr_core.h"
+#include "../../ct_pvae_b200/csrc/ctr_host.h"
+
+namespace {
+
+constexpr int NB = 4;
+
+// [G][Vp][Up][NB] packs of both classes, zero halos (mirrors ctr_pack_image_kernel).
+void pack_images(const float* img, int B, int X, int Y, std::vector<float>& pk0, std::vector<float>& pk1)
+{
+    const int G = (B + NB - 1) / NB;
+    pk0.assign((size_t)G * (X + 2) * (Y + 2) * NB, 0.f);
+    pk1.assign((size_t)G * (Y + 2) * (X + 2) * NB, 0.f);
+    for (int b = 0; b < B; ++b) {
+        const int g = b / NB, n = b % NB;
+        for (int r = 0; r < X; ++r)
+            for (int c = 0; c < Y; ++c) {
+                const float v = img[((size_t)b * X + r) * Y + c];
+                pk0[(((size_t)g * (X + 2) + r + 1) * (Y + 2) + c + 1) * NB + n] = v;
+                pk1[(((size_t)g * (Y + 2) + c + 1) * (X + 2) + r + 1) * NB + n] = v;
+            }
+    }
+}
+
+// [G][A][W+2][NB] with zero halo bins (mirrors ctr_pack_sino_kernel).
+void pack_sino(const float* y, int B, int A, int W, std::vector<float>& spk)
+{
+    const int G = (B + NB - 1) / NB;
+    spk.assign((size_t)G * A * (W + 2) * NB, 0.f);
+    for (int b = 0; b < B; ++b)
+        for (int a = 0; a < A; ++a)
+            for (int j = 0; j < W; ++j)
+                spk[(((size_t)(b / NB) * A + a) * (W + 2) + j + 1) * NB + (b % NB)] = y[((size_t)b * A + a) * W + j];
+}
+
+template <int INTERP>
+void forward_impl(const float* img, int B, int X, int Y, int H, int W, int padx, int pady,
+                  const float* t, int A, int R, float* sino)
+{
+    std::vector<float> pk[2];
+    pack_images(img, B, X, Y, pk[0], pk[1]);
+    CtrClassGeom geom[2];
+    ctr_h_class_geom(X, Y, padx, pady, geom);
+    std::vector<CtrRay> rays;
+    int n0 = 0;
+    ctr_h_build_rays(t, A, rays, n0);
+    const int G = (B + NB - 1) / NB;
+    for (int g = 0; g < G; ++g) {
+        for (size_t ri = 0; ri < rays.size(); ++ri) {
+            const CtrRay& r = rays[ri];
+            const CtrClassGeom& cg = geom[r.cls];
+            const float* pkg = pk[r.cls].data() + (size_t)g * cg.Vp * cg.Up * NB;
+            const int K = (cg.Vp + R - 1) / R;
+            for (int j = 0; j < W; ++j) {
+                CtrRayState s;
+                ctr_ray_begin(r, cg, j, H, s);
+                float acc[NB] = {0, 0, 0, 0};
+                for (int k = 0; k < K; ++k) {
+                    // the strip buffer the TMA bulk copy would have filled: rows [kR, kR+R+1)
+                    const int rows = std::min(R + 1, cg.Vp - k * R);
+                    std::vector<float> strip((size_t)(R + 1) * cg.Up * NB, -1e30f);  // poison what is not loaded
+                    std::memcpy(strip.data(), pkg + (size_t)k * R * cg.Up * NB, sizeof(float) * rows * cg.Up * NB);
+                    ctr_march<NB, INTERP>(strip.data(), cg.Up, (float)((k + 1) * R + cg.offv), k * R + cg.offv,
+                                          cg.offu, r, s, acc);
+                }
+                for (int n = 0; n < NB; ++n) {
+                    const int b = g * NB + n;
+                    if (b < B) sino[((size_t)b * A + r.angle) * W + j] = acc[n];
+                }
+            }
+        }
+    }
+}
+
+template <int MODE, int INTERP>
+void adjoint_impl(const float* y, int B, int X, int Y, int H, int W, int padx, int pady,
+                  const float* table, int A, int TW, int TH, int win, float* out)
+{
+    std::vector<float> spk;
+    pack_sino(y, B, A, W, spk);
+    const int G = (B + NB - 1) / NB;
+    const int Wp2 = W + 2;
+    const int winc = std::min(win, Wp2);
+    for (int g = 0; g < G; ++g)
+        for (int r0 = 0; r0 < X; r0 += TH)
+            for (int c0 = 0; c0 < Y; c0 += TW) {
+                std::vector<float> acc((size_t)TW * TH * NB, 0.f);
+                for (int a = 0; a < A; ++a) {
+                    const float* t = table + 8 * a;
+                    // producer lane: window start from the 4 tile corners
+                    float cu[4];
+                    int q = 0;
+                    for (int cy = 0; cy < 2; ++cy)
+                        for (int cx = 0; cx < 2; ++cx) {
+                            const float px = (float)(c0 + cx * (TW - 1) + pady), py = (float)(r0 + cy * (TH - 1) + padx);
+                            float uj, vi;
+                            if (MODE == CTR_ADJ_EXACT) ctr_adj_centre(t, px, py, uj, vi);
+                            else uj = CTR_ADD(CTR_ADD(CTR_MUL(t[0], px), CTR_MUL(t[1], py)), t[2]);
+                            cu[q++] = uj;
+                        }
+                    const int start = ctr_window_start(cu[0], cu[1], cu[2], cu[3], Wp2, winc);
+                    // NaN guard zones either side: an out-of-window read poisons the output
+                    constexpr int GUARD = 16;
+                    std::vector<float> ywin_buf((size_t)(winc + 2 * GUARD) * NB, std::nanf(""));
+                    float* ywin_p = ywin_buf.data() + (size_t)GUARD * NB;
+                    std::memcpy(ywin_p, spk.data() + (((size_t)g * A + a) * Wp2 + start) * NB,
+                                sizeof(float) * winc * NB);
+                    for (int ty = 0; ty < TH; ++ty)
+                        for (int tx = 0; tx < TW; ++tx) {
+                            const float px = (float)(c0 + tx + pady), py = (float)(r0 + ty + padx);
+                            float* ac = &acc[((size_t)ty * TW + tx) * NB];
+                            if (MODE == CTR_ADJ_EXACT) ctr_adj_exact<NB, INTERP>(t, H, W, px, py, ywin_p, start, ac);
+                            else ctr_adj_tf<NB, INTERP>(t, H, W, px, py, ywin_p, start, ac);
+                        }
+                }
+                for (int ty = 0; ty < TH; ++ty)
+                    for (int tx = 0; tx < TW; ++tx) {
+                        const int r = r0 + ty, c = c0 + tx;
+                        if (r >= X || c >= Y) continue;
+                        for (int n = 0; n < NB; ++n) {
+                            const int b = g * NB + n;
+                            if (b < B) out[((size_t)b * X + r) * Y + c] = acc[((size_t)ty * TW + tx) * NB + n];
+                        }
+                    }
+            }
+}
+
+}  // namespace
+
+extern "C" {
+
+void emu_make_transforms(const double* theta, int A, int H, int W, float* t) { ctr_h_make_transforms(theta, A, H, W, t); }
+void emu_invert_transforms(const float* t, int A, float* o) { ctr_h_invert_transforms(t, A, o); }
+int emu_num_proj_pix(int X, int Y) { return ctr_h_num_proj_pix(X, Y); }
+
+void emu_forward(const float* img, int B, int X, int Y, int H, int W, int padx, int pady, const float* t, int A,
+                 int interp, int R, float* sino)
+{
+    if (interp == CTR_NEAREST) forward_impl<CTR_NEAREST>(img, B, X, Y, H, W, padx, pady, t, A, R, sino);
+    else forward_impl<CTR_BILINEAR>(img, B, X, Y, H, W, padx, pady, t, A, R, sino);
+}
+
+// mode 0: exact (table = forward transforms); mode 1: tf-compat (table = inverted transforms)
+void emu_adjoint(const float* y, int B, int X, int Y, int H, int W, int padx, int pady, const float* table, int A,
+                 int interp, int mode, int TW, int TH, int win, float* out)
+{
+    if (mode == CTR_ADJ_EXACT) {
+        if (interp == CTR_NEAREST) adjoint_impl<CTR_ADJ_EXACT, CTR_NEAREST>(y, B, X, Y, H, W, padx, pady, table, A, TW, TH, win, out);
+        else adjoint_impl<CTR_ADJ_EXACT, CTR_BILINEAR>(y, B, X, Y, H, W, padx, pady, table, A, TW, TH, win, out);
+    } else {
+        if (interp == CTR_NEAREST) adjoint_impl<CTR_ADJ_TF, CTR_NEAREST>(y, B, X, Y, H, W, padx, pady, table, A, TW, TH, win, out);
+        else adjoint_impl<CTR_ADJ_TF, CTR_BILINEAR>(y, B, X, Y, H, W, padx, pady, table, A, TW, TH, win, out);
+    }
+}
+
+}  // extern "C"

@@ -1,0 +1,456 @@
+// ctr_capi.cu -- the C ABI declared in include/ctradon.h: plans, argument checks,
+// workspace carving and kernel launches.  No torch, no Python, no CPU compute path.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/ctradon.h"
+#include "ctr_core.h"
+#include "ctr_host.h"
+#include "ctr_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg)
+{
+    g_err = msg;
+    return code;
+}
+int fail_cuda(cudaError_t e, const char* what)
+{
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return CTR_ECUDA;
+}
+#define CTR_CUDA(call)                                   \
+    do {                                                 \
+        cudaError_t e__ = (call);                        \
+        if (e__ != cudaSuccess) return fail_cuda(e__, #call); \
+    } while (0)
+
+// switch to the plan's device for the duration of a call
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int dev)
+    {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev);
+        ok = (err == cudaSuccess);
+    }
+    ~DeviceGuard()
+    {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+struct ctr_plan {
+    int device = 0;
+    int A = 0, X = 0, Y = 0, pad = 0, H = 0, W = 0, padx = 0, pady = 0;
+    std::vector<float> t, tinv;
+    std::vector<CtrRay> rays;
+    int n_cls[2] = {0, 0};
+    CtrClassGeom geom[2];
+    ctr::FwdConfig fc;
+    int bp_win = 0;
+    float* d_t = nullptr;
+    float* d_tinv = nullptr;
+    CtrRay* d_rays = nullptr;
+};
+
+struct ctr_fbp_plan {
+    int device = 0;
+    int A = 0, P = 0, x_size = 0, y_size = 0;
+    int bp_win = 0;
+    double* d_cs = nullptr;   // [A][2]
+    float* d_h = nullptr;     // [P] spatial kernel
+};
+
+extern "C" {
+
+int ctr_version(void) { return CTR_VERSION; }
+const char* ctr_last_error(void) { return g_err.c_str(); }
+long long ctr_launch_count(void) { return ctr::launch_counter().load(); }
+
+int ctr_num_proj_pix(int X, int Y) { return (X > 0 && Y > 0) ? ctr_h_num_proj_pix(X, Y) : fail(CTR_EINVAL, "X, Y must be positive"); }
+
+int ctr_frame(int X, int Y, int pad, int* H, int* W, int* padx, int* pady)
+{
+    if (X <= 0 || Y <= 0) return fail(CTR_EINVAL, "X, Y must be positive");
+    int h, w, px, py;
+    ctr_h_frame(X, Y, pad, h, w, px, py);
+    if (H) *H = h;
+    if (W) *W = w;
+    if (padx) *padx = px;
+    if (pady) *pady = py;
+    return CTR_OK;
+}
+
+int ctr_make_transforms(const double* theta, int A, int H, int W, float* out)
+{
+    if (!theta || !out || A < 0 || H <= 0 || W <= 0) return fail(CTR_EINVAL, "ctr_make_transforms: bad argument");
+    ctr_h_make_transforms(theta, A, H, W, out);
+    return CTR_OK;
+}
+
+int ctr_invert_transforms(const float* t, int A, float* out)
+{
+    if (!t || !out || A < 0) return fail(CTR_EINVAL, "ctr_invert_transforms: bad argument");
+    ctr_h_invert_transforms(t, A, out);
+    return CTR_OK;
+}
+
+int ctr_filter_to_spatial(const double* fr, const double* fi, int P, double* out)
+{
+    if (!fr || !out || P <= 0) return fail(CTR_EINVAL, "ctr_filter_to_spatial: bad argument");
+    // real part of the inverse DFT, O(P^2) in float64 (P is a detector width)
+    const double w = 2.0 * M_PI / (double)P;
+    for (int n = 0; n < P; ++n) {
+        double acc = 0.0;
+        for (int k = 0; k < P; ++k) {
+            const double ph = w * (double)(((long long)n * k) % P);
+            acc += fr[k] * std::cos(ph) - (fi ? fi[k] * std::sin(ph) : 0.0);
+        }
+        out[n] = acc / (double)P;
+    }
+    return CTR_OK;
+}
+
+// ------------------------------------------------------------------------------------------ plans
+int ctr_plan_create(const double* theta, int A, int X, int Y, int pad, int device, ctr_plan** out)
+{
+    if (!out) return fail(CTR_EINVAL, "ctr_plan_create: out is NULL");
+    *out = nullptr;
+    if (!theta || A <= 0 || X <= 0 || Y <= 0) return fail(CTR_EINVAL, "ctr_plan_create: need theta, A>0, X>0, Y>0");
+    if ((long long)X * Y > (1ll << 28)) return fail(CTR_EUNSUPPORTED, "ctr_plan_create: image too large");
+    ctr_plan* p = new (std::nothrow) ctr_plan();
+    if (!p) return fail(CTR_EINVAL, "ctr_plan_create: out of host memory");
+    p->device = device; p->A = A; p->X = X; p->Y = Y; p->pad = pad ? 1 : 0;
+    ctr_h_frame(X, Y, p->pad, p->H, p->W, p->padx, p->pady);
+    p->t.resize((size_t)A * 8);
+    p->tinv.resize((size_t)A * 8);
+    ctr_h_make_transforms(theta, A, p->H, p->W, p->t.data());
+    ctr_h_invert_transforms(p->t.data(), A, p->tinv.data());
+    ctr_h_class_geom(X, Y, p->padx, p->pady, p->geom);
+    ctr_h_build_rays(p->t.data(), A, p->rays, p->n_cls[0]);
+    p->n_cls[1] = A - p->n_cls[0];
+    p->bp_win = std::min(ctr::kBpWin, p->W + 2);
+
+    DeviceGuard guard(device);
+    if (!guard.ok) { int rc = fail_cuda(guard.err, "cudaSetDevice"); delete p; return rc; }
+    int smem_optin = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    if (e != cudaSuccess) { int rc = fail_cuda(e, "cudaDeviceGetAttribute"); delete p; return rc; }
+    p->fc = ctr::fwd_config(p->W, p->geom, smem_optin - 2048);
+    if (p->fc.R < 1) { delete p; return fail(CTR_EUNSUPPORTED, "ctr_plan_create: image rows too wide for the shared-memory strips"); }
+    const size_t tb = (size_t)A * 8 * sizeof(float);
+    if ((e = cudaMalloc(&p->d_t, tb)) != cudaSuccess || (e = cudaMalloc(&p->d_tinv, tb)) != cudaSuccess ||
+        (e = cudaMalloc(&p->d_rays, (size_t)A * sizeof(CtrRay))) != cudaSuccess ||
+        (e = cudaMemcpy(p->d_t, p->t.data(), tb, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(p->d_tinv, p->tinv.data(), tb, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(p->d_rays, p->rays.data(), (size_t)A * sizeof(CtrRay), cudaMemcpyHostToDevice)) != cudaSuccess) {
+        int rc = fail_cuda(e, "ctr_plan_create: table upload");
+        cudaFree(p->d_t); cudaFree(p->d_tinv); cudaFree(p->d_rays);
+        delete p;
+        return rc;
+    }
+    *out = p;
+    return CTR_OK;
+}
+
+int ctr_plan_destroy(ctr_plan* p)
+{
+    if (!p) return CTR_OK;
+    DeviceGuard guard(p->device);
+    cudaFree(p->d_t); cudaFree(p->d_tinv); cudaFree(p->d_rays);
+    delete p;
+    return CTR_OK;
+}
+
+int ctr_plan_info(const ctr_plan* p, int* A, int* X, int* Y, int* H, int* W, int* padx, int* pady)
+{
+    if (!p) return fail(CTR_EINVAL, "ctr_plan_info: plan is NULL");
+    if (A) *A = p->A;
+    if (X) *X = p->X;
+    if (Y) *Y = p->Y;
+    if (H) *H = p->H;
+    if (W) *W = p->W;
+    if (padx) *padx = p->padx;
+    if (pady) *pady = p->pady;
+    return CTR_OK;
+}
+
+int ctr_plan_tables(const ctr_plan* p, float* fwd, float* inv)
+{
+    if (!p) return fail(CTR_EINVAL, "ctr_plan_tables: plan is NULL");
+    if (fwd) std::memcpy(fwd, p->t.data(), p->t.size() * sizeof(float));
+    if (inv) std::memcpy(inv, p->tinv.data(), p->tinv.size() * sizeof(float));
+    return CTR_OK;
+}
+
+static size_t pack_bytes(const ctr_plan* p, int B)
+{
+    const size_t G = (size_t)(B + ctr::kFwdNB - 1) / ctr::kFwdNB;
+    return align_up(G * (size_t)(p->X + 2) * (size_t)(p->Y + 2) * ctr::kFwdNB * sizeof(float), 256);
+}
+
+size_t ctr_forward_workspace_bytes(const ctr_plan* p, int B)
+{
+    if (!p || B <= 0) return 0;
+    return 2 * pack_bytes(p, B);
+}
+
+static size_t spk_bytes(int B, int A, int W)
+{
+    const size_t G = (size_t)(B + ctr::kBpNB - 1) / ctr::kBpNB;
+    return align_up(G * (size_t)A * (size_t)(W + 2) * ctr::kBpNB * sizeof(float), 256);
+}
+
+size_t ctr_adjoint_workspace_bytes(const ctr_plan* p, int B)
+{
+    if (!p || B <= 0) return 0;
+    return spk_bytes(B, p->A, p->W);
+}
+
+// ------------------------------------------------------------------------------------------ forward
+int ctr_radon_forward(const ctr_plan* p, const float* img, float* sino, int B, int interp, void* ws, size_t ws_bytes,
+                      void* stream)
+{
+    if (!p || !img || !sino) return fail(CTR_EINVAL, "ctr_radon_forward: NULL plan or buffer");
+    if (B <= 0) return fail(CTR_EINVAL, "ctr_radon_forward: B must be positive");
+    if (interp != CTR_INTERP_NEAREST && interp != CTR_INTERP_BILINEAR) return fail(CTR_EINVAL, "ctr_radon_forward: bad interp");
+    if (!ws || ws_bytes < ctr_forward_workspace_bytes(p, B)) return fail(CTR_EWORKSPACE, "ctr_radon_forward: workspace too small");
+    if (((uintptr_t)ws & 255) != 0) return fail(CTR_EINVAL, "ctr_radon_forward: workspace must be 256-byte aligned");
+    DeviceGuard guard(p->device);
+    if (!guard.ok) return fail_cuda(guard.err, "cudaSetDevice");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int G = (B + ctr::kFwdNB - 1) / ctr::kFwdNB;
+    float* pk0 = p->n_cls[0] ? (float*)ws : nullptr;
+    float* pk1 = p->n_cls[1] ? (float*)((char*)ws + pack_bytes(p, B)) : nullptr;
+    {
+        dim3 grid((p->Y + 2 + 31) / 32, (p->X + 2 + 31) / 32, G), block(32, 8);
+        ctr::ctr_pack_image_kernel<ctr::kFwdNB><<<grid, block, 0, st>>>(img, B, p->X, p->Y, pk0, pk1);
+        ctr::launch_counter()++;
+        CTR_CUDA(cudaGetLastError());
+    }
+    ctr::FwdParams fp;
+    fp.pk[0] = pk0; fp.pk[1] = pk1;
+    fp.geom[0] = p->geom[0]; fp.geom[1] = p->geom[1];
+    fp.rays = p->d_rays;
+    fp.n_cls[0] = p->n_cls[0]; fp.n_cls[1] = p->n_cls[1];
+    const int NA = p->fc.NS * p->fc.KA;
+    fp.chunks0 = (p->n_cls[0] + NA - 1) / NA;
+    const int chunks = fp.chunks0 + (p->n_cls[1] + NA - 1) / NA;
+    fp.H = p->H; fp.W = p->W; fp.A = p->A; fp.B = B;
+    fp.R = p->fc.R;
+    fp.sino = sino;
+    cudaError_t e = (interp == CTR_INTERP_NEAREST) ? ctr::launch_fwd_ka<CTR_NEAREST>(fp, p->fc, G, chunks, st)
+                                                   : ctr::launch_fwd_ka<CTR_BILINEAR>(fp, p->fc, G, chunks, st);
+    if (e != cudaSuccess) return fail_cuda(e, "ctr_fwd_kernel launch");
+    return CTR_OK;
+}
+
+// ------------------------------------------------------------------------------------------ adjoint
+int ctr_radon_adjoint(const ctr_plan* p, const float* dsino, float* dimg, int B, int interp, int mode, void* ws,
+                      size_t ws_bytes, void* stream)
+{
+    if (!p || !dsino || !dimg) return fail(CTR_EINVAL, "ctr_radon_adjoint: NULL plan or buffer");
+    if (B <= 0) return fail(CTR_EINVAL, "ctr_radon_adjoint: B must be positive");
+    if (interp != CTR_INTERP_NEAREST && interp != CTR_INTERP_BILINEAR) return fail(CTR_EINVAL, "ctr_radon_adjoint: bad interp");
+    if (mode != CTR_ADJOINT_EXACT && mode != CTR_ADJOINT_TF_COMPAT) return fail(CTR_EINVAL, "ctr_radon_adjoint: bad mode");
+    if (!ws || ws_bytes < ctr_adjoint_workspace_bytes(p, B)) return fail(CTR_EWORKSPACE, "ctr_radon_adjoint: workspace too small");
+    if (((uintptr_t)ws & 255) != 0) return fail(CTR_EINVAL, "ctr_radon_adjoint: workspace must be 256-byte aligned");
+    DeviceGuard guard(p->device);
+    if (!guard.ok) return fail_cuda(guard.err, "cudaSetDevice");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int G = (B + ctr::kBpNB - 1) / ctr::kBpNB;
+    float* spk = (float*)ws;
+    {
+        dim3 grid((p->W + 2 + 127) / 128, p->A, G), block(128);
+        ctr::ctr_pack_sino_kernel<ctr::kBpNB><<<grid, block, 0, st>>>(dsino, B, p->A, p->W, spk);
+        ctr::launch_counter()++;
+        CTR_CUDA(cudaGetLastError());
+    }
+    ctr::BpParams bp;
+    bp.spk = spk;
+    bp.table = (mode == CTR_ADJOINT_EXACT) ? p->d_t : p->d_tinv;
+    bp.cs = nullptr;
+    bp.out = dimg;
+    bp.B = B; bp.A = p->A; bp.X = p->X; bp.Y = p->Y; bp.H = p->H; bp.W = p->W; bp.padx = p->padx; bp.pady = p->pady;
+    bp.win = p->bp_win;
+    bp.scale = 1.f;
+    cudaError_t e;
+    if (mode == CTR_ADJOINT_EXACT)
+        e = (interp == CTR_INTERP_NEAREST) ? ctr::launch_bp<CTR_ADJ_EXACT, CTR_NEAREST>(bp, st)
+                                           : ctr::launch_bp<CTR_ADJ_EXACT, CTR_BILINEAR>(bp, st);
+    else
+        e = (interp == CTR_INTERP_NEAREST) ? ctr::launch_bp<CTR_ADJ_TF, CTR_NEAREST>(bp, st)
+                                           : ctr::launch_bp<CTR_ADJ_TF, CTR_BILINEAR>(bp, st);
+    if (e != cudaSuccess) return fail_cuda(e, "ctr_bp_kernel launch");
+    return CTR_OK;
+}
+
+// ------------------------------------------------------------------------------------------ FBP
+int ctr_fbp_plan_create(const double* theta, int A, int P, int x_size, int y_size, const double* fr, const double* fi,
+                        int device, ctr_fbp_plan** out)
+{
+    if (!out) return fail(CTR_EINVAL, "ctr_fbp_plan_create: out is NULL");
+    *out = nullptr;
+    if (!theta || !fr || A <= 0 || P <= 0 || x_size <= 0 || y_size <= 0)
+        return fail(CTR_EINVAL, "ctr_fbp_plan_create: bad argument");
+    if ((size_t)P * (ctr::kBpNB + 2) * 4 > 200 * 1024) return fail(CTR_EUNSUPPORTED, "ctr_fbp_plan_create: P too large for the smem filter");
+    ctr_fbp_plan* p = new (std::nothrow) ctr_fbp_plan();
+    if (!p) return fail(CTR_EINVAL, "ctr_fbp_plan_create: out of host memory");
+    p->device = device; p->A = A; p->P = P; p->x_size = x_size; p->y_size = y_size;
+    p->bp_win = std::min(ctr::kBpWin, P + 2);
+    std::vector<double> cs((size_t)A * 2), hd(P);
+    for (int a = 0; a < A; ++a) { cs[2 * a] = std::cos(theta[a]); cs[2 * a + 1] = std::sin(theta[a]); }
+    ctr_filter_to_spatial(fr, fi, P, hd.data());
+    std::vector<float> hf(P);
+    for (int k = 0; k < P; ++k) hf[k] = (float)hd[k];
+    DeviceGuard guard(device);
+    if (!guard.ok) { int rc = fail_cuda(guard.err, "cudaSetDevice"); delete p; return rc; }
+    cudaError_t e;
+    if ((e = cudaMalloc(&p->d_cs, cs.size() * sizeof(double))) != cudaSuccess ||
+        (e = cudaMalloc(&p->d_h, hf.size() * sizeof(float))) != cudaSuccess ||
+        (e = cudaMemcpy(p->d_cs, cs.data(), cs.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(p->d_h, hf.data(), hf.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess) {
+        int rc = fail_cuda(e, "ctr_fbp_plan_create: table upload");
+        cudaFree(p->d_cs); cudaFree(p->d_h);
+        delete p;
+        return rc;
+    }
+    *out = p;
+    return CTR_OK;
+}
+
+int ctr_fbp_plan_destroy(ctr_fbp_plan* p)
+{
+    if (!p) return CTR_OK;
+    DeviceGuard guard(p->device);
+    cudaFree(p->d_cs); cudaFree(p->d_h);
+    delete p;
+    return CTR_OK;
+}
+
+size_t ctr_fbp_workspace_bytes(const ctr_fbp_plan* p, int B)
+{
+    if (!p || B <= 0) return 0;
+    return spk_bytes(B, p->A, p->P);
+}
+
+int ctr_fbp(const ctr_fbp_plan* p, const float* sino, int A, float* recon, int B, void* ws, size_t ws_bytes, void* stream)
+{
+    if (!p || !sino || !recon) return fail(CTR_EINVAL, "ctr_fbp: NULL plan or buffer");
+    if (A != p->A)
+        return fail(CTR_EINVAL, "The given ``theta`` does not match the number of projections in ``radon_image``.");
+    if (B <= 0) return fail(CTR_EINVAL, "ctr_fbp: B must be positive");
+    if (!ws || ws_bytes < ctr_fbp_workspace_bytes(p, B)) return fail(CTR_EWORKSPACE, "ctr_fbp: workspace too small");
+    if (((uintptr_t)ws & 255) != 0) return fail(CTR_EINVAL, "ctr_fbp: workspace must be 256-byte aligned");
+    DeviceGuard guard(p->device);
+    if (!guard.ok) return fail_cuda(guard.err, "cudaSetDevice");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int G = (B + ctr::kBpNB - 1) / ctr::kBpNB;
+    float* spk = (float*)ws;
+    {
+        const size_t smem = (size_t)p->P * (ctr::kBpNB + 2) * sizeof(float);
+        CTR_CUDA(cudaFuncSetAttribute(ctr::ctr_fbp_filter_kernel<ctr::kBpNB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid(p->A, G), block(256);
+        ctr::ctr_fbp_filter_kernel<ctr::kBpNB><<<grid, block, smem, st>>>(sino, p->d_h, B, p->A, p->P, spk);
+        ctr::launch_counter()++;
+        CTR_CUDA(cudaGetLastError());
+    }
+    ctr::BpParams bp;
+    bp.spk = spk; bp.table = nullptr; bp.cs = p->d_cs; bp.out = recon;
+    bp.B = B; bp.A = p->A; bp.X = p->x_size; bp.Y = p->y_size; bp.H = p->P; bp.W = p->P; bp.padx = 0; bp.pady = 0;
+    bp.win = p->bp_win;
+    bp.scale = (float)(M_PI / (2.0 * (double)p->A));
+    cudaError_t e = ctr::launch_bp<CTR_ADJ_FBP, CTR_BILINEAR>(bp, st);
+    if (e != cudaSuccess) return fail_cuda(e, "ctr_bp_kernel<FBP> launch");
+    return CTR_OK;
+}
+
+// ------------------------------------------------------------------------------------------ DLPack
+static int dl_check(const DLTensor* t, const char* name, int min_ndim, int max_ndim, int device)
+{
+    if (!t || !t->data) return fail(CTR_EINVAL, std::string(name) + ": NULL tensor");
+    if (t->device.device_type != kDLCUDA) return fail(CTR_EINVAL, std::string(name) + ": not a CUDA tensor (there is no CPU path)");
+    if (t->device.device_id != device) return fail(CTR_EINVAL, std::string(name) + ": tensor is on a different device than the plan");
+    if (t->ndim < min_ndim || t->ndim > max_ndim) return fail(CTR_EINVAL, std::string(name) + ": wrong rank");
+    if (t->strides) {
+        int64_t expect = 1;
+        for (int d = t->ndim - 1; d >= 0; --d) {
+            if (t->shape[d] != 1 && t->strides[d] != expect) return fail(CTR_EINVAL, std::string(name) + ": not compact row-major");
+            expect *= t->shape[d];
+        }
+    }
+    return CTR_OK;
+}
+static int dl_check_f32(const DLTensor* t, const char* name, int device)
+{
+    int rc = dl_check(t, name, 3, 4, device);
+    if (rc) return rc;
+    if (t->dtype.code != kDLFloat || t->dtype.bits != 32 || t->dtype.lanes != 1) return fail(CTR_EINVAL, std::string(name) + ": dtype must be float32");
+    if (t->ndim == 4 && t->shape[3] != 1) return fail(CTR_EINVAL, std::string(name) + ": trailing channel axis must have size 1");
+    return CTR_OK;
+}
+static void* dl_ptr(const DLTensor* t) { return (char*)t->data + t->byte_offset; }
+static size_t dl_bytes(const DLTensor* t)
+{
+    size_t n = 1;
+    for (int d = 0; d < t->ndim; ++d) n *= (size_t)t->shape[d];
+    return n * (size_t)((t->dtype.bits * t->dtype.lanes + 7) / 8);
+}
+
+int ctr_radon_forward_dl(const ctr_plan* p, const DLTensor* img, DLTensor* sino, int interp, DLTensor* ws, void* stream)
+{
+    if (!p) return fail(CTR_EINVAL, "ctr_radon_forward_dl: plan is NULL");
+    int rc;
+    if ((rc = dl_check_f32(img, "img", p->device)) || (rc = dl_check_f32(sino, "sino", p->device)) ||
+        (rc = dl_check(ws, "workspace", 1, 8, p->device)))
+        return rc;
+    const int64_t B = img->shape[0];
+    if (img->shape[1] != p->X || img->shape[2] != p->Y) return fail(CTR_EINVAL, "img: shape does not match the plan's X, Y");
+    if (sino->shape[0] != B || sino->shape[1] != p->A || sino->shape[2] != p->W) return fail(CTR_EINVAL, "sino: expected [B, A, W]");
+    return ctr_radon_forward(p, (const float*)dl_ptr(img), (float*)dl_ptr(sino), (int)B, interp, dl_ptr(ws), dl_bytes(ws), stream);
+}
+
+int ctr_radon_adjoint_dl(const ctr_plan* p, const DLTensor* dsino, DLTensor* dimg, int interp, int mode, DLTensor* ws, void* stream)
+{
+    if (!p) return fail(CTR_EINVAL, "ctr_radon_adjoint_dl: plan is NULL");
+    int rc;
+    if ((rc = dl_check_f32(dsino, "dsino", p->device)) || (rc = dl_check_f32(dimg, "dimg", p->device)) ||
+        (rc = dl_check(ws, "workspace", 1, 8, p->device)))
+        return rc;
+    const int64_t B = dsino->shape[0];
+    if (dsino->shape[1] != p->A || dsino->shape[2] != p->W) return fail(CTR_EINVAL, "dsino: expected [B, A, W]");
+    if (dimg->shape[0] != B || dimg->shape[1] != p->X || dimg->shape[2] != p->Y) return fail(CTR_EINVAL, "dimg: expected [B, X, Y]");
+    return ctr_radon_adjoint(p, (const float*)dl_ptr(dsino), (float*)dl_ptr(dimg), (int)B, interp, mode, dl_ptr(ws), dl_bytes(ws), stream);
+}
+
+int ctr_fbp_dl(const ctr_fbp_plan* p, const DLTensor* sino, DLTensor* recon, DLTensor* ws, void* stream)
+{
+    if (!p) return fail(CTR_EINVAL, "ctr_fbp_dl: plan is NULL");
+    int rc;
+    if ((rc = dl_check_f32(sino, "sinogram", p->device)) || (rc = dl_check_f32(recon, "recon", p->device)) ||
+        (rc = dl_check(ws, "workspace", 1, 8, p->device)))
+        return rc;
+    const int64_t B = sino->shape[0];
+    if (sino->shape[2] != p->P) return fail(CTR_EINVAL, "sinogram: last axis must be num_proj_pix");
+    if (recon->shape[0] != B || recon->shape[1] != p->x_size || recon->shape[2] != p->y_size) return fail(CTR_EINVAL, "recon: expected [B, x_size, y_size]");
+    return ctr_fbp(p, (const float*)dl_ptr(sino), (int)sino->shape[1], (float*)dl_ptr(recon), (int)B, dl_ptr(ws), dl_bytes(ws), stream);
+}
+
+}  // extern "C"

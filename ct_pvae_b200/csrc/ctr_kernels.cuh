@@ -1,0 +1,518 @@
+// ctr_kernels.cuh -- sm_100a kernels of the Radon path and their launchers.
+//
+//   K0  ctr_pack_image_kernel   [B,X,Y] -> batch-interleaved, halo-padded packs (row-major + transposed)
+//   K0' ctr_pack_sino_kernel    [B,A,W] -> [G,A,W+2,NB] interleaved sinogram rows with zero halo bins
+//   K1  ctr_fwd_kernel          ray-driven forward projector (project_tf_fast / project_tf_low_mem,
+//                               /root/reference/ctvae/forward_functions.py:80-123, :49-78)
+//   K2  ctr_bp_kernel<EXACT>    pixel-driven gather adjoint, the exact transpose of K1 (no atomics)
+//   K2' ctr_bp_kernel<TF>       TensorFlow's registered gradient of the projector graph
+//   K3a ctr_fbp_filter_kernel   circular row filter in shared memory (fbp_tensorflow.py:49-50)
+//   K3b ctr_bp_kernel<FBP>      linear-interpolating back-projection of iradon (fbp_tensorflow.py:52-74)
+//
+// Data movement: image strips (K1) and sinogram bin windows (K2/K3b) are staged in
+// shared memory by the TMA engine with 1-D bulk copies (cp.async.bulk, SASS UBLKCP)
+// completing on mbarriers, double buffered.  The packs exist so that every staged
+// block is ONE contiguous, 16-byte aligned range in HBM and so that one 128-bit
+// shared-memory load serves 4 images: the per-sample geometry (coordinates, floor,
+// weights, address) is computed once per NB images.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+
+#include "ctr_core.h"
+
+// ------------------------------------------------------------------------------------------ PTX glue
+namespace ctr {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+// make mbarrier.init visible to the async proxy (TMA) before the first copy is issued
+__device__ __forceinline__ void fence_barrier_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// 1-D TMA bulk copy global -> shared, completion bytes counted on `bar`.
+// dst/src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+inline std::atomic<long long>& launch_counter()
+{
+    static std::atomic<long long> c{0};
+    return c;
+}
+
+constexpr int kFwdNB = 4;   // images interleaved per forward CTA (one LDS.128 per tap)
+constexpr int kBpNB = 8;    // images interleaved per back-projection CTA
+constexpr int kBpTW = 32, kBpTH = 16, kBpAB = 8, kBpWin = 44;
+constexpr int kFwdMaxThreads = 768;
+
+__host__ __device__ static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// ------------------------------------------------------------------------------------------ K0 packs
+// grid (ceil((Y+2)/32), ceil((X+2)/32), G), block (32, 8).  Reads are coalesced along
+// image rows; both packs are written with 16-byte-per-lane coalesced stores, the
+// transposed one through a padded shared-memory tile.
+template <int NB>
+__global__ void __launch_bounds__(256) ctr_pack_image_kernel(const float* __restrict__ img, int B, int X, int Y,
+                                                             float* __restrict__ pk0, float* __restrict__ pk1)
+{
+    __shared__ float tile[NB][32][33];
+    const int g = blockIdx.z;
+    const int pr0 = blockIdx.y * 32, pc0 = blockIdx.x * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+#pragma unroll
+    for (int n = 0; n < NB; ++n) {
+        const int b = g * NB + n;
+        for (int rr = ty; rr < 32; rr += 8) {
+            const int r = pr0 + rr - 1, c = pc0 + tx - 1;
+            float v = 0.f;
+            if (b < B && r >= 0 && r < X && c >= 0 && c < Y) v = __ldg(img + ((size_t)b * X + r) * Y + c);
+            tile[n][rr][tx] = v;
+        }
+    }
+    __syncthreads();
+    if (pk0) {
+        for (int rr = ty; rr < 32; rr += 8) {
+            const int pr = pr0 + rr, pc = pc0 + tx;
+            if (pr < X + 2 && pc < Y + 2) {
+                float* dst = pk0 + (((size_t)g * (X + 2) + pr) * (Y + 2) + pc) * NB;
+#pragma unroll
+                for (int q = 0; q < NB / 4; ++q)
+                    reinterpret_cast<float4*>(dst)[q] = make_float4(tile[4 * q][rr][tx], tile[4 * q + 1][rr][tx],
+                                                                    tile[4 * q + 2][rr][tx], tile[4 * q + 3][rr][tx]);
+            }
+        }
+    }
+    if (pk1) {
+        for (int cc = ty; cc < 32; cc += 8) {
+            const int pc = pc0 + cc, pr = pr0 + tx;
+            if (pr < X + 2 && pc < Y + 2) {
+                float* dst = pk1 + (((size_t)g * (Y + 2) + pc) * (X + 2) + pr) * NB;
+#pragma unroll
+                for (int q = 0; q < NB / 4; ++q)
+                    reinterpret_cast<float4*>(dst)[q] = make_float4(tile[4 * q][tx][cc], tile[4 * q + 1][tx][cc],
+                                                                    tile[4 * q + 2][tx][cc], tile[4 * q + 3][tx][cc]);
+            }
+        }
+    }
+}
+
+// grid (ceil((W+2)/128), A, G), block 128.
+template <int NB>
+__global__ void __launch_bounds__(128) ctr_pack_sino_kernel(const float* __restrict__ y, int B, int A, int W,
+                                                            float* __restrict__ spk)
+{
+    const int jp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (jp >= W + 2) return;
+    const int a = blockIdx.y, g = blockIdx.z, j = jp - 1;
+    float v[NB];
+#pragma unroll
+    for (int n = 0; n < NB; ++n) {
+        const int b = g * NB + n;
+        v[n] = (b < B && j >= 0 && j < W) ? __ldg(y + ((size_t)b * A + a) * W + j) : 0.f;
+    }
+    float* dst = spk + (((size_t)g * A + a) * (W + 2) + jp) * NB;
+#pragma unroll
+    for (int q = 0; q < NB / 4; ++q)
+        reinterpret_cast<float4*>(dst)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+}
+
+// ------------------------------------------------------------------------------------------ K1 forward
+struct FwdParams {
+    const float* pk[2];     // packed images per class  [G][Vp][Up][NB]
+    CtrClassGeom geom[2];
+    const CtrRay* rays;     // class-sorted ray table [A]
+    int n_cls[2];           // angles per class
+    int chunks0;            // CTAs (along grid.x) that serve class 0
+    int H, W, A, B;
+    int R;                  // key rows per strip (strip holds R+1 packed rows)
+    float* sino;            // [B][A][W]
+};
+
+// One CTA = (angle chunk of NS*KA same-class angles) x (image group of NB) x (detector chunk of JW bins).
+// thread (tx, ty): detector bin j = blockIdx.z*JW + tx, angles ty*KA .. ty*KA+KA-1 of the chunk.
+// All threads walk the image group's strips in lock step; thread 0 drives the TMA double buffer.
+template <int NB, int KA, int INTERP>
+__global__ void __launch_bounds__(kFwdMaxThreads, 1) ctr_fwd_kernel(const FwdParams p)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int JW = blockDim.x, NS = blockDim.y;
+    const int NA = NS * KA;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int tid = ty * JW + tx, nthreads = JW * NS;
+
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);                 // 2 mbarriers
+    CtrRay* rays_s = reinterpret_cast<CtrRay*>(smem_raw + 128);              // NA rays
+    const int rays_bytes = round_up(NA * (int)sizeof(CtrRay), 128);
+
+    const int cls = (int)blockIdx.x >= p.chunks0;
+    const int lchunk = cls ? (int)blockIdx.x - p.chunks0 : (int)blockIdx.x;
+    const int first = (cls ? p.n_cls[0] : 0) + lchunk * NA;
+    const int cnt = min(NA, (cls ? p.n_cls[1] : p.n_cls[0]) - lchunk * NA);
+    const int g = blockIdx.y;
+    const CtrClassGeom geom = cls ? p.geom[1] : p.geom[0];  // static indices: stays in registers
+    const int R = p.R;
+    const int strip_floats = (R + 1) * geom.Up * NB;
+    float* buf0 = reinterpret_cast<float*>(smem_raw + 128 + rays_bytes);
+    float* buf1 = buf0 + strip_floats;
+    const int K = (geom.Vp + R - 1) / R;
+    const float* pkg = (cls ? p.pk[1] : p.pk[0]) + (size_t)g * geom.Vp * geom.Up * NB;
+
+    for (int k = tid; k < cnt; k += nthreads) rays_s[k] = p.rays[first + k];
+    if (tid == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int k) {
+        const int rows = min(R + 1, geom.Vp - k * R);
+        const uint32_t bytes = (uint32_t)rows * geom.Up * NB * 4u;
+        uint64_t* bar = &full[k & 1];
+        mbar_arrive_expect_tx(bar, bytes);
+        bulk_g2s((k & 1) ? buf1 : buf0, pkg + (size_t)k * R * geom.Up * NB, bytes, bar);
+    };
+    if (tid == 0) {
+        issue(0);
+        if (K > 1) issue(1);
+    }
+
+    // per-ray state: next step and steps left (coefficients are re-read from smem per strip)
+    const int j = blockIdx.z * JW + tx;
+    int ri[KA], rn[KA];
+    float acc[KA][NB];
+#pragma unroll
+    for (int q = 0; q < KA; ++q) {
+        const int la = ty * KA + q;
+        ri[q] = 0;
+        rn[q] = 0;
+        if (la < cnt && j < p.W) {
+            CtrRayState s;
+            ctr_ray_begin(rays_s[la], geom, j, p.H, s);
+            ri[q] = s.i;
+            rn[q] = s.n;
+        }
+#pragma unroll
+        for (int n = 0; n < NB; ++n) acc[q][n] = 0.f;
+    }
+
+    for (int k = 0; k < K; ++k) {
+        mbar_wait(&full[k & 1], (uint32_t)((k >> 1) & 1));
+        const float* strip = (k & 1) ? buf1 : buf0;
+        const float vend = (float)((k + 1) * R + geom.offv);
+        const int rbase = k * R + geom.offv;
+#pragma unroll
+        for (int q = 0; q < KA; ++q) {
+            if (rn[q] > 0) {
+                const CtrRay r = rays_s[ty * KA + q];
+                CtrRayState s;
+                s.pu = CTR_MUL(r.u0, (float)j);
+                s.pv = CTR_MUL(r.v0, (float)j);
+                s.i = ri[q];
+                s.n = rn[q];
+                s.di = (r.v1 >= 0.f) ? 1 : -1;
+                ctr_march<NB, INTERP>(strip, geom.Up, vend, rbase, geom.offu, r, s, acc[q]);
+                ri[q] = s.i;
+                rn[q] = s.n;
+            }
+        }
+        __syncthreads();  // every thread is done reading this buffer -> it may be refilled
+        if (tid == 0 && k + 2 < K) issue(k + 2);
+    }
+
+#pragma unroll
+    for (int q = 0; q < KA; ++q) {
+        const int la = ty * KA + q;
+        if (la < cnt && j < p.W) {
+            const int a = rays_s[la].angle;
+#pragma unroll
+            for (int n = 0; n < NB; ++n) {
+                const int b = g * NB + n;
+                if (b < p.B) p.sino[((size_t)b * p.A + a) * p.W + j] = acc[q][n];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ K2 / K2' / K3b
+struct BpParams {
+    const float* spk;      // packed sinogram [G][A][W+2][NB]
+    const float* table;    // [A][8] forward (EXACT) or inverted (TF) transforms; unused for FBP
+    const double* cs;      // [A][2] cos/sin(theta) for FBP
+    float* out;            // [B][X][Y]
+    int B, A, X, Y, H, W, padx, pady;
+    int win;               // bins staged per angle (<= W+2)
+    float scale;           // 1, or pi/(2A) for FBP
+};
+
+// One CTA = TW x TH pixel tile x image group of NB.  Angles are processed in batches
+// of AB: lanes 0..AB-1 of warp 0 each own one angle of the batch -- they compute the
+// bin window the tile needs, publish its start + the angle's coefficients to shared
+// memory, and issue the window's TMA bulk copy -- while all threads gather from the
+// previous batch.  No atomics anywhere: each thread owns its pixel's NB accumulators.
+template <int NB, int MODE, int INTERP>
+__global__ void __launch_bounds__(kBpTW * kBpTH, 2) ctr_bp_kernel(const BpParams p)
+{
+    constexpr int TW = kBpTW, TH = kBpTH, AB = kBpAB;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);            // [2]
+    int* jb = reinterpret_cast<int*>(smem_raw + 16);                   // [2][AB]
+    float* tbl = reinterpret_cast<float*>(smem_raw + 128);             // [2][AB][8]
+    double* css = reinterpret_cast<double*>(smem_raw + 128 + 2 * AB * 8 * 4);  // [2][AB][2]
+    float* wins = reinterpret_cast<float*>(smem_raw + 128 + 2 * AB * 8 * 4 + 2 * AB * 2 * 8);  // [2][AB][win*NB]
+
+    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TW + tx;
+    const int c0 = blockIdx.x * TW, r0 = blockIdx.y * TH, g = blockIdx.z;
+    const int c = c0 + tx, r = r0 + ty;
+    const int Wp2 = p.W + 2;
+    const int win = p.win;
+    const int nbatch = (p.A + AB - 1) / AB;
+    const float px = (float)(c + p.pady), py = (float)(r + p.padx);
+    // FBP pixel coordinates (fbp_tensorflow.py:52-53): x' = row - x_size/2, y' = col - y_size/2
+    const double xpr = (double)r - 0.5 * (double)p.X, ypr = (double)c - 0.5 * (double)p.Y;
+
+    if (tid == 0) {
+        mbar_init(&full[0], AB);
+        mbar_init(&full[1], AB);
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    auto produce = [&](int nb, int lane) {
+        const int s = nb & 1;
+        const int a = nb * AB + lane;
+        uint64_t* bar = &full[s];
+        if (a >= p.A) { mbar_arrive(bar); return; }
+        float cu[4];
+        if (MODE == CTR_ADJ_FBP) {
+            const double co = p.cs[2 * a], si = p.cs[2 * a + 1];
+            css[(s * AB + lane) * 2 + 0] = co;
+            css[(s * AB + lane) * 2 + 1] = si;
+            int q = 0;
+            for (int cy = 0; cy < 2; ++cy)
+                for (int cx = 0; cx < 2; ++cx) {
+                    const double xr = (double)(r0 + cy * (TH - 1)) - 0.5 * (double)p.X;
+                    const double yr = (double)(c0 + cx * (TW - 1)) - 0.5 * (double)p.Y;
+                    cu[q++] = (float)(yr * co - xr * si + 0.5 * (double)p.W);
+                }
+        } else {
+            float t[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) t[q] = p.table[8 * a + q];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) tbl[(s * AB + lane) * 8 + q] = t[q];
+            int q = 0;
+            for (int cy = 0; cy < 2; ++cy)
+                for (int cx = 0; cx < 2; ++cx) {
+                    const float qx = (float)(c0 + cx * (TW - 1) + p.pady), qy = (float)(r0 + cy * (TH - 1) + p.padx);
+                    float uj, vi;
+                    if (MODE == CTR_ADJ_EXACT) ctr_adj_centre(t, qx, qy, uj, vi);
+                    else uj = CTR_ADD(CTR_ADD(CTR_MUL(t[0], qx), CTR_MUL(t[1], qy)), t[2]);
+                    cu[q++] = uj;
+                }
+        }
+        const int start = ctr_window_start(cu[0], cu[1], cu[2], cu[3], Wp2, win);
+        jb[s * AB + lane] = start;
+        const uint32_t bytes = (uint32_t)win * NB * 4u;
+        mbar_arrive_expect_tx(bar, bytes);   // release: publishes jb/tbl/css to the waiters
+        bulk_g2s(wins + (size_t)(s * AB + lane) * win * NB,
+                 p.spk + (((size_t)g * p.A + a) * Wp2 + start) * NB, bytes, bar);
+    };
+
+    if (tid < AB) {
+        produce(0, tid);
+        if (nbatch > 1) produce(1, tid);
+    }
+
+    float acc[NB];
+#pragma unroll
+    for (int n = 0; n < NB; ++n) acc[n] = 0.f;
+
+    for (int nb = 0; nb < nbatch; ++nb) {
+        const int s = nb & 1;
+        mbar_wait(&full[s], (uint32_t)((nb >> 1) & 1));
+        const int na = min(AB, p.A - nb * AB);
+        for (int k = 0; k < na; ++k) {
+            const float* ywin = wins + (size_t)(s * AB + k) * win * NB;
+            const int start = jb[s * AB + k];
+            if (MODE == CTR_ADJ_FBP) {
+                ctr_adj_fbp<NB>(&css[(s * AB + k) * 2], p.W, xpr, ypr, ywin, start, acc);
+            } else {
+                float t[8];
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const float4 tv = reinterpret_cast<const float4*>(tbl + (s * AB + k) * 8)[q];
+                    t[4 * q] = tv.x; t[4 * q + 1] = tv.y; t[4 * q + 2] = tv.z; t[4 * q + 3] = tv.w;
+                }
+                if (MODE == CTR_ADJ_EXACT) ctr_adj_exact<NB, INTERP>(t, p.H, p.W, px, py, ywin, start, acc);
+                else ctr_adj_tf<NB, INTERP>(t, p.H, p.W, px, py, ywin, start, acc);
+            }
+        }
+        __syncthreads();  // batch buffers free again
+        if (tid < AB && nb + 2 < nbatch) produce(nb + 2, tid);
+    }
+
+    if (r < p.X && c < p.Y) {
+#pragma unroll
+        for (int n = 0; n < NB; ++n) {
+            const int b = g * NB + n;
+            if (b < p.B) p.out[((size_t)b * p.X + r) * p.Y + c] = acc[n] * p.scale;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ K3a filter
+// rf[n] = sum_k s[k] * h[(n-k) mod P]  ==  real(ifft(fft(s) * filter_1d))   for real s
+// (fbp_tensorflow.py:49-50; no zero padding, so the convolution is circular).
+// grid (A, G), block 256.  smem: NB rows interleaved [P][NB] + doubled kernel h2[2P].
+template <int NB>
+__global__ void __launch_bounds__(256) ctr_fbp_filter_kernel(const float* __restrict__ sino, const float* __restrict__ h,
+                                                             int B, int A, int P, float* __restrict__ spk)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* s = reinterpret_cast<float*>(smem_raw);   // [P][NB]
+    float* h2 = s + (size_t)P * NB;                   // [2P]
+    const int a = blockIdx.x, g = blockIdx.y;
+    for (int idx = threadIdx.x; idx < P * NB; idx += blockDim.x) {
+        const int n = idx / P, k = idx - n * P;       // coalesced along k per image
+        const int b = g * NB + n;
+        s[k * NB + n] = (b < B) ? __ldg(sino + ((size_t)b * A + a) * P + k) : 0.f;
+    }
+    for (int m = threadIdx.x; m < 2 * P; m += blockDim.x) h2[m] = __ldg(h + (m >= P ? m - P : m));
+    __syncthreads();
+    float* dst_row = spk + ((size_t)g * A + a) * (P + 2) * NB;
+    for (int n_out = threadIdx.x; n_out < P; n_out += blockDim.x) {
+        float acc[NB];
+#pragma unroll
+        for (int n = 0; n < NB; ++n) acc[n] = 0.f;
+        const float* hp = h2 + n_out + P;
+        for (int k = 0; k < P; ++k) {
+            const float hv = hp[-k];
+            float sv[NB];
+            ctr_ldv<NB>(s + (size_t)k * NB, sv);
+#pragma unroll
+            for (int n = 0; n < NB; ++n) acc[n] = fmaf(hv, sv[n], acc[n]);
+        }
+        float* dst = dst_row + (size_t)(n_out + 1) * NB;
+#pragma unroll
+        for (int q = 0; q < NB / 4; ++q)
+            reinterpret_cast<float4*>(dst)[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+    }
+    if (threadIdx.x < 2) {  // halo bins (never read by the FBP gather; keep them defined)
+        float* dst = dst_row + (size_t)(threadIdx.x ? P + 1 : 0) * NB;
+#pragma unroll
+        for (int n = 0; n < NB; ++n) dst[n] = 0.f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ launchers
+struct FwdConfig {
+    int JW, NS, KA, R, jchunks;
+    size_t smem;
+};
+
+// Shape the forward CTA: JW detector bins x NS angle slots x KA angles per slot, and the
+// largest strip height R whose double buffer fits the shared-memory budget.
+inline FwdConfig fwd_config(int W, const CtrClassGeom geom[2], int smem_budget)
+{
+    FwdConfig c;
+    c.JW = round_up(W, 32);
+    if (c.JW > kFwdMaxThreads) c.JW = kFwdMaxThreads;
+    c.jchunks = (W + c.JW - 1) / c.JW;
+    c.NS = kFwdMaxThreads / c.JW;
+    if (c.NS > 8) c.NS = 8;
+    if (c.NS < 1) c.NS = 1;
+    c.KA = (c.NS == 1) ? 4 : (c.NS == 2 ? 2 : 1);
+    const int NA = c.NS * c.KA;
+    const int fixed = 128 + round_up(NA * (int)sizeof(CtrRay), 128);
+    const int Upmax = geom[0].Up > geom[1].Up ? geom[0].Up : geom[1].Up;
+    const int Vpmax = geom[0].Vp > geom[1].Vp ? geom[0].Vp : geom[1].Vp;
+    const int row_bytes = Upmax * kFwdNB * 4;
+    int rows = (smem_budget - fixed) / (2 * row_bytes);   // rows per buffer = R + 1
+    if (rows > Vpmax) rows = Vpmax;
+    if (rows > 33) rows = 33;   // bigger strips only lengthen the un-overlapped first load
+    c.R = rows - 1;
+    if (c.R < 1) c.R = 0;  // caller treats 0 as "image too wide for the strip buffers"
+    c.smem = (size_t)fixed + 2ull * (size_t)(c.R + 1) * row_bytes;
+    return c;
+}
+
+template <int INTERP>
+inline cudaError_t launch_fwd_ka(const FwdParams& p, const FwdConfig& c, int G, int chunks, cudaStream_t st)
+{
+    dim3 grid(chunks, G, c.jchunks), block(c.JW, c.NS);
+    cudaError_t e;
+#define CTR_FWD_CASE(KA_)                                                                                          \
+    case KA_:                                                                                                      \
+        e = cudaFuncSetAttribute(ctr_fwd_kernel<kFwdNB, KA_, INTERP>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                 (int)c.smem);                                                                     \
+        if (e != cudaSuccess) return e;                                                                            \
+        ctr_fwd_kernel<kFwdNB, KA_, INTERP><<<grid, block, c.smem, st>>>(p);                                       \
+        break;
+    switch (c.KA) {
+        CTR_FWD_CASE(1)
+        CTR_FWD_CASE(2)
+        CTR_FWD_CASE(4)
+        default: return cudaErrorInvalidValue;
+    }
+#undef CTR_FWD_CASE
+    launch_counter()++;
+    return cudaGetLastError();
+}
+
+inline size_t bp_smem_bytes(int win)
+{
+    return 128 + 2 * kBpAB * 8 * 4 + 2 * kBpAB * 2 * 8 + 2ull * kBpAB * (size_t)win * kBpNB * 4;
+}
+
+template <int MODE, int INTERP>
+inline cudaError_t launch_bp(const BpParams& p, cudaStream_t st)
+{
+    const int G = (p.B + kBpNB - 1) / kBpNB;
+    dim3 grid((p.Y + kBpTW - 1) / kBpTW, (p.X + kBpTH - 1) / kBpTH, G), block(kBpTW, kBpTH);
+    const size_t smem = bp_smem_bytes(p.win);
+    cudaError_t e = cudaFuncSetAttribute(ctr_bp_kernel<kBpNB, MODE, INTERP>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    ctr_bp_kernel<kBpNB, MODE, INTERP><<<grid, block, smem, st>>>(p);
+    launch_counter()++;
+    return cudaGetLastError();
+}
+
+}  // namespace ctr

@@ -1,0 +1,107 @@
+"""Device-level operators: torch CUDA tensors in, torch CUDA tensors out.
+
+torch is plumbing here (device memory, the current stream, autograd bookkeeping);
+every FLOP runs in libctradon's sm_100a kernels, reached through the C ABI with
+zero-copy DLPack tensors.  CPU tensors are rejected -- there is no fallback.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+
+INTERP = {"nearest": _lib.INTERP_NEAREST, "bilinear": _lib.INTERP_BILINEAR}
+ADJOINT = {"exact": _lib.ADJOINT_EXACT, "tf_compat": _lib.ADJOINT_TF_COMPAT}
+
+
+def _require_cuda_f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: ct_pvae_b200 has no CPU path")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+    return t.contiguous()
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return int(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _workspace(nbytes: int, device: torch.device) -> torch.Tensor:
+    # caller-owned scratch from torch's caching allocator (512-byte aligned blocks)
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def theta_to_host(theta) -> np.ndarray:
+    """Angles as the float64 host vector the plan is keyed on.  float32 inputs (the
+    training path casts theta to float32, helper_functions.py:355) widen exactly."""
+    if isinstance(theta, torch.Tensor):
+        theta = theta.detach().cpu().numpy()
+    th = np.asarray(theta)
+    if th.ndim > 1:
+        raise ValueError("angles should have rank 0 or 1.")
+    return np.ascontiguousarray(th.reshape(-1), dtype=np.float64)
+
+
+def radon_forward(img: torch.Tensor, plan: _lib.Plan, interp: int) -> torch.Tensor:
+    """img [B,X,Y] float32 CUDA -> sino [B,A,W] float32 CUDA (ctr_radon_forward_dl)."""
+    img = _require_cuda_f32(img, "img")
+    if img.dim() != 3 or img.shape[1] != plan.X or img.shape[2] != plan.Y:
+        raise ValueError(f"img must be [B,{plan.X},{plan.Y}], got {tuple(img.shape)}")
+    B = img.shape[0]
+    sino = torch.empty((B, plan.A, plan.W), dtype=torch.float32, device=img.device)
+    if B == 0:
+        return sino
+    ws = _workspace(plan.forward_workspace_bytes(B), img.device)
+    vi, vs, vw = _lib.DLView(img), _lib.DLView(sino), _lib.DLView(ws)
+    _lib.check(_lib.lib().ctr_radon_forward_dl(plan.handle, vi.ptr, vs.ptr, interp, vw.ptr, _stream_ptr(img.device)))
+    return sino
+
+
+def radon_adjoint(dsino: torch.Tensor, plan: _lib.Plan, interp: int, mode: int) -> torch.Tensor:
+    """dsino [B,A,W] float32 CUDA -> dimg [B,X,Y] float32 CUDA (ctr_radon_adjoint_dl)."""
+    dsino = _require_cuda_f32(dsino, "dsino")
+    if dsino.dim() != 3 or dsino.shape[1] != plan.A or dsino.shape[2] != plan.W:
+        raise ValueError(f"dsino must be [B,{plan.A},{plan.W}], got {tuple(dsino.shape)}")
+    B = dsino.shape[0]
+    dimg = torch.empty((B, plan.X, plan.Y), dtype=torch.float32, device=dsino.device)
+    if B == 0:
+        return dimg
+    ws = _workspace(plan.adjoint_workspace_bytes(B), dsino.device)
+    vi, vo, vw = _lib.DLView(dsino), _lib.DLView(dimg), _lib.DLView(ws)
+    _lib.check(_lib.lib().ctr_radon_adjoint_dl(plan.handle, vi.ptr, vo.ptr, interp, mode, vw.ptr, _stream_ptr(dsino.device)))
+    return dimg
+
+
+def fbp(sino: torch.Tensor, plan: _lib.FbpPlan) -> torch.Tensor:
+    """sino [B,A,P] float32 CUDA -> recon [B,x_size,y_size] float32 CUDA (ctr_fbp_dl)."""
+    sino = _require_cuda_f32(sino, "sinogram")
+    B = sino.shape[0]
+    out = torch.empty((B, plan.x_size, plan.y_size), dtype=torch.float32, device=sino.device)
+    if B == 0:
+        return out
+    ws = _workspace(plan.workspace_bytes(B), sino.device)
+    vi, vo, vw = _lib.DLView(sino), _lib.DLView(out), _lib.DLView(ws)
+    _lib.check(_lib.lib().ctr_fbp_dl(plan.handle, vi.ptr, vo.ptr, vw.ptr, _stream_ptr(sino.device)))
+    return out
+
+
+class RadonFunction(torch.autograd.Function):
+    """Differentiable projector: forward dispatches K1, backward dispatches the adjoint
+    (exact transpose by default, TensorFlow's gradient with adjoint="tf_compat").
+    Mirrors what tf.GradientTape does around project_tf_fast (main_ct_vae.py:471-481)."""
+
+    @staticmethod
+    def forward(ctx, img, plan, interp, mode):
+        ctx.plan, ctx.interp, ctx.mode = plan, interp, mode
+        return radon_forward(img, plan, interp)
+
+    @staticmethod
+    def backward(ctx, dsino):
+        return radon_adjoint(dsino.contiguous(), ctx.plan, ctx.interp, ctx.mode), None, None, None
+
+
+def project(img: torch.Tensor, plan: _lib.Plan, interp: int, mode: int) -> torch.Tensor:
+    if img.requires_grad and torch.is_grad_enabled():
+        return RadonFunction.apply(img, plan, interp, mode)
+    return radon_forward(img, plan, interp)

@@ -1,0 +1,133 @@
+/*
+ * ctradon.h -- C ABI of libctradon.so, the B200 (sm_100a) Radon path of CT_PVAE.
+ *
+ * The reference exposes no FFI: its boundary is four Python functions
+ *   ctvae/forward_functions.py:18   pad_phantom(phantom, dim=3, integrate_vae=False)
+ *   ctvae/forward_functions.py:49   project_tf_low_mem(phantom, theta, pad=False)
+ *   ctvae/forward_functions.py:80   project_tf_fast(phantom, theta, pad=False, dim=3, integrate_vae=False)
+ *   ctvae/fbp_tensorflow.py:14      iradon(sinogram, theta, x_size, y_size, filter_1d)
+ * plus TensorFlow's autodiff through project_tf_fast (ctvae/main_ct_vae.py:471-481).
+ * The entry points below are what a ctypes binding of those functions calls; each
+ * one names the reference lines it replaces.  INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - Every function returns CTR_OK (0) or a negative CTR_E* code and never throws
+ *     or aborts; ctr_last_error() gives the thread-local message of the last failure.
+ *   - The caller allocates and owns every buffer, inputs, outputs and workspace
+ *     alike.  The library borrows pointers for the duration of the call, never
+ *     allocates result memory and never calls a DLPack deleter.
+ *   - Device buffers are float32, C-contiguous: images [B,X,Y], sinograms [B,A,W]
+ *     (the reference's trailing size-1 channel axis is a free reshape).
+ *   - Work is enqueued on `stream` (a cudaStream_t passed as void*, NULL = legacy
+ *     default stream) and the call returns without synchronising.
+ *   - Plans are immutable after creation and may be shared between threads.
+ *   - There is no CPU path: without a CUDA device every compute call fails with
+ *     CTR_ECUDA.
+ */
+#ifndef CTRADON_H_
+#define CTRADON_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#include "ctr_dlpack.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTR_VERSION 100 /* 0.1.0 */
+
+enum {
+    CTR_OK = 0,
+    CTR_EINVAL = -1,      /* bad argument (shape, enum, NULL, dtype, device, contiguity) */
+    CTR_ECUDA = -2,       /* a CUDA runtime call failed; message carries cudaGetErrorString */
+    CTR_EWORKSPACE = -3,  /* workspace smaller than ctr_*_workspace_bytes() */
+    CTR_EUNSUPPORTED = -4 /* shape outside what the kernels are built for */
+};
+
+enum { CTR_INTERP_NEAREST = 0, CTR_INTERP_BILINEAR = 1 };
+/* CTR_ADJOINT_EXACT    : exact transpose of the forward operator (<Ax,y> == <x,A^T y>)
+ * CTR_ADJOINT_TF_COMPAT: TensorFlow's registered gradient of the reference graph
+ *                        (rotate the row-broadcast cotangent by the inverted transforms) */
+enum { CTR_ADJOINT_EXACT = 0, CTR_ADJOINT_TF_COMPAT = 1 };
+
+typedef struct ctr_plan ctr_plan;
+typedef struct ctr_fbp_plan ctr_fbp_plan;
+
+int ctr_version(void);
+const char* ctr_last_error(void);
+/* number of kernel launches this process has made through the library (bench.py's gpu_launches) */
+long long ctr_launch_count(void);
+
+/* ---- host-side geometry (no GPU needed) ------------------------------------------------ */
+
+/* forward_functions.py:29-30: ceil((sqrt(X^2+Y^2)+2)/2)*2 */
+int ctr_num_proj_pix(int X, int Y);
+/* forward_functions.py:32-39: frame the image is padded to and the "before" pads */
+int ctr_frame(int X, int Y, int pad, int* H, int* W, int* padx, int* pady);
+/* forward_functions.py:113 -> tfa.image.rotate(imgs, -theta): [A,8] float32 projective
+ * transforms (angles_to_projective_transforms), float32 arithmetic, no FMA */
+int ctr_make_transforms(const double* theta, int A, int H, int W, float* out_a8);
+/* TF's gradient of ImageProjectiveTransformV3: float32 3x3 inverse of each transform */
+int ctr_invert_transforms(const float* t_a8, int A, float* out_a8);
+/* real(ifft(filter_1d)): the spatial kernel equivalent to fbp_tensorflow.py:49-50's
+ * frequency-domain product for real sinograms (filt_im may be NULL) */
+int ctr_filter_to_spatial(const double* filt_re, const double* filt_im, int P, double* out_p);
+
+/* ---- projector plans --------------------------------------------------------------------- */
+
+/* Geometry of one project_tf_fast call: the angles `theta` (radians, as passed to the
+ * reference function; the minus sign of forward_functions.py:113 is applied inside),
+ * the image size X x Y (rows x cols) and whether pad_phantom is applied.  Uploads the
+ * transform tables and the class-sorted ray table to `device`. */
+int ctr_plan_create(const double* theta, int A, int X, int Y, int pad, int device, ctr_plan** out);
+int ctr_plan_destroy(ctr_plan* plan);
+/* any of the out pointers may be NULL */
+int ctr_plan_info(const ctr_plan* plan, int* A, int* X, int* Y, int* H, int* W, int* padx, int* pady);
+/* copies the plan's [A,8] tables to host buffers (either may be NULL) */
+int ctr_plan_tables(const ctr_plan* plan, float* fwd_a8, float* inv_a8);
+
+size_t ctr_forward_workspace_bytes(const ctr_plan* plan, int B);
+size_t ctr_adjoint_workspace_bytes(const ctr_plan* plan, int B);
+
+/* project_tf_fast (interp = CTR_INTERP_NEAREST, forward_functions.py:80-123) and
+ * project_tf_low_mem (CTR_INTERP_BILINEAR, :49-78):
+ *   sino[b,a,j] = sum_i rotate_{-theta_a}(pad(img_b))[i,j]
+ * img [B,X,Y] -> sino [B,A,W], both on the plan's device. */
+int ctr_radon_forward(const ctr_plan* plan, const float* img, float* sino, int B, int interp,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* Gradient of the above w.r.t. img given d(loss)/d(sino)  (main_ct_vae.py:471-481):
+ * dsino [B,A,W] -> dimg [B,X,Y].  mode selects the exact transpose or TF's gradient. */
+int ctr_radon_adjoint(const ctr_plan* plan, const float* dsino, float* dimg, int B, int interp, int mode,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- filtered back-projection ------------------------------------------------------------ */
+
+/* iradon(sinogram, theta, x_size, y_size, filter_1d)  (fbp_tensorflow.py:14-75).
+ * filter_1d is the length-P frequency-domain filter in FFT order (imaginary part
+ * optional).  Returns CTR_EINVAL if A does not match at call time, like the
+ * reference's ValueError (:43-45). */
+int ctr_fbp_plan_create(const double* theta, int A, int P, int x_size, int y_size, const double* filt_re,
+                        const double* filt_im, int device, ctr_fbp_plan** out);
+int ctr_fbp_plan_destroy(ctr_fbp_plan* plan);
+size_t ctr_fbp_workspace_bytes(const ctr_fbp_plan* plan, int B);
+/* sino [B,A,P] -> recon [B,x_size,y_size] (float32 on device; the Python shim widens
+ * to float64 to keep the reference's return dtype) */
+int ctr_fbp(const ctr_fbp_plan* plan, const float* sino, int A, float* recon, int B, void* workspace,
+            size_t workspace_bytes, void* stream);
+
+/* ---- zero-copy DLPack entry points ---------------------------------------------------------
+ * Same operations on borrowed DLTensors (kDLCUDA, float32, compact row-major).
+ * img may be [B,X,Y] or [B,X,Y,1]; sino [B,A,W] or [B,A,W,1].  `workspace` is any
+ * compact CUDA tensor with at least ctr_*_workspace_bytes() bytes. */
+int ctr_radon_forward_dl(const ctr_plan* plan, const DLTensor* img, DLTensor* sino, int interp,
+                         DLTensor* workspace, void* stream);
+int ctr_radon_adjoint_dl(const ctr_plan* plan, const DLTensor* dsino, DLTensor* dimg, int interp, int mode,
+                         DLTensor* workspace, void* stream);
+int ctr_fbp_dl(const ctr_fbp_plan* plan, const DLTensor* sino, DLTensor* recon, DLTensor* workspace, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTRADON_H_ */

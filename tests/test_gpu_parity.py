@@ -1,0 +1,217 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle.
+
+Tolerance (north_star): relative L2 <= 1e-5 for the float32 projector and its
+adjoints; <Ax,y> == <x,A^T y> to float32 rounding.  FBP computes in float32 against a
+float64 oracle: relative L2 <= 2e-5.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+INTERPS = ["nearest", "bilinear"]
+IID = {"nearest": 0, "bilinear": 1}
+
+# (B, X, Y, A, pad): ragged batches (B % 4, B % 8 != 0), non-square, no-pad, tiny, multi-strip
+SHAPES = [
+    (1, 2, 2, 2, False),
+    (5, 16, 16, 12, True),
+    (3, 16, 16, 12, False),
+    (2, 33, 20, 17, True),
+    (2, 20, 33, 17, False),
+    (9, 64, 64, 24, True),
+    (4, 128, 128, 20, True),
+    (1, 200, 200, 7, True),
+]
+
+
+def _theta(A):
+    return np.linspace(0, np.pi, A, endpoint=False)
+
+
+@pytest.fixture(scope="module")
+def cp():
+    import ct_pvae_b200
+
+    assert torch.cuda.is_available()
+    return ct_pvae_b200
+
+
+@pytest.mark.parametrize("interp", INTERPS)
+@pytest.mark.parametrize("B,X,Y,A,pad", SHAPES)
+def test_forward_matches_oracle(cp, orc, B, X, Y, A, pad, interp):
+    rng = np.random.default_rng(0)
+    img = rng.random((B, X, Y), dtype=np.float32)
+    th = _theta(A) if (X, Y) != (2, 2) else np.array([0, np.pi / 2])
+    want = orc.forward(img, th, pad, IID[interp])
+    got = cp.project_tf_fast(torch.from_numpy(img).cuda().unsqueeze(-1), th, pad=pad, dim=2, integrate_vae=True,
+                             interpolation=interp)
+    assert got.shape == (B, len(th), want.shape[2], 1)
+    assert rel_l2(got[..., 0].cpu().numpy(), want) <= TOL
+
+
+@pytest.mark.parametrize("mode", ["exact", "tf_compat"])
+@pytest.mark.parametrize("interp", INTERPS)
+@pytest.mark.parametrize("B,X,Y,A,pad", SHAPES)
+def test_adjoint_matches_oracle(cp, orc, B, X, Y, A, pad, interp, mode):
+    rng = np.random.default_rng(1)
+    th = _theta(A) if (X, Y) != (2, 2) else np.array([0, np.pi / 2])
+    W = orc.frame_of(X, Y, pad)[1]
+    y = rng.random((B, len(th), W), dtype=np.float32)
+    fn = orc.adjoint_exact if mode == "exact" else orc.adjoint_tf
+    want = fn(y, th, X, Y, pad, IID[interp])
+    got = cp.backproject(torch.from_numpy(y).cuda(), th, X, Y, pad=pad, interpolation=interp, adjoint=mode)
+    assert got.shape == (B, X, Y)
+    assert rel_l2(got.cpu().numpy(), want) <= TOL
+
+
+def test_random_angles_and_signs(cp, orc):
+    rng = np.random.default_rng(2)
+    th = rng.uniform(-7, 7, 23)
+    img = rng.random((3, 40, 40), dtype=np.float32)
+    for interp in INTERPS:
+        want = orc.forward(img, th, True, IID[interp])
+        got = cp.project_tf_fast(torch.from_numpy(img).cuda().unsqueeze(-1), th, pad=True, dim=2, integrate_vae=True,
+                                 interpolation=interp)
+        assert rel_l2(got[..., 0].cpu().numpy(), want) <= TOL
+
+
+def test_toy_known_answers(cp):
+    # scripts/create_toy_images.py:36-37 + scripts/images_to_sinograms.py:54-59
+    x0 = np.array([[1, 2], [3, 4]], np.float32) / 10
+    th = np.array([0, np.pi / 2])
+    for interp in INTERPS:
+        s = cp.project_tf_fast(torch.from_numpy(x0).cuda(), th, pad=False, dim=2, integrate_vae=False,
+                               interpolation=interp)
+        assert s.shape == (2, 2, 1)
+        np.testing.assert_allclose(s[..., 0].cpu().numpy(), [[0.4, 0.6], [0.7, 0.3]], rtol=1e-6)
+
+
+def test_layouts_and_dtypes(cp, orc):
+    rng = np.random.default_rng(3)
+    th = _theta(9)
+    vol = rng.random((24, 24, 3))  # [X,Y,Z] float64 like tomopy_forward_compare.py:52,56
+    want = np.transpose(orc.forward(np.transpose(vol, (2, 0, 1)).astype(np.float32), th, True, 0), (1, 2, 0))
+    got = cp.project_tf_fast(vol, th, pad=True)       # numpy in -> numpy out, dtype kept
+    assert isinstance(got, np.ndarray) and got.dtype == np.float64 and got.shape == want.shape
+    assert rel_l2(got, want) <= TOL
+    want_b = np.transpose(orc.forward(np.transpose(vol, (2, 0, 1)).astype(np.float32), th, True, 1), (1, 2, 0))
+    got_b = cp.project_tf_low_mem(torch.from_numpy(vol), th, pad=True)   # CPU tensor in -> CPU tensor out
+    assert got_b.device.type == "cpu" and got_b.dtype == torch.float64
+    assert rel_l2(got_b.numpy(), want_b) <= TOL
+    one = cp.project_tf_fast(vol[:, :, 0].astype(np.float32), th, pad=True, dim=2)
+    assert one.shape == (9, want.shape[1], 1) and rel_l2(one[..., 0], want[..., 0]) <= TOL
+
+
+@pytest.mark.parametrize("interp", INTERPS)
+def test_autograd_is_the_adjoint(cp, orc, interp):
+    rng = np.random.default_rng(4)
+    th = _theta(15)
+    img = torch.from_numpy(rng.random((3, 32, 32, 1), dtype=np.float32)).cuda().requires_grad_(True)
+    W = orc.frame_of(32, 32, True)[1]
+    y = torch.from_numpy(rng.random((3, 15, W, 1), dtype=np.float32)).cuda()
+    s = cp.project_tf_fast(img, th, pad=True, dim=2, integrate_vae=True, interpolation=interp)
+    (s * y).sum().backward()
+    want = orc.adjoint_exact(y[..., 0].cpu().numpy(), th, 32, 32, True, IID[interp])
+    assert rel_l2(img.grad[..., 0].cpu().numpy(), want) <= TOL
+    img.grad = None
+    s = cp.project_tf_fast(img, th, pad=True, dim=2, integrate_vae=True, interpolation=interp, adjoint="tf_compat")
+    (s * y).sum().backward()
+    want = orc.adjoint_tf(y[..., 0].cpu().numpy(), th, 32, 32, True, IID[interp])
+    assert rel_l2(img.grad[..., 0].cpu().numpy(), want) <= TOL
+
+
+@pytest.mark.parametrize("interp", INTERPS)
+@pytest.mark.parametrize("B,X,A", [(256, 128, 180), (8, 512, 720)])
+def test_full_size_properties(cp, B, X, A, interp):
+    """BASELINE.json sizes (C2: 256x128^2x180, C4 slice: 512^2x720): size-independent checks."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    th = _theta(A)
+    img = torch.rand((B, X, X), device="cuda", generator=g)
+    s = cp.project_tf_fast(img.unsqueeze(-1), th, pad=True, dim=2, integrate_vae=True, interpolation=interp)[..., 0]
+    P = s.shape[2]
+    assert P == cp.num_proj_pix(X, X)
+    # theta = 0: exact column sums, centred in the detector
+    pady = (P - X) // 2
+    col = img.double().sum(dim=1)
+    assert torch.allclose(s[:, 0, pady:pady + X].double(), col, rtol=2e-6, atol=0)
+    assert float(s[:, 0, :pady].abs().max()) == 0.0 and float(s[:, 0, pady + X:].abs().max()) == 0.0
+    if interp == "bilinear":  # mass conservation: the padded support never leaves the frame
+        mass = img.double().sum(dim=(1, 2))
+        assert torch.allclose(s.double().sum(dim=2), mass[:, None].expand(-1, A), rtol=1e-5)
+    # linearity
+    img2 = torch.rand((B, X, X), device="cuda", generator=g)
+    s2 = cp.project_tf_fast(img2.unsqueeze(-1), th, pad=True, dim=2, integrate_vae=True, interpolation=interp)[..., 0]
+    s12 = cp.project_tf_fast((img + 2 * img2).unsqueeze(-1), th, pad=True, dim=2, integrate_vae=True,
+                             interpolation=interp)[..., 0]
+    assert float((s12 - (s + 2 * s2)).norm() / s12.norm()) <= 2e-6
+    # adjoint identity <Ax,y> = <x,A^T y>
+    y = torch.rand(s.shape, device="cuda", generator=g)
+    gimg = cp.backproject(y, th, X, X, pad=True, interpolation=interp, adjoint="exact")
+    lhs = float((s.double() * y.double()).sum())
+    rhs = float((img.double() * gimg.double()).sum())
+    assert abs(lhs - rhs) / abs(lhs) <= 2e-6
+
+
+def test_fbp_matches_oracle(cp, orc):
+    rng = np.random.default_rng(6)
+    for (B, A, P, xs, ys, name) in [(3, 20, 46, 30, 30, "ramp"), (9, 45, 184, 128, 128, "hann"),
+                                    (2, 12, 50, 33, 21, None), (1, 7, 23, 16, 16, "shepp-logan")]:
+        th = _theta(A)
+        sino = rng.random((B, A, P))
+        filt = orc.get_fourier_filter(P, name)
+        np.testing.assert_allclose(cp.get_fourier_filter(P, name), filt)
+        want = orc.iradon(sino, th, xs, ys, filt)
+        got = cp.iradon(torch.from_numpy(sino).cuda(), th, xs, ys, filt)
+        assert got.dtype == torch.float64 and got.shape == (B, xs, ys)
+        assert rel_l2(got.cpu().numpy(), want) <= 2e-5
+    with pytest.raises(ValueError):
+        cp.iradon(torch.zeros((1, 5, 16), device="cuda"), _theta(4), 8, 8, np.ones(16))
+
+
+def test_fbp_reconstructs_disk(cp):
+    """forward (bilinear) -> iradon(ramp) recovers a 0.8-valued disk."""
+    X = 128
+    yy, xx = np.meshgrid(np.arange(X) - X / 2 + 0.5, np.arange(X) - X / 2 + 0.5, indexing="ij")
+    img = (0.8 * ((xx ** 2 + yy ** 2) <= 40 ** 2)).astype(np.float32)
+    th = _theta(180)
+    s = cp.project_tf_fast(torch.from_numpy(img).cuda()[None, ..., None], th, pad=True, dim=2, integrate_vae=True,
+                           interpolation="bilinear")[..., 0]
+    P = s.shape[2]
+    rec = cp.iradon(s, th, X, X, cp.get_fourier_filter(P, "ramp"))[0].cpu().numpy()
+    inner = (xx ** 2 + yy ** 2) <= 30 ** 2
+    assert abs(rec[inner].mean() - 0.8) < 0.01
+
+
+def test_golden_fixtures(cp):
+    import os
+
+    d = os.path.join(os.path.dirname(__file__), "golden")
+    z = np.load(os.path.join(d, "radon_golden.npz"))
+    img, th = z["img"], z["theta"]
+    for interp in INTERPS:
+        got = cp.project_tf_fast(torch.from_numpy(img).cuda().unsqueeze(-1), th, pad=True, dim=2, integrate_vae=True,
+                                 interpolation=interp)[..., 0].cpu().numpy()
+        assert rel_l2(got, z[f"sino_{interp}"]) <= TOL
+        for mode in ("exact", "tf_compat"):
+            g = cp.backproject(torch.from_numpy(z["cot"]).cuda(), th, img.shape[1], img.shape[2], pad=True,
+                               interpolation=interp, adjoint=mode).cpu().numpy()
+            assert rel_l2(g, z[f"grad_{mode}_{interp}"]) <= TOL
+    rec = cp.iradon(torch.from_numpy(z["fbp_sino"]).cuda(), th, img.shape[1], img.shape[2], z["fbp_filter"])
+    assert rel_l2(rec.cpu().numpy(), z["fbp_recon"]) <= 2e-5
+
+
+def test_errors_are_loud(cp):
+    with pytest.raises(RuntimeError):
+        from ct_pvae_b200 import ops, _lib
+
+        plan = _lib.get_plan(np.array([0.0]), 4, 4, False, 0)
+        ops.radon_forward(torch.zeros((1, 4, 4)), plan, 0)   # CPU tensor: no fallback
+    with pytest.raises(ValueError):
+        cp.project_tf_fast(torch.zeros((4, 4), device="cuda"), np.zeros((2, 2)), dim=2)  # rank-2 angles
+    with pytest.raises(TypeError):
+        cp.project_tf_fast(torch.zeros((4, 4), dtype=torch.int32, device="cuda"), np.zeros(2), dim=2)

@@ -1,0 +1,52 @@
+"""Quick CUDA-event timings of each kernel path (developer tool, not the bench contract)."""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import ct_pvae_b200 as cp  # noqa: E402
+from ct_pvae_b200 import _lib, ops  # noqa: E402
+
+
+def timeit(fn, iters=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return min(ts), float(np.median(ts))
+
+
+def run(B, X, A, tag):
+    th = np.linspace(0, np.pi, A, endpoint=False)
+    plan = _lib.get_plan(th, X, X, True, 0)
+    img = torch.rand((B, X, X), device="cuda")
+    y = torch.rand((B, A, plan.W), device="cuda")
+    rays = B * A * plan.W
+    upd = B * A * X * X
+    for name, iid in (("nearest", 0), ("bilinear", 1)):
+        best, med = timeit(lambda: ops.radon_forward(img, plan, iid))
+        print(f"{tag} fwd {name:8s}: {best:8.3f} ms (med {med:8.3f})  {rays / best / 1e6:8.2f} G ray-sums/s  "
+              f"{B * A * (X + 1) ** 2 / best / 1e6:9.1f} G samples/s", flush=True)
+        for mode, mid in (("exact", 0), ("tf_compat", 1)):
+            best, med = timeit(lambda: ops.radon_adjoint(y, plan, iid, mid))
+            print(f"{tag} adj {name:8s} {mode:9s}: {best:8.3f} ms (med {med:8.3f})  {upd / best / 1e6:8.2f} G updates/s", flush=True)
+    filt = cp.get_fourier_filter(plan.W, "ramp")
+    fplan = _lib.get_fbp_plan(th, plan.W, X, X, filt, 0)
+    best, med = timeit(lambda: ops.fbp(y, fplan))
+    print(f"{tag} fbp: {best:8.3f} ms (med {med:8.3f})  {upd / best / 1e6:8.2f} G updates/s", flush=True)
+
+
+if __name__ == "__main__":
+    print(torch.cuda.get_device_name(0))
+    run(256, 128, 180, "C2")
+    run(64, 512, 720, "C4")

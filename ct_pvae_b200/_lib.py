@@ -30,6 +30,10 @@ SYMBOLS = {
     "ctr_version": (_c_int, []),
     "ctr_last_error": (ctypes.c_char_p, []),
     "ctr_launch_count": (ctypes.c_longlong, []),
+    "ctr_profile_enable": (_c_int, [_c_int]),
+    "ctr_profile_reset": (_c_int, []),
+    "ctr_profile_read": (_c_int, [_c_int, _f64p, ctypes.POINTER(ctypes.c_longlong)]),
+    "ctr_kernel_name": (ctypes.c_char_p, [_c_int]),
     "ctr_num_proj_pix": (_c_int, [_c_int, _c_int]),
     "ctr_frame": (_c_int, [_c_int, _c_int, _c_int, _intp, _intp, _intp, _intp]),
     "ctr_make_transforms": (_c_int, [_f64p, _c_int, _c_int, _c_int, _f32p]),
@@ -92,6 +96,28 @@ def check(rc: int) -> None:
 
 def launch_count() -> int:
     return int(lib().ctr_launch_count())
+
+
+N_KERNELS = 7
+
+
+def profile_enable(on: bool) -> None:
+    check(lib().ctr_profile_enable(int(bool(on))))
+
+
+def profile_reset() -> None:
+    check(lib().ctr_profile_reset())
+
+
+def profile_read() -> dict:
+    """{kernel name: (total device ms, launches)} since the last reset (synchronises)."""
+    out = {}
+    for k in range(N_KERNELS):
+        ms, n = ctypes.c_double(), ctypes.c_longlong()
+        check(lib().ctr_profile_read(k, ctypes.byref(ms), ctypes.byref(n)))
+        if n.value:
+            out[lib().ctr_kernel_name(k).decode()] = (ms.value, n.value)
+    return out
 
 
 # --------------------------------------------------------------------------- DLPack (zero copy)

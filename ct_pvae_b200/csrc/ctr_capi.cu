@@ -4,7 +4,9 @@
 
 #include <cmath>
 #include <cstdio>
+#include <atomic>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -54,6 +56,29 @@ struct DeviceGuard {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// ---- optional per-kernel event timing (ctr_profile_*) ----
+struct ProfRec { int id; cudaEvent_t e0, e1; };
+std::mutex g_prof_mu;
+std::vector<ProfRec> g_prof;
+std::atomic<int> g_prof_on{0};
+
+struct ProfScope {
+    int id; cudaStream_t st; cudaEvent_t e0 = nullptr, e1 = nullptr; bool on;
+    ProfScope(int id_, cudaStream_t st_) : id(id_), st(st_), on(g_prof_on.load() != 0)
+    {
+        if (!on) return;
+        if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) { on = false; return; }
+        cudaEventRecord(e0, st);
+    }
+    ~ProfScope()
+    {
+        if (!on) return;
+        cudaEventRecord(e1, st);
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        g_prof.push_back({id, e0, e1});
+    }
+};
+
 }  // namespace
 
 struct ctr_plan {
@@ -83,6 +108,44 @@ extern "C" {
 int ctr_version(void) { return CTR_VERSION; }
 const char* ctr_last_error(void) { return g_err.c_str(); }
 long long ctr_launch_count(void) { return ctr::launch_counter().load(); }
+
+static const char* kKernelNames[CTR_K_COUNT] = {"ctr_pack_image_kernel", "ctr_pack_sino_kernel", "ctr_fwd_kernel",
+                                                "ctr_bp_kernel<exact>", "ctr_bp_kernel<tf_compat>",
+                                                "ctr_fbp_filter_kernel", "ctr_bp_kernel<fbp>"};
+const char* ctr_kernel_name(int id) { return (id >= 0 && id < CTR_K_COUNT) ? kKernelNames[id] : ""; }
+
+int ctr_profile_enable(int on)
+{
+    g_prof_on.store(on ? 1 : 0);
+    return CTR_OK;
+}
+
+int ctr_profile_reset(void)
+{
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (auto& r : g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    g_prof.clear();
+    return CTR_OK;
+}
+
+int ctr_profile_read(int id, double* total_ms, long long* launches)
+{
+    if (id < 0 || id >= CTR_K_COUNT) return fail(CTR_EINVAL, "ctr_profile_read: bad kernel id");
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    double tot = 0.0;
+    long long n = 0;
+    for (auto& r : g_prof) {
+        if (r.id != id) continue;
+        CTR_CUDA(cudaEventSynchronize(r.e1));
+        float ms = 0.f;
+        CTR_CUDA(cudaEventElapsedTime(&ms, r.e0, r.e1));
+        tot += ms;
+        ++n;
+    }
+    if (total_ms) *total_ms = tot;
+    if (launches) *launches = n;
+    return CTR_OK;
+}
 
 int ctr_num_proj_pix(int X, int Y) { return (X > 0 && Y > 0) ? ctr_h_num_proj_pix(X, Y) : fail(CTR_EINVAL, "X, Y must be positive"); }
 
@@ -241,6 +304,7 @@ int ctr_radon_forward(const ctr_plan* p, const float* img, float* sino, int B, i
     float* pk1 = p->n_cls[1] ? (float*)((char*)ws + pack_bytes(p, B)) : nullptr;
     {
         dim3 grid((p->Y + 2 + 31) / 32, (p->X + 2 + 31) / 32, G), block(32, 8);
+        ProfScope prof(CTR_K_PACK_IMAGE, st);
         ctr::ctr_pack_image_kernel<ctr::kFwdNB><<<grid, block, 0, st>>>(img, B, p->X, p->Y, pk0, pk1);
         ctr::launch_counter()++;
         CTR_CUDA(cudaGetLastError());
@@ -256,8 +320,12 @@ int ctr_radon_forward(const ctr_plan* p, const float* img, float* sino, int B, i
     fp.H = p->H; fp.W = p->W; fp.A = p->A; fp.B = B;
     fp.R = p->fc.R;
     fp.sino = sino;
-    cudaError_t e = (interp == CTR_INTERP_NEAREST) ? ctr::launch_fwd_ka<CTR_NEAREST>(fp, p->fc, G, chunks, st)
-                                                   : ctr::launch_fwd_ka<CTR_BILINEAR>(fp, p->fc, G, chunks, st);
+    cudaError_t e;
+    {
+        ProfScope prof(CTR_K_FORWARD, st);
+        e = (interp == CTR_INTERP_NEAREST) ? ctr::launch_fwd_ka<CTR_NEAREST>(fp, p->fc, G, chunks, st)
+                                           : ctr::launch_fwd_ka<CTR_BILINEAR>(fp, p->fc, G, chunks, st);
+    }
     if (e != cudaSuccess) return fail_cuda(e, "ctr_fwd_kernel launch");
     return CTR_OK;
 }
@@ -279,6 +347,7 @@ int ctr_radon_adjoint(const ctr_plan* p, const float* dsino, float* dimg, int B,
     float* spk = (float*)ws;
     {
         dim3 grid((p->W + 2 + 127) / 128, p->A, G), block(128);
+        ProfScope prof(CTR_K_PACK_SINO, st);
         ctr::ctr_pack_sino_kernel<ctr::kBpNB><<<grid, block, 0, st>>>(dsino, B, p->A, p->W, spk);
         ctr::launch_counter()++;
         CTR_CUDA(cudaGetLastError());
@@ -292,6 +361,7 @@ int ctr_radon_adjoint(const ctr_plan* p, const float* dsino, float* dimg, int B,
     bp.win = p->bp_win;
     bp.scale = 1.f;
     cudaError_t e;
+    ProfScope prof(mode == CTR_ADJOINT_EXACT ? CTR_K_ADJ_EXACT : CTR_K_ADJ_TF, st);
     if (mode == CTR_ADJOINT_EXACT)
         e = (interp == CTR_INTERP_NEAREST) ? ctr::launch_bp<CTR_ADJ_EXACT, CTR_NEAREST>(bp, st)
                                            : ctr::launch_bp<CTR_ADJ_EXACT, CTR_BILINEAR>(bp, st);
@@ -368,6 +438,7 @@ int ctr_fbp(const ctr_fbp_plan* p, const float* sino, int A, float* recon, int B
         const size_t smem = (size_t)p->P * (ctr::kBpNB + 2) * sizeof(float);
         CTR_CUDA(cudaFuncSetAttribute(ctr::ctr_fbp_filter_kernel<ctr::kBpNB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid(p->A, G), block(256);
+        ProfScope prof(CTR_K_FBP_FILTER, st);
         ctr::ctr_fbp_filter_kernel<ctr::kBpNB><<<grid, block, smem, st>>>(sino, p->d_h, B, p->A, p->P, spk);
         ctr::launch_counter()++;
         CTR_CUDA(cudaGetLastError());
@@ -377,7 +448,11 @@ int ctr_fbp(const ctr_fbp_plan* p, const float* sino, int A, float* recon, int B
     bp.B = B; bp.A = p->A; bp.X = p->x_size; bp.Y = p->y_size; bp.H = p->P; bp.W = p->P; bp.padx = 0; bp.pady = 0;
     bp.win = p->bp_win;
     bp.scale = (float)(M_PI / (2.0 * (double)p->A));
-    cudaError_t e = ctr::launch_bp<CTR_ADJ_FBP, CTR_BILINEAR>(bp, st);
+    cudaError_t e;
+    {
+        ProfScope prof(CTR_K_FBP_BP, st);
+        e = ctr::launch_bp<CTR_ADJ_FBP, CTR_BILINEAR>(bp, st);
+    }
     if (e != cudaSuccess) return fail_cuda(e, "ctr_bp_kernel<FBP> launch");
     return CTR_OK;
 }

@@ -55,7 +55,14 @@ def _compute_device(t: torch.Tensor) -> torch.device:
 
 
 def _finish(out: torch.Tensor, like: torch.Tensor, was_numpy: bool):
-    out = out.to(device=like.device, dtype=like.dtype if like.dtype.is_floating_point else torch.float32)
+    dtype = like.dtype if like.dtype.is_floating_point else torch.float32
+    if out.is_cuda and like.device.type == "cpu" and like.is_pinned() and not out.requires_grad:
+        # pinned in -> pinned out: the device->host copy runs at full PCIe rate
+        host = torch.empty(out.shape, dtype=dtype, pin_memory=True)
+        host.copy_(out.to(dtype), non_blocking=True)
+        torch.cuda.current_stream(out.device).synchronize()
+        return host
+    out = out.to(device=like.device, dtype=dtype)
     return out.detach().numpy() if was_numpy else out
 
 

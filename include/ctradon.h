@@ -59,6 +59,19 @@ const char* ctr_last_error(void);
 /* number of kernel launches this process has made through the library (bench.py's gpu_launches) */
 long long ctr_launch_count(void);
 
+/* ---- per-kernel timing (bench.py's roofline leg) ---------------------------------------------
+ * When enabled, every kernel launch is bracketed by cudaEvents recorded on the
+ * launching stream; ctr_profile_read synchronises those events and returns the summed
+ * device time and launch count of one kernel since the last reset. */
+enum {
+    CTR_K_PACK_IMAGE = 0, CTR_K_PACK_SINO = 1, CTR_K_FORWARD = 2, CTR_K_ADJ_EXACT = 3,
+    CTR_K_ADJ_TF = 4, CTR_K_FBP_FILTER = 5, CTR_K_FBP_BP = 6, CTR_K_COUNT = 7
+};
+int ctr_profile_enable(int on);
+int ctr_profile_reset(void);
+int ctr_profile_read(int kernel_id, double* total_ms, long long* launches);
+const char* ctr_kernel_name(int kernel_id);
+
 /* ---- host-side geometry (no GPU needed) ------------------------------------------------ */
 
 /* forward_functions.py:29-30: ceil((sqrt(X^2+Y^2)+2)/2)*2 */

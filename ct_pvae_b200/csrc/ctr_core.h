@@ -70,6 +70,15 @@ CTR_HD void ctr_ldv(const float* __restrict__ p, float* __restrict__ out)
 #endif
 }
 
+// Sinogram windows are staged as NB/4 planes of [bin][4 images] (pstride floats apart):
+// with 16-byte bins, lanes that read consecutive bins hit consecutive bank groups.
+template <int NB>
+CTR_HD void ctr_ld_bins(const float* __restrict__ ywin, int pstride, int idx, float* __restrict__ out)
+{
+#pragma unroll
+    for (int h = 0; h < NB / 4; ++h) ctr_ldv<4>(ywin + (size_t)h * pstride + (size_t)idx * 4, out + 4 * h);
+}
+
 CTR_HD float ctr_coord(float p0j, float c1, float fi, float c2)
 {
     return CTR_ADD(CTR_ADD(p0j, CTR_MUL(c1, fi)), c2);
@@ -178,9 +187,9 @@ CTR_HD void ctr_march(const float* __restrict__ strip, int Up, float vend, int r
 // ---------------------------------------------------------------------------------------------
 // Pixel-driven back-projections.  t[] is one row of the [A,8] transform table
 // (forward table for EXACT, inverted table for TF).  (px,py) are the pixel's frame
-// coordinates as floats.  ywin holds sinogram bins [jbase_p, jbase_p+wlen) of the
-// halo-padded row (packed bin index = j + 1; bins -1 and W are zero), NB images
-// interleaved: ywin[(jp - jbase_p)*NB + n].
+// coordinates as floats.  ywin holds sinogram bins [jbase_p, jbase_p+win) of the
+// halo-padded row (packed bin index = j + 1; bins -1 and W are zero) as NB/4 planes
+// of [bin][4 images], `pstride` floats apart (see ctr_ld_bins).
 
 // First-order inverse of the forward rotation: which (j,i) lattice point samples closest to (px,py).
 CTR_HD void ctr_adj_centre(const float* t, float px, float py, float& uj, float& vi)
@@ -197,7 +206,7 @@ CTR_HD void ctr_adj_centre(const float* t, float px, float py, float& uj, float&
 // so a superset window is harmless (weight exactly 0).
 template <int NB, int INTERP>
 CTR_HD void ctr_adj_exact(const float* t, int H, int W, float px, float py,
-                          const float* __restrict__ ywin, int jbase_p, float* __restrict__ acc)
+                          const float* __restrict__ ywin, int pstride, int jbase_p, float* __restrict__ acc)
 {
     float uj, vi;
     ctr_adj_centre(t, px, py, uj, vi);
@@ -228,7 +237,7 @@ CTR_HD void ctr_adj_exact(const float* t, int H, int W, float px, float py,
             if (i >= 0 && i < H) wsum += w;
         }
         float yv[NB];
-        ctr_ldv<NB>(ywin + (size_t)(j + 1 - jbase_p) * NB, yv);
+        ctr_ld_bins<NB>(ywin, pstride, j + 1 - jbase_p, yv);
 #pragma unroll
         for (int q = 0; q < NB; ++q) acc[q] += wsum * yv[q];
     }
@@ -238,16 +247,17 @@ CTR_HD void ctr_adj_exact(const float* t, int H, int W, float px, float py,
 // row-broadcast cotangent with the inverted transforms; main_ct_vae.py:471-481).
 template <int NB, int INTERP>
 CTR_HD void ctr_adj_tf(const float* ti, int H, int W, float px, float py,
-                       const float* __restrict__ ywin, int jbase_p, float* __restrict__ acc)
+                       const float* __restrict__ ywin, int pstride, int jbase_p, float* __restrict__ acc)
 {
     const float x = CTR_ADD(CTR_ADD(CTR_MUL(ti[0], px), CTR_MUL(ti[1], py)), ti[2]);
     const float y = CTR_ADD(CTR_ADD(CTR_MUL(ti[3], px), CTR_MUL(ti[4], py)), ti[5]);
     if (INTERP == CTR_NEAREST) {
         const float jj = ctr_round(x), ii = ctr_round(y);
         if (ii >= 0.f && ii < (float)H && jj >= 0.f && jj < (float)W) {
-            const float* yp = ywin + (size_t)((int)jj + 1 - jbase_p) * NB;
+            float yv[NB];
+            ctr_ld_bins<NB>(ywin, pstride, (int)jj + 1 - jbase_p, yv);
 #pragma unroll
-            for (int q = 0; q < NB; ++q) acc[q] += yp[q];
+            for (int q = 0; q < NB; ++q) acc[q] += yv[q];
         }
     } else {
         const float xf = floorf(x), yf = floorf(y);
@@ -255,10 +265,12 @@ CTR_HD void ctr_adj_tf(const float* ti, int H, int W, float px, float py,
             const float wxf = CTR_SUB(CTR_ADD(xf, 1.f), x), wxc = CTR_SUB(x, xf);
             const float wyf = (yf >= 0.f && yf < (float)H) ? CTR_SUB(CTR_ADD(yf, 1.f), y) : 0.f;
             const float wyc = (yf >= -1.f && yf < (float)(H - 1)) ? CTR_SUB(y, yf) : 0.f;
-            const float* yp = ywin + (size_t)((int)xf + 1 - jbase_p) * NB;
+            float y0[NB], y1[NB];
+            ctr_ld_bins<NB>(ywin, pstride, (int)xf + 1 - jbase_p, y0);
+            ctr_ld_bins<NB>(ywin, pstride, (int)xf + 2 - jbase_p, y1);
 #pragma unroll
             for (int q = 0; q < NB; ++q) {
-                const float vrow = CTR_ADD(CTR_MUL(wxf, yp[q]), CTR_MUL(wxc, yp[NB + q]));
+                const float vrow = CTR_ADD(CTR_MUL(wxf, y0[q]), CTR_MUL(wxc, y1[q]));
                 acc[q] += CTR_ADD(CTR_MUL(wyf, vrow), CTR_MUL(wyc, vrow));
             }
         }
@@ -272,7 +284,7 @@ CTR_HD void ctr_adj_tf(const float* ti, int H, int W, float px, float py,
 // bins of the packed row (packed index = j + 1) are never read here.
 template <int NB>
 CTR_HD void ctr_adj_fbp(const double* cs, int P, double xpr, double ypr,
-                        const float* __restrict__ ywin, int jbase_p, float* __restrict__ acc)
+                        const float* __restrict__ ywin, int pstride, int jbase_p, float* __restrict__ acc)
 {
     const double tt = ypr * cs[0] - xpr * cs[1];
     double idx = tt + 0.5 * (double)P;   // (t - x_ref_min)/(x_ref_max - x_ref_min)*(P-1)
@@ -281,8 +293,9 @@ CTR_HD void ctr_adj_fbp(const double* cs, int P, double xpr, double ypr,
     double above = fmin(below + 1.0, (double)(P - 1));
     below = fmax(above - 1.0, 0.0);
     const float alpha = (float)(idx - below);
-    const float* yb = ywin + (size_t)((int)below + 1 - jbase_p) * NB;
-    const float* ya = ywin + (size_t)((int)above + 1 - jbase_p) * NB;
+    float yb[NB], ya[NB];
+    ctr_ld_bins<NB>(ywin, pstride, (int)below + 1 - jbase_p, yb);
+    ctr_ld_bins<NB>(ywin, pstride, (int)above + 1 - jbase_p, ya);
 #pragma unroll
     for (int q = 0; q < NB; ++q) acc[q] += (1.f - alpha) * yb[q] + alpha * ya[q];
 }

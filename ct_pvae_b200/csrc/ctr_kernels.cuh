@@ -77,8 +77,7 @@ inline std::atomic<long long>& launch_counter()
 }
 
 constexpr int kFwdNB = 4;   // images interleaved per forward CTA (one LDS.128 per tap)
-constexpr int kBpNB = 8;    // images interleaved per back-projection CTA
-constexpr int kBpTW = 32, kBpTH = 16, kBpAB = 8, kBpWin = 44;
+constexpr int kBpTW = 32, kBpAB = 8;
 constexpr int kFwdMaxThreads = 768;
 
 __host__ __device__ static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -132,6 +131,7 @@ __global__ void __launch_bounds__(256) ctr_pack_image_kernel(const float* __rest
     }
 }
 
+// [B,A,W] -> [G][A][NB/4 planes][W+2][4]: zero halo bins, 4 images interleaved per 16-byte bin.
 // grid (ceil((W+2)/128), A, G), block 128.
 template <int NB>
 __global__ void __launch_bounds__(128) ctr_pack_sino_kernel(const float* __restrict__ y, int B, int A, int W,
@@ -140,16 +140,17 @@ __global__ void __launch_bounds__(128) ctr_pack_sino_kernel(const float* __restr
     const int jp = blockIdx.x * blockDim.x + threadIdx.x;
     if (jp >= W + 2) return;
     const int a = blockIdx.y, g = blockIdx.z, j = jp - 1;
-    float v[NB];
 #pragma unroll
-    for (int n = 0; n < NB; ++n) {
-        const int b = g * NB + n;
-        v[n] = (b < B && j >= 0 && j < W) ? __ldg(y + ((size_t)b * A + a) * W + j) : 0.f;
+    for (int h = 0; h < NB / 4; ++h) {
+        float v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int b = g * NB + 4 * h + q;
+            v[q] = (b < B && j >= 0 && j < W) ? __ldg(y + ((size_t)b * A + a) * W + j) : 0.f;
+        }
+        float* dst = spk + ((((size_t)g * A + a) * (NB / 4) + h) * (W + 2) + jp) * 4;
+        *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
     }
-    float* dst = spk + (((size_t)g * A + a) * (W + 2) + jp) * NB;
-#pragma unroll
-    for (int q = 0; q < NB / 4; ++q)
-        reinterpret_cast<float4*>(dst)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
 }
 
 // ------------------------------------------------------------------------------------------ K1 forward
@@ -272,7 +273,7 @@ __global__ void __launch_bounds__(kFwdMaxThreads, 1) ctr_fwd_kernel(const FwdPar
 
 // ------------------------------------------------------------------------------------------ K2 / K2' / K3b
 struct BpParams {
-    const float* spk;      // packed sinogram [G][A][W+2][NB]
+    const float* spk;      // packed sinogram [G][A][NB/4][W+2][4]
     const float* table;    // [A][8] forward (EXACT) or inverted (TF) transforms; unused for FBP
     const double* cs;      // [A][2] cos/sin(theta) for FBP
     float* out;            // [B][X][Y]
@@ -281,27 +282,32 @@ struct BpParams {
     float scale;           // 1, or pi/(2A) for FBP
 };
 
-// One CTA = TW x TH pixel tile x image group of NB.  Angles are processed in batches
+// bins a 32 x TH pixel tile can touch for one angle: |u| extent sqrt(31^2+(TH-1)^2) + 6 bins of slack
+__host__ __device__ constexpr int bp_win(int TH) { return TH <= 8 ? 40 : 44; }
+
+// One CTA = 32 x TH pixel tile x image group of NB.  Angles are processed in batches
 // of AB: lanes 0..AB-1 of warp 0 each own one angle of the batch -- they compute the
 // bin window the tile needs, publish its start + the angle's coefficients to shared
-// memory, and issue the window's TMA bulk copy -- while all threads gather from the
-// previous batch.  No atomics anywhere: each thread owns its pixel's NB accumulators.
-template <int NB, int MODE, int INTERP>
-__global__ void __launch_bounds__(kBpTW * kBpTH, 2) ctr_bp_kernel(const BpParams p)
+// memory, and issue the window's TMA bulk copies (one per 4-image plane) -- while all
+// threads gather from the previous batch.  No atomics anywhere: each thread owns its
+// pixel's NB accumulators, and the per-pixel geometry is shared by the NB images.
+template <int NB, int TH, int MINB, int MODE, int INTERP>
+__global__ void __launch_bounds__(kBpTW * TH, MINB) ctr_bp_kernel(const BpParams p)
 {
-    constexpr int TW = kBpTW, TH = kBpTH, AB = kBpAB;
+    constexpr int TW = kBpTW, AB = kBpAB, NBP = NB / 4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);            // [2]
     int* jb = reinterpret_cast<int*>(smem_raw + 16);                   // [2][AB]
     float* tbl = reinterpret_cast<float*>(smem_raw + 128);             // [2][AB][8]
     double* css = reinterpret_cast<double*>(smem_raw + 128 + 2 * AB * 8 * 4);  // [2][AB][2]
-    float* wins = reinterpret_cast<float*>(smem_raw + 128 + 2 * AB * 8 * 4 + 2 * AB * 2 * 8);  // [2][AB][win*NB]
+    float* wins = reinterpret_cast<float*>(smem_raw + 128 + 2 * AB * 8 * 4 + 2 * AB * 2 * 8);  // [2][AB][NBP][win][4]
 
     const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TW + tx;
     const int c0 = blockIdx.x * TW, r0 = blockIdx.y * TH, g = blockIdx.z;
     const int c = c0 + tx, r = r0 + ty;
     const int Wp2 = p.W + 2;
     const int win = p.win;
+    const int pstride = win * 4;
     const int nbatch = (p.A + AB - 1) / AB;
     const float px = (float)(c + p.pady), py = (float)(r + p.padx);
     // FBP pixel coordinates (fbp_tensorflow.py:52-53): x' = row - x_size/2, y' = col - y_size/2
@@ -349,10 +355,12 @@ __global__ void __launch_bounds__(kBpTW * kBpTH, 2) ctr_bp_kernel(const BpParams
         }
         const int start = ctr_window_start(cu[0], cu[1], cu[2], cu[3], Wp2, win);
         jb[s * AB + lane] = start;
-        const uint32_t bytes = (uint32_t)win * NB * 4u;
-        mbar_arrive_expect_tx(bar, bytes);   // release: publishes jb/tbl/css to the waiters
-        bulk_g2s(wins + (size_t)(s * AB + lane) * win * NB,
-                 p.spk + (((size_t)g * p.A + a) * Wp2 + start) * NB, bytes, bar);
+        const uint32_t bytes = (uint32_t)win * 16u;
+        mbar_arrive_expect_tx(bar, bytes * NBP);   // release: publishes jb/tbl/css to the waiters
+#pragma unroll
+        for (int h = 0; h < NBP; ++h)
+            bulk_g2s(wins + ((size_t)(s * AB + lane) * NBP + h) * pstride,
+                     p.spk + ((((size_t)g * p.A + a) * NBP + h) * Wp2 + start) * 4, bytes, bar);
     };
 
     if (tid < AB) {
@@ -369,10 +377,10 @@ __global__ void __launch_bounds__(kBpTW * kBpTH, 2) ctr_bp_kernel(const BpParams
         mbar_wait(&full[s], (uint32_t)((nb >> 1) & 1));
         const int na = min(AB, p.A - nb * AB);
         for (int k = 0; k < na; ++k) {
-            const float* ywin = wins + (size_t)(s * AB + k) * win * NB;
+            const float* ywin = wins + (size_t)(s * AB + k) * NBP * pstride;
             const int start = jb[s * AB + k];
             if (MODE == CTR_ADJ_FBP) {
-                ctr_adj_fbp<NB>(&css[(s * AB + k) * 2], p.W, xpr, ypr, ywin, start, acc);
+                ctr_adj_fbp<NB>(&css[(s * AB + k) * 2], p.W, xpr, ypr, ywin, pstride, start, acc);
             } else {
                 float t[8];
 #pragma unroll
@@ -380,8 +388,8 @@ __global__ void __launch_bounds__(kBpTW * kBpTH, 2) ctr_bp_kernel(const BpParams
                     const float4 tv = reinterpret_cast<const float4*>(tbl + (s * AB + k) * 8)[q];
                     t[4 * q] = tv.x; t[4 * q + 1] = tv.y; t[4 * q + 2] = tv.z; t[4 * q + 3] = tv.w;
                 }
-                if (MODE == CTR_ADJ_EXACT) ctr_adj_exact<NB, INTERP>(t, p.H, p.W, px, py, ywin, start, acc);
-                else ctr_adj_tf<NB, INTERP>(t, p.H, p.W, px, py, ywin, start, acc);
+                if (MODE == CTR_ADJ_EXACT) ctr_adj_exact<NB, INTERP>(t, p.H, p.W, px, py, ywin, pstride, start, acc);
+                else ctr_adj_tf<NB, INTERP>(t, p.H, p.W, px, py, ywin, pstride, start, acc);
             }
         }
         __syncthreads();  // batch buffers free again
@@ -401,6 +409,7 @@ __global__ void __launch_bounds__(kBpTW * kBpTH, 2) ctr_bp_kernel(const BpParams
 // rf[n] = sum_k s[k] * h[(n-k) mod P]  ==  real(ifft(fft(s) * filter_1d))   for real s
 // (fbp_tensorflow.py:49-50; no zero padding, so the convolution is circular).
 // grid (A, G), block 256.  smem: NB rows interleaved [P][NB] + doubled kernel h2[2P].
+// Output goes straight into the plane-layout sinogram pack K3b reads.
 template <int NB>
 __global__ void __launch_bounds__(256) ctr_fbp_filter_kernel(const float* __restrict__ sino, const float* __restrict__ h,
                                                              int B, int A, int P, float* __restrict__ spk)
@@ -416,7 +425,7 @@ __global__ void __launch_bounds__(256) ctr_fbp_filter_kernel(const float* __rest
     }
     for (int m = threadIdx.x; m < 2 * P; m += blockDim.x) h2[m] = __ldg(h + (m >= P ? m - P : m));
     __syncthreads();
-    float* dst_row = spk + ((size_t)g * A + a) * (P + 2) * NB;
+    float* dst_row = spk + ((size_t)g * A + a) * (NB / 4) * (size_t)(P + 2) * 4;
     for (int n_out = threadIdx.x; n_out < P; n_out += blockDim.x) {
         float acc[NB];
 #pragma unroll
@@ -429,15 +438,15 @@ __global__ void __launch_bounds__(256) ctr_fbp_filter_kernel(const float* __rest
 #pragma unroll
             for (int n = 0; n < NB; ++n) acc[n] = fmaf(hv, sv[n], acc[n]);
         }
-        float* dst = dst_row + (size_t)(n_out + 1) * NB;
 #pragma unroll
         for (int q = 0; q < NB / 4; ++q)
-            reinterpret_cast<float4*>(dst)[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+            *reinterpret_cast<float4*>(dst_row + ((size_t)q * (P + 2) + n_out + 1) * 4) =
+                make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
     }
-    if (threadIdx.x < 2) {  // halo bins (never read by the FBP gather; keep them defined)
-        float* dst = dst_row + (size_t)(threadIdx.x ? P + 1 : 0) * NB;
-#pragma unroll
-        for (int n = 0; n < NB; ++n) dst[n] = 0.f;
+    if (threadIdx.x < 2 * (NB / 4)) {  // halo bins (never read by the FBP gather; keep them defined)
+        const int q = threadIdx.x >> 1;
+        *reinterpret_cast<float4*>(dst_row + ((size_t)q * (P + 2) + ((threadIdx.x & 1) ? P + 1 : 0)) * 4) =
+            make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
 
@@ -496,23 +505,36 @@ inline cudaError_t launch_fwd_ka(const FwdParams& p, const FwdConfig& c, int G, 
     return cudaGetLastError();
 }
 
-inline size_t bp_smem_bytes(int win)
+inline size_t bp_smem_bytes(int win, int NB)
 {
-    return 128 + 2 * kBpAB * 8 * 4 + 2 * kBpAB * 2 * 8 + 2ull * kBpAB * (size_t)win * kBpNB * 4;
+    return 128 + 2 * kBpAB * 8 * 4 + 2 * kBpAB * 2 * 8 + 2ull * kBpAB * (size_t)win * NB * 4;
+}
+
+// Two shapes: 16 images per thread on 32x8-pixel tiles for real batches, 8 images on
+// 32x16 tiles when the batch is tiny (fewer idle accumulator lanes).
+inline int bp_nb_for_batch(int B) { return B > 8 ? 16 : 8; }
+inline int bp_th_for_batch(int B) { return B > 8 ? 8 : 16; }
+
+template <int NB, int TH, int MINB, int MODE, int INTERP>
+inline cudaError_t launch_bp_cfg(BpParams p, cudaStream_t st)
+{
+    const int G = (p.B + NB - 1) / NB;
+    dim3 grid((p.Y + kBpTW - 1) / kBpTW, (p.X + TH - 1) / TH, G), block(kBpTW, TH);
+    if (p.win > bp_win(TH)) p.win = bp_win(TH);
+    const size_t smem = bp_smem_bytes(p.win, NB);
+    cudaError_t e = cudaFuncSetAttribute(ctr_bp_kernel<NB, TH, MINB, MODE, INTERP>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    ctr_bp_kernel<NB, TH, MINB, MODE, INTERP><<<grid, block, smem, st>>>(p);
+    launch_counter()++;
+    return cudaGetLastError();
 }
 
 template <int MODE, int INTERP>
 inline cudaError_t launch_bp(const BpParams& p, cudaStream_t st)
 {
-    const int G = (p.B + kBpNB - 1) / kBpNB;
-    dim3 grid((p.Y + kBpTW - 1) / kBpTW, (p.X + kBpTH - 1) / kBpTH, G), block(kBpTW, kBpTH);
-    const size_t smem = bp_smem_bytes(p.win);
-    cudaError_t e = cudaFuncSetAttribute(ctr_bp_kernel<kBpNB, MODE, INTERP>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    ctr_bp_kernel<kBpNB, MODE, INTERP><<<grid, block, smem, st>>>(p);
-    launch_counter()++;
-    return cudaGetLastError();
+    if (bp_nb_for_batch(p.B) == 16) return launch_bp_cfg<16, 8, 3, MODE, INTERP>(p, st);
+    return launch_bp_cfg<8, 16, 2, MODE, INTERP>(p, st);
 }
 
 }  // namespace ctr

@@ -23,7 +23,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from . import _lib, ops
+from . import _lib, hostpipe, ops
 
 __all__ = ["pad_phantom", "project_tf_low_mem", "project_tf_fast", "backproject", "num_proj_pix"]
 
@@ -98,6 +98,11 @@ def _project_bxy(img_bxy: torch.Tensor, theta, pad: bool, interpolation: str, ad
     dev = _compute_device(img_bxy)
     th = ops.theta_to_host(theta)
     plan = _lib.get_plan(th, int(img_bxy.shape[1]), int(img_bxy.shape[2]), bool(pad), dev.index or 0)
+    if hostpipe.eligible(img_bxy):
+        # host (pinned) batch: overlap copy-in / kernels / copy-out chunk by chunk; result stays on the host
+        iid = ops.INTERP[interpolation]
+        return hostpipe.run_chunked(lambda x: ops.radon_forward(x, plan, iid), img_bxy,
+                                    (img_bxy.shape[0], plan.A, plan.W), dev)
     x = img_bxy.to(device=dev, dtype=torch.float32, non_blocking=True)
     return ops.project(x, plan, ops.INTERP[interpolation], ops.ADJOINT[adjoint])
 
@@ -155,6 +160,11 @@ def backproject(sinogram, theta, x_size, y_size, pad=False, *, interpolation="ne
     dev = _compute_device(s3)
     th = ops.theta_to_host(theta)
     plan = _lib.get_plan(th, int(x_size), int(y_size), bool(pad), dev.index or 0)
+    if hostpipe.eligible(s3):
+        iid, mid = ops.INTERP[interpolation], ops.ADJOINT[adjoint]
+        g = hostpipe.run_chunked(lambda y: ops.radon_adjoint(y, plan, iid, mid), s3,
+                                 (s3.shape[0], int(x_size), int(y_size)), dev)
+        return _finish(g.unsqueeze(-1) if squeeze else g, t, was_numpy)
     y = s3.to(device=dev, dtype=torch.float32)
     g = ops.radon_adjoint(y, plan, ops.INTERP[interpolation], ops.ADJOINT[adjoint])
     return _finish(g.unsqueeze(-1) if squeeze else g, t, was_numpy)

@@ -34,15 +34,19 @@ void pack_images(const float* img, int B, int X, int Y, std::vector<float>& pk0,
     }
 }
 
-// [G][A][W+2][NB] with zero halo bins (mirrors ctr_pack_sino_kernel).
+// [G][A][NB/4 planes][W+2][4] with zero halo bins (mirrors ctr_pack_sino_kernel).
+template <int NBP>
 void pack_sino(const float* y, int B, int A, int W, std::vector<float>& spk)
 {
-    const int G = (B + NB - 1) / NB;
-    spk.assign((size_t)G * A * (W + 2) * NB, 0.f);
+    const int G = (B + NBP - 1) / NBP;
+    spk.assign((size_t)G * A * (W + 2) * NBP, 0.f);
     for (int b = 0; b < B; ++b)
         for (int a = 0; a < A; ++a)
-            for (int j = 0; j < W; ++j)
-                spk[(((size_t)(b / NB) * A + a) * (W + 2) + j + 1) * NB + (b % NB)] = y[((size_t)b * A + a) * W + j];
+            for (int j = 0; j < W; ++j) {
+                const int n = b % NBP;
+                spk[((((size_t)(b / NBP) * A + a) * (NBP / 4) + n / 4) * (W + 2) + j + 1) * 4 + (n % 4)] =
+                    y[((size_t)b * A + a) * W + j];
+            }
 }
 
 template <int INTERP>
@@ -84,12 +88,13 @@ void forward_impl(const float* img, int B, int X, int Y, int H, int W, int padx,
     }
 }
 
-template <int MODE, int INTERP>
+template <int MODE, int INTERP, int NBA>
 void adjoint_impl(const float* y, int B, int X, int Y, int H, int W, int padx, int pady,
                   const float* table, int A, int TW, int TH, int win, float* out)
 {
+    constexpr int NB = NBA;  // images per back-projection CTA (shadows the forward's NB)
     std::vector<float> spk;
-    pack_sino(y, B, A, W, spk);
+    pack_sino<NB>(y, B, A, W, spk);
     const int G = (B + NB - 1) / NB;
     const int Wp2 = W + 2;
     const int winc = std::min(win, Wp2);
@@ -113,16 +118,20 @@ void adjoint_impl(const float* y, int B, int X, int Y, int H, int W, int padx, i
                     const int start = ctr_window_start(cu[0], cu[1], cu[2], cu[3], Wp2, winc);
                     // NaN guard zones either side: an out-of-window read poisons the output
                     constexpr int GUARD = 16;
-                    std::vector<float> ywin_buf((size_t)(winc + 2 * GUARD) * NB, std::nanf(""));
-                    float* ywin_p = ywin_buf.data() + (size_t)GUARD * NB;
-                    std::memcpy(ywin_p, spk.data() + (((size_t)g * A + a) * Wp2 + start) * NB,
-                                sizeof(float) * winc * NB);
+                    // one bulk copy per plane; planes sit pstride floats apart in shared memory
+                    const int pstride = (winc + 2 * GUARD) * 4;
+                    std::vector<float> ywin_buf((size_t)pstride * (NB / 4), std::nanf(""));
+                    float* ywin_p = ywin_buf.data() + (size_t)GUARD * 4;
+                    for (int h = 0; h < NB / 4; ++h)
+                        std::memcpy(ywin_p + (size_t)h * pstride,
+                                    spk.data() + ((((size_t)g * A + a) * (NB / 4) + h) * Wp2 + start) * 4,
+                                    sizeof(float) * winc * 4);
                     for (int ty = 0; ty < TH; ++ty)
                         for (int tx = 0; tx < TW; ++tx) {
                             const float px = (float)(c0 + tx + pady), py = (float)(r0 + ty + padx);
                             float* ac = &acc[((size_t)ty * TW + tx) * NB];
-                            if (MODE == CTR_ADJ_EXACT) ctr_adj_exact<NB, INTERP>(t, H, W, px, py, ywin_p, start, ac);
-                            else ctr_adj_tf<NB, INTERP>(t, H, W, px, py, ywin_p, start, ac);
+                            if (MODE == CTR_ADJ_EXACT) ctr_adj_exact<NB, INTERP>(t, H, W, px, py, ywin_p, pstride, start, ac);
+                            else ctr_adj_tf<NB, INTERP>(t, H, W, px, py, ywin_p, pstride, start, ac);
                         }
                 }
                 for (int ty = 0; ty < TH; ++ty)
@@ -156,12 +165,13 @@ void emu_forward(const float* img, int B, int X, int Y, int H, int W, int padx, 
 void emu_adjoint(const float* y, int B, int X, int Y, int H, int W, int padx, int pady, const float* table, int A,
                  int interp, int mode, int TW, int TH, int win, float* out)
 {
+    constexpr int NBA = 16;
     if (mode == CTR_ADJ_EXACT) {
-        if (interp == CTR_NEAREST) adjoint_impl<CTR_ADJ_EXACT, CTR_NEAREST>(y, B, X, Y, H, W, padx, pady, table, A, TW, TH, win, out);
-        else adjoint_impl<CTR_ADJ_EXACT, CTR_BILINEAR>(y, B, X, Y, H, W, padx, pady, table, A, TW, TH, win, out);
+        if (interp == CTR_NEAREST) adjoint_impl<CTR_ADJ_EXACT, CTR_NEAREST, NBA>(y, B, X, Y, H, W, padx, pady, table, A, TW, TH, win, out);
+        else adjoint_impl<CTR_ADJ_EXACT, CTR_BILINEAR, NBA>(y, B, X, Y, H, W, padx, pady, table, A, TW, TH, win, out);
     } else {
-        if (interp == CTR_NEAREST) adjoint_impl<CTR_ADJ_TF, CTR_NEAREST>(y, B, X, Y, H, W, padx, pady, table, A, TW, TH, win, out);
-        else adjoint_impl<CTR_ADJ_TF, CTR_BILINEAR>(y, B, X, Y, H, W, padx, pady, table, A, TW, TH, win, out);
+        if (interp == CTR_NEAREST) adjoint_impl<CTR_ADJ_TF, CTR_NEAREST, NBA>(y, B, X, Y, H, W, padx, pady, table, A, TW, TH, win, out);
+        else adjoint_impl<CTR_ADJ_TF, CTR_BILINEAR, NBA>(y, B, X, Y, H, W, padx, pady, table, A, TW, TH, win, out);
     }
 }
 

@@ -189,6 +189,22 @@ def test_fbp_reconstructs_disk(cp):
     assert abs(rec[inner].mean() - 0.8) < 0.01
 
 
+def test_pinned_host_batch_goes_through_the_chunked_pipeline(cp, orc):
+    """B >= 32 pinned float32 host batch: copy-in / kernels / copy-out overlap chunk by chunk."""
+    rng = np.random.default_rng(8)
+    B, X, A = 70, 24, 9
+    th = _theta(A)
+    img = rng.random((B, X, X), dtype=np.float32)
+    img_h = torch.from_numpy(img).unsqueeze(-1).pin_memory()
+    s = cp.project_tf_fast(img_h, th, pad=True, dim=2, integrate_vae=True, interpolation="bilinear")
+    assert s.device.type == "cpu" and s.is_pinned() and s.shape[:2] == (B, A)
+    want = orc.forward(img, th, True, 1)
+    assert rel_l2(s[..., 0].numpy(), want) <= TOL
+    cot = rng.random(want.shape, dtype=np.float32)
+    g = cp.backproject(torch.from_numpy(cot).pin_memory(), th, X, X, pad=True, interpolation="bilinear")
+    assert g.device.type == "cpu" and rel_l2(g.numpy(), orc.adjoint_exact(cot, th, X, X, True, 1)) <= TOL
+
+
 def test_golden_fixtures(cp):
     import os
 

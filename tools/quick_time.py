@@ -46,7 +46,28 @@ def run(B, X, A, tag):
     print(f"{tag} fbp: {best:8.3f} ms (med {med:8.3f})  {upd / best / 1e6:8.2f} G updates/s", flush=True)
 
 
+def pcie():
+    n = 64 << 20
+    h = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    d = torch.empty(n, dtype=torch.uint8, device="cuda")
+    s2 = torch.cuda.Stream()
+    for name, fn in (("H2D", lambda: d.copy_(h, non_blocking=True)), ("D2H", lambda: h.copy_(d, non_blocking=True))):
+        best, med = timeit(fn, iters=5, warm=2)
+        print(f"PCIe {name}: {n / best / 1e6:.1f} GB/s", flush=True)
+    h2 = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    d2 = torch.empty(n, dtype=torch.uint8, device="cuda")
+    def both():
+        s2.wait_stream(torch.cuda.current_stream())
+        d.copy_(h, non_blocking=True)
+        with torch.cuda.stream(s2):
+            h2.copy_(d2, non_blocking=True)
+        torch.cuda.current_stream().wait_stream(s2)
+    best, med = timeit(both, iters=5, warm=2)
+    print(f"PCIe duplex: {2 * n / best / 1e6:.1f} GB/s aggregate", flush=True)
+
+
 if __name__ == "__main__":
     print(torch.cuda.get_device_name(0))
+    pcie()
     run(256, 128, 180, "C2")
     run(64, 512, 720, "C4")

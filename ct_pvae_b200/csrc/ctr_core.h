@@ -94,6 +94,40 @@ CTR_HD float ctr_round(float v)
     return r;
 }
 
+// floor / round-half-away of a coordinate as (float, int) in one go.  On the device the
+// 1.5*2^23 trick does it on the FP32 pipe (no FRND/F2I on the quarter-rate conversion
+// unit): v + 12582912 rounded down (resp. to nearest-even) leaves the integer in the
+// mantissa.  Exact for |v| < 2^22, far beyond any frame coordinate.
+#define CTR_MAGIC 12582912.0f
+#define CTR_MAGIC_BITS 0x4B400000
+CTR_HD void ctr_floor_fi(float v, float& f, int& i)
+{
+#if defined(__CUDA_ARCH__)
+    const float t = __fadd_rd(v, CTR_MAGIC);
+    f = __fsub_rn(t, CTR_MAGIC);
+    i = __float_as_int(t) - CTR_MAGIC_BITS;
+#else
+    f = floorf(v);
+    i = (int)f;
+#endif
+}
+CTR_HD void ctr_round_fi(float v, float& f, int& i)
+{
+#if defined(__CUDA_ARCH__)
+    const float t = __fadd_rn(v, CTR_MAGIC);   // nearest-even
+    float r = __fsub_rn(t, CTR_MAGIC);
+    int k = __float_as_int(t) - CTR_MAGIC_BITS;
+    const float d = __fsub_rn(v, r);            // exact
+    if (d == 0.5f && v > 0.f) { r += 1.f; k += 1; }     // ties go away from zero (std::round)
+    if (d == -0.5f && v < 0.f) { r -= 1.f; k -= 1; }
+    f = r;
+    i = k;
+#else
+    f = ctr_round(v);
+    i = (int)f;
+#endif
+}
+
 // Smallest i in [0,H] with sgn*coord(i) > bound (strict) or >= bound.  float32
 // rounding is monotone, so coord(i) is monotone in i and the predicate flips once.
 CTR_HD int ctr_search(float p0j, float c1, float c2, float sgn, float bound, bool strict, int H)
@@ -124,10 +158,12 @@ CTR_HD void ctr_ray_interval(const CtrRay& r, const CtrClassGeom& g, int j, int 
     if (ie < ib) ie = ib;
 }
 
-// A ray in flight: next step, steps left, direction of travel (towards larger v).
+// A ray in flight: next step (kept as a float: integers < 2^24 are exact and the
+// coordinate needs it as a float anyway), steps left, direction of travel (towards larger v).
 struct CtrRayState {
     float pu, pv;  // u0*j, v0*j
-    int i, n, di;
+    float fi, dfi; // next step i and +-1
+    int n;
 };
 
 CTR_HD void ctr_ray_begin(const CtrRay& r, const CtrClassGeom& g, int j, int H, CtrRayState& s)
@@ -137,8 +173,8 @@ CTR_HD void ctr_ray_begin(const CtrRay& r, const CtrClassGeom& g, int j, int H, 
     s.pu = CTR_MUL(r.u0, (float)j);
     s.pv = CTR_MUL(r.v0, (float)j);
     s.n = ie - ib;
-    s.di = (r.v1 >= 0.f) ? 1 : -1;
-    s.i = (s.di > 0) ? ib : ie - 1;
+    s.dfi = (r.v1 >= 0.f) ? 1.f : -1.f;
+    s.fi = (float)((r.v1 >= 0.f) ? ib : ie - 1);
 }
 
 // March one ray through one strip.  `strip` holds packed rows [row0p, row0p+rows)
@@ -152,34 +188,35 @@ CTR_HD void ctr_march(const float* __restrict__ strip, int Up, float vend, int r
                       const CtrRay& r, CtrRayState& s, float* __restrict__ acc)
 {
     while (s.n > 0) {
-        const float fi = (float)s.i;
-        const float u = ctr_coord(s.pu, r.u1, fi, r.u2);
-        const float v = ctr_coord(s.pv, r.v1, fi, r.v2);
+        const float u = ctr_coord(s.pu, r.u1, s.fi, r.u2);
+        const float v = ctr_coord(s.pv, r.v1, s.fi, r.v2);
+        float kvf, kuf;
+        int kvi, kui;
         if (INTERP == CTR_NEAREST) {
-            const float kv = ctr_round(v);
-            if (kv >= vend) break;
-            const float ku = ctr_round(u);
+            ctr_round_fi(v, kvf, kvi);
+            if (kvf >= vend) break;
+            ctr_round_fi(u, kuf, kui);
             float a[NB];
-            ctr_ldv<NB>(strip + ((size_t)((int)kv - rbase) * Up + ((int)ku - offu)) * NB, a);
+            ctr_ldv<NB>(strip + ((kvi - rbase) * Up + (kui - offu)) * NB, a);
 #pragma unroll
             for (int q = 0; q < NB; ++q) acc[q] += a[q];
         } else {
-            const float kv = floorf(v);
-            if (kv >= vend) break;
-            const float ku = floorf(u);
-            const float fu = CTR_SUB(u, ku), gu = CTR_SUB(CTR_ADD(ku, 1.f), u);
-            const float fv = CTR_SUB(v, kv), gv = CTR_SUB(CTR_ADD(kv, 1.f), v);
+            ctr_floor_fi(v, kvf, kvi);
+            if (kvf >= vend) break;
+            ctr_floor_fi(u, kuf, kui);
+            const float fu = CTR_SUB(u, kuf), gu = CTR_SUB(CTR_ADD(kuf, 1.f), u);
+            const float fv = CTR_SUB(v, kvf), gv = CTR_SUB(CTR_ADD(kvf, 1.f), v);
             const float w00 = gv * gu, w01 = gv * fu, w10 = fv * gu, w11 = fv * fu;
-            const float* p0 = strip + ((size_t)((int)kv - rbase) * Up + ((int)ku - offu)) * NB;
-            const float* p1 = p0 + (size_t)Up * NB;
+            const float* p0 = strip + ((kvi - rbase) * Up + (kui - offu)) * NB;
+            const float* p1 = p0 + Up * NB;
             float a00[NB], a01[NB], a10[NB], a11[NB];
             ctr_ldv<NB>(p0, a00); ctr_ldv<NB>(p0 + NB, a01);
             ctr_ldv<NB>(p1, a10); ctr_ldv<NB>(p1 + NB, a11);
 #pragma unroll
             for (int q = 0; q < NB; ++q)
-                acc[q] += w00 * a00[q] + w01 * a01[q] + w10 * a10[q] + w11 * a11[q];
+                acc[q] = fmaf(w11, a11[q], fmaf(w10, a10[q], fmaf(w01, a01[q], fmaf(w00, a00[q], acc[q]))));
         }
-        s.i += s.di;
+        s.fi += s.dfi;
         --s.n;
     }
 }

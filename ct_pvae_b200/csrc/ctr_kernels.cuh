@@ -18,6 +18,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -216,17 +217,18 @@ __global__ void __launch_bounds__(kFwdMaxThreads, 1) ctr_fwd_kernel(const FwdPar
 
     // per-ray state: next step and steps left (coefficients are re-read from smem per strip)
     const int j = blockIdx.z * JW + tx;
-    int ri[KA], rn[KA];
+    float ri[KA];
+    int rn[KA];
     float acc[KA][NB];
 #pragma unroll
     for (int q = 0; q < KA; ++q) {
         const int la = ty * KA + q;
-        ri[q] = 0;
+        ri[q] = 0.f;
         rn[q] = 0;
         if (la < cnt && j < p.W) {
             CtrRayState s;
             ctr_ray_begin(rays_s[la], geom, j, p.H, s);
-            ri[q] = s.i;
+            ri[q] = s.fi;
             rn[q] = s.n;
         }
 #pragma unroll
@@ -245,11 +247,11 @@ __global__ void __launch_bounds__(kFwdMaxThreads, 1) ctr_fwd_kernel(const FwdPar
                 CtrRayState s;
                 s.pu = CTR_MUL(r.u0, (float)j);
                 s.pv = CTR_MUL(r.v0, (float)j);
-                s.i = ri[q];
+                s.fi = ri[q];
                 s.n = rn[q];
-                s.di = (r.v1 >= 0.f) ? 1 : -1;
+                s.dfi = (r.v1 >= 0.f) ? 1.f : -1.f;
                 ctr_march<NB, INTERP>(strip, geom.Up, vend, rbase, geom.offu, r, s, acc[q]);
-                ri[q] = s.i;
+                ri[q] = s.fi;
                 rn[q] = s.n;
             }
         }
@@ -464,10 +466,18 @@ inline FwdConfig fwd_config(int W, const CtrClassGeom geom[2], int smem_budget)
     c.JW = round_up(W, 32);
     if (c.JW > kFwdMaxThreads) c.JW = kFwdMaxThreads;
     c.jchunks = (W + c.JW - 1) / c.JW;
-    c.NS = kFwdMaxThreads / c.JW;
-    if (c.NS > 8) c.NS = 8;
-    if (c.NS < 1) c.NS = 1;
-    c.KA = (c.NS == 1) ? 4 : (c.NS == 2 ? 2 : 1);
+    // r1 sweep (tools/sweep_fwd.py): several small CTAs per SM beat one big one (their
+    // strip barriers and ragged ray ends overlap), so one angle slot per CTA unless the
+    // detector is tiny, two angles per thread, and the shared memory split 4 / 2 / 1 ways.
+    c.NS = (c.JW >= 128) ? 1 : 128 / c.JW;
+    c.KA = 2;
+    const int threads = c.JW * c.NS;
+    const int ctas_per_sm = threads <= 256 ? 4 : (threads <= 512 ? 2 : 1);
+    if (smem_budget > (228 * 1024) / ctas_per_sm - 1024) smem_budget = (228 * 1024) / ctas_per_sm - 1024;
+    // developer overrides for tuning sweeps (tools/sweep_fwd.py); not part of the API
+    if (const char* e = getenv("CTR_FWD_NS")) { int v = atoi(e); if (v >= 1 && v * c.JW <= kFwdMaxThreads) c.NS = v; }
+    if (const char* e = getenv("CTR_FWD_KA")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4) c.KA = v; }
+    if (const char* e = getenv("CTR_FWD_SMEM")) { int v = atoi(e); if (v >= 16384 && v < smem_budget) smem_budget = v; }
     const int NA = c.NS * c.KA;
     const int fixed = 128 + round_up(NA * (int)sizeof(CtrRay), 128);
     const int Upmax = geom[0].Up > geom[1].Up ? geom[0].Up : geom[1].Up;
@@ -476,6 +486,7 @@ inline FwdConfig fwd_config(int W, const CtrClassGeom geom[2], int smem_budget)
     int rows = (smem_budget - fixed) / (2 * row_bytes);   // rows per buffer = R + 1
     if (rows > Vpmax) rows = Vpmax;
     if (rows > 33) rows = 33;   // bigger strips only lengthen the un-overlapped first load
+    if (const char* e = getenv("CTR_FWD_R")) { int v = atoi(e); if (v >= 1 && v + 1 <= rows) rows = v + 1; }
     c.R = rows - 1;
     if (c.R < 1) c.R = 0;  // caller treats 0 as "image too wide for the strip buffers"
     c.smem = (size_t)fixed + 2ull * (size_t)(c.R + 1) * row_bytes;

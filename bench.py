@@ -221,6 +221,8 @@ def run_ours(args, wl):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
 
     B, X, A = wl["B"], wl["X"], wl["A"]
@@ -285,6 +287,34 @@ def run_ours(args, wl):
     units_per_step = B * A * P * (1 if angle_mode else world)   # whole-job ray-sums per step
     value = units_per_step / (ms_per_step * 1e-3) / 1e9
 
+    # ---- side legs (reported under "extra", not part of the headline step): the reference's
+    # default nearest mode, TF-compatible gradient, and the FBP evaluation pass on the same batch
+    def best_ms(fn, iters=5):
+        fn()
+        torch.cuda.synchronize(dev)
+        ts = []
+        for _ in range(iters):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize(dev)
+            ts.append(a.elapsed_time(b))
+        return float(np.median(ts))
+
+    side = {}
+    if rank == 0 and not args.no_side_legs:
+        nid = ops.INTERP["nearest"]
+        side["fwd_nearest_ms"] = best_ms(lambda: ops.radon_forward(img, plan, nid))
+        side["adj_exact_nearest_ms"] = best_ms(lambda: ops.radon_adjoint(cot, plan, nid, mid))
+        side["adj_tf_compat_bilinear_ms"] = best_ms(lambda: ops.radon_adjoint(cot, plan, iid, ops.ADJOINT["tf_compat"]))
+        fplan = _lib.get_fbp_plan(theta_local, P, X, X, cp.get_fourier_filter(P, "ramp"), local)
+        side["fbp_ms"] = best_ms(lambda: ops.fbp(cot, fplan))
+        side["fbp_gupdates_per_s"] = B * A_loc * X * X / (side["fbp_ms"] * 1e-3) / 1e9
+        side["fwd_nearest_gray_sums_per_s"] = B * A_loc * P / (side["fwd_nearest_ms"] * 1e-3) / 1e9
+    sync_all()
+
     # ---- e2e: the public API with pinned HOST buffers, copies inside the timed region
     img_h = img.cpu().unsqueeze(-1).pin_memory()
     cot_h = cot.cpu().pin_memory()
@@ -320,6 +350,7 @@ def run_ours(args, wl):
         smem_peak = 148 * 128 * sm_hz * 1e6 / 1e9     # GB/s of shared-memory reads at the sampled clock
         extra = {
             "kernels": kern,
+            "side_legs": side,
             "fwd_gray_sums_per_s": (B * A_loc * P / (fwd_ms * 1e-3) / 1e9) if fwd_ms else None,
             "adjoint_gupdates_per_s": (B * A_loc * X * X / (adj_ms * 1e-3) / 1e9) if adj_ms else None,
             # binding on-chip limit of the forward gather: 16 B of shared memory per in-support bilinear sample
@@ -363,6 +394,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--shard", default="batch", choices=["batch", "angle"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-side-legs", action="store_true")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -251,6 +251,10 @@ CTR_HD void ctr_adj_exact(const float* t, int H, int W, float px, float py,
     uj = fminf(fmaxf(uj, 0.f), (float)(W - 1));
     vi = fminf(fmaxf(vi, 0.f), (float)(H - 1));
     const int j0 = (int)rintf(uj), i0 = (int)rintf(vi);
+    // nearest: std::round(x) == px  <=>  x in [px-0.5, px+0.5)  (px >= 1), (-0.5, 0.5) for px == 0;
+    // both bounds are exact floats, so the test needs no rounding at all
+    const float lox = (px >= 1.f) ? px - 0.5f : -0.49999997f, hix = px + 0.5f;
+    const float loy = (py >= 1.f) ? py - 0.5f : -0.49999997f, hiy = py + 0.5f;
 #pragma unroll
     for (int dj = -1; dj <= 1; ++dj) {
         const int j = j0 + dj;
@@ -265,7 +269,7 @@ CTR_HD void ctr_adj_exact(const float* t, int H, int W, float px, float py,
             const float y = ctr_coord(p0y, t[4], fi, t[5]);
             float w;
             if (INTERP == CTR_NEAREST) {
-                w = (ctr_round(x) == px && ctr_round(y) == py) ? 1.f : 0.f;
+                w = (x >= lox && x < hix && y >= loy && y < hiy) ? 1.f : 0.f;
             } else {
                 const float wx = fmaxf(0.f, CTR_SUB(1.f, fabsf(CTR_SUB(x, px))));
                 const float wy = fmaxf(0.f, CTR_SUB(1.f, fabsf(CTR_SUB(y, py))));
@@ -289,10 +293,13 @@ CTR_HD void ctr_adj_tf(const float* ti, int H, int W, float px, float py,
     const float x = CTR_ADD(CTR_ADD(CTR_MUL(ti[0], px), CTR_MUL(ti[1], py)), ti[2]);
     const float y = CTR_ADD(CTR_ADD(CTR_MUL(ti[3], px), CTR_MUL(ti[4], py)), ti[5]);
     if (INTERP == CTR_NEAREST) {
-        const float jj = ctr_round(x), ii = ctr_round(y);
-        if (ii >= 0.f && ii < (float)H && jj >= 0.f && jj < (float)W) {
+        float jj, ii;
+        int jji, iii;
+        ctr_round_fi(x, jj, jji);
+        ctr_round_fi(y, ii, iii);
+        if (iii >= 0 && iii < H && jji >= 0 && jji < W) {
             float yv[NB];
-            ctr_ld_bins<NB>(ywin, pstride, (int)jj + 1 - jbase_p, yv);
+            ctr_ld_bins<NB>(ywin, pstride, jji + 1 - jbase_p, yv);
 #pragma unroll
             for (int q = 0; q < NB; ++q) acc[q] += yv[q];
         }

@@ -8,5 +8,6 @@ The kernels live in ``csrc/`` and are reached through the C ABI of
 """
 from .forward_functions import backproject, num_proj_pix, pad_phantom, project_tf_fast, project_tf_low_mem  # noqa: F401
 from .fbp_tensorflow import get_fourier_filter, iradon  # noqa: F401
+from .likelihood import calculate_log_prob_M_given_R, log_prob_M_given_R_sum  # noqa: F401
 
 __version__ = "0.1.0"

@@ -47,6 +47,10 @@ SYMBOLS = {
     "ctr_adjoint_workspace_bytes": (_c_size_t, [_c_void_p, _c_int]),
     "ctr_radon_forward": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_size_t, _c_void_p]),
     "ctr_radon_adjoint": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_size_t, _c_void_p]),
+    "ctr_radon_adjoint_scaled": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, ctypes.c_float, _c_void_p, _c_size_t, _c_void_p]),
+    "ctr_loglik_workspace_bytes": (_c_size_t, [_c_void_p, _c_int]),
+    "ctr_radon_loglik": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, ctypes.c_float, ctypes.c_float,
+                                  _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_size_t, _c_void_p]),
     "ctr_fbp_plan_create": (_c_int, [_f64p, _c_int, _c_int, _c_int, _c_int, _f64p, _f64p, _c_int, ctypes.POINTER(_c_void_p)]),
     "ctr_fbp_plan_destroy": (_c_int, [_c_void_p]),
     "ctr_fbp_workspace_bytes": (_c_size_t, [_c_void_p, _c_int]),
@@ -161,6 +165,9 @@ class Plan:
 
     def forward_workspace_bytes(self, B: int) -> int:
         return int(lib().ctr_forward_workspace_bytes(self.handle, B))
+
+    def loglik_workspace_bytes(self, B: int) -> int:
+        return int(lib().ctr_loglik_workspace_bytes(self.handle, B))
 
     def adjoint_workspace_bytes(self, B: int) -> int:
         return int(lib().ctr_adjoint_workspace_bytes(self.handle, B))

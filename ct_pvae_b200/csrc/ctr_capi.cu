@@ -286,14 +286,27 @@ size_t ctr_adjoint_workspace_bytes(const ctr_plan* p, int B)
 }
 
 // ------------------------------------------------------------------------------------------ forward
-int ctr_radon_forward(const ctr_plan* p, const float* img, float* sino, int B, int interp, void* ws, size_t ws_bytes,
-                      void* stream)
+struct LoglikArgs {
+    const float* mask; const float* meas; const int* amap; int A_all; float pnm, sqrt_reg; float* loglik;
+};
+
+static size_t loglik_partial_bytes(const ctr_plan* p, int B)
 {
-    if (!p || !img || !sino) return fail(CTR_EINVAL, "ctr_radon_forward: NULL plan or buffer");
-    if (B <= 0) return fail(CTR_EINVAL, "ctr_radon_forward: B must be positive");
-    if (interp != CTR_INTERP_NEAREST && interp != CTR_INTERP_BILINEAR) return fail(CTR_EINVAL, "ctr_radon_forward: bad interp");
-    if (!ws || ws_bytes < ctr_forward_workspace_bytes(p, B)) return fail(CTR_EWORKSPACE, "ctr_radon_forward: workspace too small");
-    if (((uintptr_t)ws & 255) != 0) return fail(CTR_EINVAL, "ctr_radon_forward: workspace must be 256-byte aligned");
+    const int NA = p->fc.NS * p->fc.KA;
+    const size_t chunks = (size_t)(p->n_cls[0] + NA - 1) / NA + (size_t)(p->n_cls[1] + NA - 1) / NA;
+    const size_t G = (size_t)(B + ctr::kFwdNB - 1) / ctr::kFwdNB;
+    return align_up(chunks * p->fc.jchunks * G * ctr::kFwdNB * sizeof(float), 256);
+}
+
+static int forward_impl(const ctr_plan* p, const float* img, float* out, int B, int interp, const LoglikArgs* ll,
+                        void* ws, size_t ws_bytes, void* stream, const char* who)
+{
+    if (!p || !img || !out) return fail(CTR_EINVAL, std::string(who) + ": NULL plan or buffer");
+    if (B <= 0) return fail(CTR_EINVAL, std::string(who) + ": B must be positive");
+    if (interp != CTR_INTERP_NEAREST && interp != CTR_INTERP_BILINEAR) return fail(CTR_EINVAL, std::string(who) + ": bad interp");
+    const size_t need = ll ? ctr_loglik_workspace_bytes(p, B) : ctr_forward_workspace_bytes(p, B);
+    if (!ws || ws_bytes < need) return fail(CTR_EWORKSPACE, std::string(who) + ": workspace too small");
+    if (((uintptr_t)ws & 255) != 0) return fail(CTR_EINVAL, std::string(who) + ": workspace must be 256-byte aligned");
     DeviceGuard guard(p->device);
     if (!guard.ok) return fail_cuda(guard.err, "cudaSetDevice");
     cudaStream_t st = (cudaStream_t)stream;
@@ -317,20 +330,62 @@ int ctr_radon_forward(const ctr_plan* p, const float* img, float* sino, int B, i
     const int chunks = fp.chunks0 + (p->n_cls[1] + NA - 1) / NA;
     fp.H = p->H; fp.W = p->W; fp.A = p->A; fp.B = B;
     fp.R = p->fc.R;
-    fp.sino = sino;
+    fp.sino = out;
+    fp.mask = nullptr; fp.meas = nullptr; fp.amap = nullptr; fp.A_all = p->A; fp.pnm = 1.f; fp.sqrt_reg = 0.f; fp.partial = nullptr;
     cudaError_t e;
+    if (!ll) {
+        ProfScope prof(CTR_K_FORWARD, st);
+        e = (interp == CTR_INTERP_NEAREST) ? ctr::launch_fwd_ka<CTR_NEAREST, 0>(fp, p->fc, G, chunks, st)
+                                           : ctr::launch_fwd_ka<CTR_BILINEAR, 0>(fp, p->fc, G, chunks, st);
+        if (e != cudaSuccess) return fail_cuda(e, "ctr_fwd_kernel launch");
+        return CTR_OK;
+    }
+    fp.mask = ll->mask; fp.meas = ll->meas; fp.amap = ll->amap; fp.A_all = ll->A_all; fp.pnm = ll->pnm; fp.sqrt_reg = ll->sqrt_reg;
+    fp.partial = (float*)((char*)ws + 2 * pack_bytes(p, B));
     {
         ProfScope prof(CTR_K_FORWARD, st);
-        e = (interp == CTR_INTERP_NEAREST) ? ctr::launch_fwd_ka<CTR_NEAREST>(fp, p->fc, G, chunks, st)
-                                           : ctr::launch_fwd_ka<CTR_BILINEAR>(fp, p->fc, G, chunks, st);
+        e = (interp == CTR_INTERP_NEAREST) ? ctr::launch_fwd_ka<CTR_NEAREST, 1>(fp, p->fc, G, chunks, st)
+                                           : ctr::launch_fwd_ka<CTR_BILINEAR, 1>(fp, p->fc, G, chunks, st);
     }
-    if (e != cudaSuccess) return fail_cuda(e, "ctr_fwd_kernel launch");
+    if (e != cudaSuccess) return fail_cuda(e, "ctr_fwd_kernel<loglik> launch");
+    ctr::ctr_loglik_reduce_kernel<<<(B + 127) / 128, 128, 0, st>>>(fp.partial, chunks * p->fc.jchunks, G * ctr::kFwdNB, B, ll->loglik);
+    ctr::launch_counter()++;
+    CTR_CUDA(cudaGetLastError());
     return CTR_OK;
+}
+
+int ctr_radon_forward(const ctr_plan* p, const float* img, float* sino, int B, int interp, void* ws, size_t ws_bytes,
+                      void* stream)
+{
+    return forward_impl(p, img, sino, B, interp, nullptr, ws, ws_bytes, stream, "ctr_radon_forward");
+}
+
+size_t ctr_loglik_workspace_bytes(const ctr_plan* p, int B)
+{
+    if (!p || B <= 0) return 0;
+    return 2 * pack_bytes(p, B) + loglik_partial_bytes(p, B);
+}
+
+int ctr_radon_loglik(const ctr_plan* p, const float* img, const float* mask, const float* meas, const int* angle_map,
+                     int A_all, float pnm, float sqrt_reg, float* loglik, float* dproj, int B, int interp, void* ws,
+                     size_t ws_bytes, void* stream)
+{
+    if (!mask || !meas || !loglik) return fail(CTR_EINVAL, "ctr_radon_loglik: NULL mask, measurement or output");
+    if (A_all < (p ? p->A : 0) && !angle_map) return fail(CTR_EINVAL, "ctr_radon_loglik: A_all smaller than the plan's angle count");
+    if (!(pnm > 0.f) || !(sqrt_reg >= 0.f)) return fail(CTR_EINVAL, "ctr_radon_loglik: pnm must be > 0 and sqrt_reg >= 0");
+    LoglikArgs ll{mask, meas, angle_map, A_all, pnm, sqrt_reg, loglik};
+    return forward_impl(p, img, dproj, B, interp, &ll, ws, ws_bytes, stream, "ctr_radon_loglik");
 }
 
 // ------------------------------------------------------------------------------------------ adjoint
 int ctr_radon_adjoint(const ctr_plan* p, const float* dsino, float* dimg, int B, int interp, int mode, void* ws,
                       size_t ws_bytes, void* stream)
+{
+    return ctr_radon_adjoint_scaled(p, dsino, dimg, B, interp, mode, 1.0f, ws, ws_bytes, stream);
+}
+
+int ctr_radon_adjoint_scaled(const ctr_plan* p, const float* dsino, float* dimg, int B, int interp, int mode, float scale,
+                             void* ws, size_t ws_bytes, void* stream)
 {
     if (!p || !dsino || !dimg) return fail(CTR_EINVAL, "ctr_radon_adjoint: NULL plan or buffer");
     if (B <= 0) return fail(CTR_EINVAL, "ctr_radon_adjoint: B must be positive");
@@ -359,7 +414,7 @@ int ctr_radon_adjoint(const ctr_plan* p, const float* dsino, float* dimg, int B,
     bp.out = dimg;
     bp.B = B; bp.A = p->A; bp.X = p->X; bp.Y = p->Y; bp.H = p->H; bp.W = p->W; bp.padx = p->padx; bp.pady = p->pady;
     bp.win = p->W + 2;   // clamped to the tile's window size by the launcher
-    bp.scale = 1.f;
+    bp.scale = scale;
     cudaError_t e;
     ProfScope prof(mode == CTR_ADJOINT_EXACT ? CTR_K_ADJ_EXACT : CTR_K_ADJ_TF, st);
     if (mode == CTR_ADJOINT_EXACT)

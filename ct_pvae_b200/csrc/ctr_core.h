@@ -344,6 +344,22 @@ CTR_HD void ctr_adj_fbp(const double* cs, int P, double xpr, double ypr,
     for (int q = 0; q < NB; ++q) acc[q] += (1.f - alpha) * yb[q] + alpha * ya[q];
 }
 
+// Measurement log-likelihood of one ray-sum (ctvae/helper_functions.py:359-368):
+//   pm = proj * mask ;  scale = sqrt_reg + sqrt(pm / pnm + sqrt_reg)
+//   lp = Normal(loc = pm, scale).log_prob(y)
+// and its derivative with respect to proj (what the tape would propagate for d(sum lp)).
+CTR_HD void ctr_loglik_term(float proj, float mask, float y, float pnm, float sqrt_reg, float& lp, float& dlp_dproj)
+{
+    const float pm = proj * mask;
+    const float sr = sqrtf(pm / pnm + sqrt_reg);
+    const float sc = sqrt_reg + sr;
+    const float inv = 1.f / sc;
+    const float z = (y - pm) * inv;
+    lp = -0.5f * z * z - logf(sc) - 0.91893853320467274f;   // 0.5*log(2*pi)
+    const float dsc = 0.5f / (pnm * sr);                     // d scale / d pm
+    dlp_dproj = (z * inv + (z * z - 1.f) * inv * dsc) * mask;
+}
+
 // Sinogram-bin window a pixel tile needs for one angle: packed start bin so that
 // [start, start+win) covers every bin any of the tile's pixels can touch.
 //   u(px,py) is linear, so its extremes over the tile sit at the 4 corners.

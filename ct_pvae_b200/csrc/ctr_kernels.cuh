@@ -163,13 +163,20 @@ struct FwdParams {
     int chunks0;            // CTAs (along grid.x) that serve class 0
     int H, W, A, B;
     int R;                  // key rows per strip (strip holds R+1 packed rows)
-    float* sino;            // [B][A][W]
+    float* sino;            // [B][A][W]   (EPI 0: ray sums; EPI 1: d loglik / d proj, the adjoint's cotangent)
+    // fused measurement log-likelihood epilogue (EPI 1), helper_functions.py:355-368
+    const float* mask;      // [B][A_all]
+    const float* meas;      // [B][A_all][W]  measured sinogram (proj_sample)
+    const int* amap;        // [A] plan angle -> column of mask/meas (the angles_i gather), or null = identity
+    int A_all;
+    float pnm, sqrt_reg;    // poisson_noise_multiplier, sqrt_reg
+    float* partial;         // [gridDim.z*gridDim.x][G*NB] per-CTA log-likelihood sums
 };
 
 // One CTA = (angle chunk of NS*KA same-class angles) x (image group of NB) x (detector chunk of JW bins).
 // thread (tx, ty): detector bin j = blockIdx.z*JW + tx, angles ty*KA .. ty*KA+KA-1 of the chunk.
 // All threads walk the image group's strips in lock step; thread 0 drives the TMA double buffer.
-template <int NB, int KA, int INTERP>
+template <int NB, int KA, int INTERP, int EPI>
 __global__ void __launch_bounds__(kFwdMaxThreads, 1) ctr_fwd_kernel(const FwdParams p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -259,18 +266,62 @@ __global__ void __launch_bounds__(kFwdMaxThreads, 1) ctr_fwd_kernel(const FwdPar
         if (tid == 0 && k + 2 < K) issue(k + 2);
     }
 
+    float lsum[NB];
+#pragma unroll
+    for (int n = 0; n < NB; ++n) lsum[n] = 0.f;
 #pragma unroll
     for (int q = 0; q < KA; ++q) {
         const int la = ty * KA + q;
         if (la < cnt && j < p.W) {
             const int a = rays_s[la].angle;
+            const int ao = (EPI && p.amap) ? p.amap[a] : a;
 #pragma unroll
             for (int n = 0; n < NB; ++n) {
                 const int b = g * NB + n;
-                if (b < p.B) p.sino[((size_t)b * p.A + a) * p.W + j] = acc[q][n];
+                if (b < p.B) {
+                    float outv = acc[q][n];
+                    if (EPI) {
+                        const size_t ma = (size_t)b * p.A_all + ao;
+                        float lp;
+                        ctr_loglik_term(acc[q][n], __ldg(p.mask + ma), __ldg(p.meas + ma * p.W + j), p.pnm, p.sqrt_reg, lp, outv);
+                        lsum[n] += lp;
+                    }
+                    p.sino[((size_t)b * p.A + a) * p.W + j] = outv;
+                }
             }
         }
     }
+    if (EPI) {
+        // deterministic CTA reduction of the log-likelihood: shuffles, then one partial per CTA and image.
+        // The strip buffers are free now (the loop above ended on a __syncthreads).
+        float* red = buf0;
+        const int lane = tid & 31, warp = tid >> 5, nwarps = (nthreads + 31) >> 5;
+#pragma unroll
+        for (int n = 0; n < NB; ++n) {
+            float v = lsum[n];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+            if (lane == 0) red[warp * NB + n] = v;
+        }
+        __syncthreads();
+        if (tid < NB) {
+            float v = 0.f;
+            for (int w = 0; w < nwarps; ++w) v += red[w * NB + tid];
+            const size_t cta = (size_t)blockIdx.z * gridDim.x + blockIdx.x;
+            p.partial[cta * ((size_t)gridDim.y * NB) + (size_t)g * NB + tid] = v;
+        }
+    }
+}
+
+// loglik[b] = sum over CTAs of partial[cta][b]  (float64 accumulation, fixed order -> deterministic)
+__global__ void __launch_bounds__(128) ctr_loglik_reduce_kernel(const float* __restrict__ partial, int nctas, int stride, int B,
+                                                                float* __restrict__ loglik)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double acc = 0.0;
+    for (int c = 0; c < nctas; ++c) acc += (double)partial[(size_t)c * stride + b];
+    loglik[b] = (float)acc;
 }
 
 // ------------------------------------------------------------------------------------------ K2 / K2' / K3b
@@ -493,17 +544,17 @@ inline FwdConfig fwd_config(int W, const CtrClassGeom geom[2], int smem_budget)
     return c;
 }
 
-template <int INTERP>
+template <int INTERP, int EPI>
 inline cudaError_t launch_fwd_ka(const FwdParams& p, const FwdConfig& c, int G, int chunks, cudaStream_t st)
 {
     dim3 grid(chunks, G, c.jchunks), block(c.JW, c.NS);
     cudaError_t e;
-#define CTR_FWD_CASE(KA_)                                                                                          \
-    case KA_:                                                                                                      \
-        e = cudaFuncSetAttribute(ctr_fwd_kernel<kFwdNB, KA_, INTERP>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                 (int)c.smem);                                                                     \
-        if (e != cudaSuccess) return e;                                                                            \
-        ctr_fwd_kernel<kFwdNB, KA_, INTERP><<<grid, block, c.smem, st>>>(p);                                       \
+#define CTR_FWD_CASE(KA_)                                                                                               \
+    case KA_:                                                                                                           \
+        e = cudaFuncSetAttribute(ctr_fwd_kernel<kFwdNB, KA_, INTERP, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                 (int)c.smem);                                                                          \
+        if (e != cudaSuccess) return e;                                                                                 \
+        ctr_fwd_kernel<kFwdNB, KA_, INTERP, EPI><<<grid, block, c.smem, st>>>(p);                                       \
         break;
     switch (c.KA) {
         CTR_FWD_CASE(1)

@@ -105,3 +105,69 @@ def project(img: torch.Tensor, plan: _lib.Plan, interp: int, mode: int) -> torch
     if img.requires_grad and torch.is_grad_enabled():
         return RadonFunction.apply(img, plan, interp, mode)
     return radon_forward(img, plan, interp)
+
+
+def radon_adjoint_scaled(dsino: torch.Tensor, plan: _lib.Plan, interp: int, mode: int, scale: float) -> torch.Tensor:
+    """``scale * A^T dsino`` in one launch (ctr_radon_adjoint_scaled)."""
+    dsino = _require_cuda_f32(dsino, "dsino")
+    B = dsino.shape[0]
+    dimg = torch.empty((B, plan.X, plan.Y), dtype=torch.float32, device=dsino.device)
+    if B == 0:
+        return dimg
+    ws = _workspace(plan.adjoint_workspace_bytes(B), dsino.device)
+    _lib.check(_lib.lib().ctr_radon_adjoint_scaled(plan.handle, dsino.data_ptr(), dimg.data_ptr(), B, interp, mode, float(scale),
+                                                   ws.data_ptr(), ws.numel(), _stream_ptr(dsino.device)))
+    return dimg
+
+
+def radon_loglik(img: torch.Tensor, plan: _lib.Plan, mask: torch.Tensor, meas: torch.Tensor, angle_map, pnm: float,
+                 sqrt_reg: float, interp: int):
+    """Fused projector + measurement log-likelihood (ctr_radon_loglik).
+
+    img [B,X,Y], mask [B,A_all], meas [B,A_all,W] float32 CUDA; angle_map int32 CUDA [A] or None.
+    Returns (loglik [B], dproj [B,A,W]) -- dproj is d loglik / d proj, the adjoint's cotangent."""
+    img = _require_cuda_f32(img, "img")
+    mask = _require_cuda_f32(mask, "mask")
+    meas = _require_cuda_f32(meas, "proj_sample")
+    B, A_all = img.shape[0], mask.shape[1]
+    if mask.shape[0] != B or meas.shape[0] != B or meas.shape[1] != A_all or meas.shape[2] != plan.W:
+        raise ValueError("mask must be [B,A_all] and proj_sample [B,A_all,num_proj_pix]")
+    if angle_map is None:
+        if A_all != plan.A:
+            raise ValueError("without angles_i the mask must cover exactly the plan's angles")
+        amap_ptr = None
+    else:
+        if angle_map.dtype != torch.int32 or not angle_map.is_cuda or angle_map.numel() != plan.A:
+            raise ValueError("angle_map must be an int32 CUDA tensor with one entry per plan angle")
+        angle_map = angle_map.contiguous()
+        amap_ptr = angle_map.data_ptr()
+    loglik = torch.empty((B,), dtype=torch.float32, device=img.device)
+    dproj = torch.empty((B, plan.A, plan.W), dtype=torch.float32, device=img.device)
+    ws = _workspace(plan.loglik_workspace_bytes(B), img.device)
+    _lib.check(_lib.lib().ctr_radon_loglik(plan.handle, img.data_ptr(), mask.data_ptr(), meas.data_ptr(), amap_ptr, A_all,
+                                           float(pnm), float(sqrt_reg), loglik.data_ptr(), dproj.data_ptr(), B, interp,
+                                           ws.data_ptr(), ws.numel(), _stream_ptr(img.device)))
+    return loglik, dproj
+
+
+class LoglikFunction(torch.autograd.Function):
+    """sum_b loglik[b] with the gradient d/d img = A^T (d loglik / d proj): the forward pass
+    already produced the cotangent, so backward is a single (scaled) adjoint launch."""
+
+    @staticmethod
+    def forward(ctx, img, plan, mask, meas, angle_map, pnm, sqrt_reg, interp, mode):
+        loglik, dproj = radon_loglik(img, plan, mask, meas, angle_map, pnm, sqrt_reg, interp)
+        ctx.plan, ctx.interp, ctx.mode = plan, interp, mode
+        ctx.save_for_backward(dproj)
+        return loglik
+
+    @staticmethod
+    def backward(ctx, grad_loglik):
+        (dproj,) = ctx.saved_tensors
+        g = grad_loglik.reshape(-1)
+        if g.numel() > 1 and bool((g != g[0]).any()):
+            cot = dproj * g.view(-1, 1, 1)          # per-image upstream weights (rare): one elementwise scale
+            dimg = radon_adjoint(cot, ctx.plan, ctx.interp, ctx.mode)
+        else:
+            dimg = radon_adjoint_scaled(dproj, ctx.plan, ctx.interp, ctx.mode, float(g[0]))
+        return (dimg,) + (None,) * 8

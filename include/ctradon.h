@@ -115,6 +115,25 @@ int ctr_radon_forward(const ctr_plan* plan, const float* img, float* sino, int B
 int ctr_radon_adjoint(const ctr_plan* plan, const float* dsino, float* dimg, int B, int interp, int mode,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* Same, with the result multiplied by `scale` (the upstream scalar of a summed loss). */
+int ctr_radon_adjoint_scaled(const ctr_plan* plan, const float* dsino, float* dimg, int B, int interp, int mode,
+                             float scale, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- fused measurement log-likelihood ------------------------------------------
+ * calculate_log_prob_M_given_R (ctvae/helper_functions.py:336-368) reduced over angles and
+ * bins as find_loss_vae_unsup does (:305-311), in ONE pass of the projector:
+ *   proj   = project_tf_fast(img, theta)                      (never written)
+ *   pm     = proj * mask[b, angle_map[a]]
+ *   lp     = Normal(pm, sqrt_reg + sqrt(pm/pnm + sqrt_reg)).log_prob(meas[b, angle_map[a], j])
+ *   loglik[b] = sum_{a,j} lp          dproj[b,a,j] = d lp / d proj
+ * dproj [B,A,W] is the cotangent ctr_radon_adjoint[_scaled] turns into d loglik / d img.
+ * mask [B,A_all], meas [B,A_all,W], angle_map [A] device int32 (NULL = identity, the
+ * reference's angles_i gather :355-357), loglik [B]; all on the plan's device. */
+size_t ctr_loglik_workspace_bytes(const ctr_plan* plan, int B);
+int ctr_radon_loglik(const ctr_plan* plan, const float* img, const float* mask, const float* meas,
+                     const int* angle_map, int A_all, float pnm, float sqrt_reg, float* loglik, float* dproj,
+                     int B, int interp, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- filtered back-projection ------------------------------------------------------------ */
 
 /* iradon(sinogram, theta, x_size, y_size, filter_1d)  (fbp_tensorflow.py:14-75).

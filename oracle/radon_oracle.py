@@ -305,6 +305,29 @@ def iradon_np(sinogram, theta, x_size: int, y_size: int, filter_1d) -> np.ndarra
     return rec * np.pi / (2 * num_angles)
 
 
+# ----------------------------------------------------------------------------- measurement log-likelihood
+def log_prob_M_given_R(img, mask, proj_sample, pnm, sqrt_reg, theta, angles_i=None, pad=True, interp=NEAREST):
+    """float64 restatement of calculate_log_prob_M_given_R (ctvae/helper_functions.py:336-368)
+    on top of the float32 projector oracle.  Returns (logp [B,A',P], d logp / d proj [B,A',P])."""
+    theta = np.asarray(theta, np.float64).reshape(-1)
+    mask = np.asarray(mask, np.float64)
+    y = np.asarray(proj_sample, np.float64)
+    if angles_i is not None:
+        idx = np.asarray(angles_i, np.int64)
+        theta = theta[idx].astype(np.float32).astype(np.float64)      # tf.cast(tf.gather(theta, angles_i), float32), :355
+        mask, y = mask[:, idx], y[:, idx]
+    proj = forward(np.asarray(img, np.float32), theta, pad, interp).astype(np.float64)
+    m = mask[:, :, None]
+    pm = proj * m
+    sr = np.sqrt(pm / pnm + sqrt_reg)
+    sc = sqrt_reg + sr
+    z = (y - pm) / sc
+    logp = -0.5 * z * z - np.log(sc) - 0.5 * np.log(2 * np.pi)
+    dsc = 0.5 / (pnm * sr)
+    dproj = (z / sc + (z * z - 1.0) / sc * dsc) * m
+    return logp, dproj
+
+
 # ----------------------------------------------------------------------------- synthetic inputs
 def synthetic_foam(n: int, size: int, seed: int = 0) -> np.ndarray:
     """Stand-in for xdesign.Foam (scripts/create_foam_images.py:27-40): a unit disk

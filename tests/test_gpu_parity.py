@@ -205,6 +205,38 @@ def test_pinned_host_batch_goes_through_the_chunked_pipeline(cp, orc):
     assert g.device.type == "cpu" and rel_l2(g.numpy(), orc.adjoint_exact(cot, th, X, X, True, 1)) <= TOL
 
 
+@pytest.mark.parametrize("interp", INTERPS)
+@pytest.mark.parametrize("gather", [False, True])
+def test_fused_loglik_matches_oracle(cp, orc, interp, gather):
+    """projector + mask + Normal log-prob + reduction in one pass, and its gradient."""
+    rng = np.random.default_rng(9)
+    B, X, A_all = 6, 32, 20
+    th = _theta(A_all)
+    angles_i = rng.permutation(A_all)[:7] if gather else None
+    pnm, sreg = 1e4, float(np.finfo(np.float32).eps)
+    img = rng.random((B, X, X), dtype=np.float32)
+    P = orc.frame_of(X, X, True)[1]
+    mask = (rng.random((B, A_all)) < 0.5).astype(np.float32) / 3.0
+    clean = orc.forward(img, th, True, IID[interp])
+    meas = (clean * mask[:, :, None] * (1 + 0.05 * rng.standard_normal(clean.shape))).astype(np.float32)
+    logp, dproj = orc.log_prob_M_given_R(img, mask, meas, pnm, sreg, th, angles_i, True, IID[interp])
+    x = torch.from_numpy(img).cuda().unsqueeze(-1).requires_grad_(True)
+    ai = None if angles_i is None else torch.from_numpy(angles_i)
+    per = cp.log_prob_M_given_R_sum(x, torch.from_numpy(mask).cuda(), torch.from_numpy(meas).cuda(), pnm, sreg, theta=th,
+                                    angles_i=ai, pad=True, interpolation=interp, per_image=True)
+    want = logp.sum(axis=(1, 2))
+    np.testing.assert_allclose(per.detach().cpu().numpy(), want, rtol=2e-5)
+    per.sum().backward()
+    th_sub = th if angles_i is None else th[angles_i].astype(np.float32).astype(np.float64)
+    gwant = orc.adjoint_exact(dproj.astype(np.float32), th_sub, X, X, True, IID[interp])
+    assert rel_l2(x.grad[..., 0].cpu().numpy(), gwant) <= 2e-5
+    # the drop-in full-tensor form agrees with the fused sum
+    full = cp.calculate_log_prob_M_given_R(x.detach(), torch.from_numpy(mask).cuda(), torch.from_numpy(meas).cuda(), pnm, sreg,
+                                           theta=th, angles_i=ai, pad=True, interpolation=interp)
+    assert full.shape == (B, logp.shape[1], P, 1)
+    np.testing.assert_allclose(full[..., 0].double().sum(dim=(1, 2)).cpu().numpy(), want, rtol=2e-5)
+
+
 def test_golden_fixtures(cp):
     import os
 

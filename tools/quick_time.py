@@ -71,3 +71,29 @@ if __name__ == "__main__":
     pcie()
     run(256, 128, 180, "C2")
     run(64, 512, 720, "C4")
+
+
+def loglik_time(B=256, X=128, A=180):
+    from ct_pvae_b200 import likelihood
+    th = np.linspace(0, np.pi, A, endpoint=False)
+    plan = _lib.get_plan(th, X, X, True, 0)
+    img = torch.rand((B, X, X), device="cuda")
+    mask = (torch.rand((B, A), device="cuda") < 0.2).float() / 20
+    meas = torch.rand((B, A, plan.W), device="cuda")
+    best, med = timeit(lambda: ops.radon_loglik(img, plan, mask, meas, None, 1e4, 1.19e-7, 0))
+    print(f"fused loglik (nearest) fwd: {best:.3f} ms", flush=True)
+    x4 = img.unsqueeze(-1)
+    best, med = timeit(lambda: likelihood.calculate_log_prob_M_given_R(x4, mask, meas, 1e4, 1.19e-7, theta=th, pad=True).sum())
+    print(f"unfused (project + torch elementwise + sum) fwd: {best:.3f} ms", flush=True)
+    xg = x4.clone().requires_grad_(True)
+    def fused_fb():
+        xg.grad = None
+        likelihood.log_prob_M_given_R_sum(xg, mask, meas, 1e4, 1.19e-7, theta=th, pad=True).backward()
+    def unfused_fb():
+        xg.grad = None
+        likelihood.calculate_log_prob_M_given_R(xg, mask, meas, 1e4, 1.19e-7, theta=th, pad=True).sum().backward()
+    print("fused fwd+bwd: %.3f ms ; unfused fwd+bwd: %.3f ms" % (timeit(fused_fb)[0], timeit(unfused_fb)[0]), flush=True)
+
+
+if __name__ == "__main__":
+    loglik_time()

@@ -209,6 +209,43 @@ def run_reference(args, wl):
     print(json.dumps(line), flush=True)
 
 
+def vae_training_leg(dev, iters=20, warm=3):
+    """End-to-end VAE training it/s on BASELINE configs[0] (README quick-start: 50 foam images
+    128x128, 180 angles, -b 5 --nsa 20 --api 20 --ns 2 --pnm 1e4 --normal --random), with the
+    torch restatement of the reference's networks/loss (ct_pvae_b200/vae.py) around the fused
+    projector.  Random-init weights, synthetic foam; wall clock with a sync on both sides."""
+    import torch
+
+    from ct_pvae_b200 import vae
+
+    torch.manual_seed(0)
+    N, X, A, b, nsa, api, ns, pnm = 50, 128, 180, 5, 20, 20, 2, 1e4
+    theta = np.linspace(0, np.pi, A, endpoint=False)
+    imgs = synthetic_foam_torch(N, X, dev, seed=123)
+    sino = vae.create_sinogram(imgs, theta, pad=True, interpolation="bilinear")
+    masks, meas = vae.create_all_masks(sino, A, pnm, num_sparse_angles=nsa, random=True)
+    enc_in = vae.iradon_all(meas, masks, theta, X, X)
+    model = vae.CTVAE(X, X, num_filters=1).to(dev)
+    g = torch.Generator().manual_seed(1)
+
+    def one():
+        idx = torch.randint(0, N, (b,), generator=g).to(dev)
+        angles_i = torch.randperm(A, generator=g)[:api]
+        loss, _, _, _ = model.train_step(meas[idx], masks[idx], enc_in[idx], pnm, theta, angles_i=angles_i, num_samples=ns)
+        return loss
+
+    for _ in range(warm):
+        one()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        loss = one()
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    return {"it_per_s": iters / dt, "ms_per_it": dt / iters * 1e3, "final_loss": float(loss),
+            "config": "README quick-start: b=5, 128x128, 180 angles, nsa=20, api=20, ns=2, pnm=1e4, --normal --random"}
+
+
 # ----------------------------------------------------------------------------------------- GPU arm
 def run_ours(args, wl):
     import torch
@@ -313,6 +350,11 @@ def run_ours(args, wl):
         side["fbp_ms"] = best_ms(lambda: ops.fbp(cot, fplan))
         side["fbp_gupdates_per_s"] = B * A_loc * X * X / (side["fbp_ms"] * 1e-3) / 1e9
         side["fwd_nearest_gray_sums_per_s"] = B * A_loc * P / (side["fwd_nearest_ms"] * 1e-3) / 1e9
+        if not args.no_train_leg:
+            try:
+                side["vae_train"] = vae_training_leg(dev)
+            except Exception as exc:  # the restated VAE is a caller, never a reason to lose the headline
+                side["vae_train"] = {"error": repr(exc)[:200]}
     sync_all()
 
     # ---- e2e: the public API with pinned HOST buffers, copies inside the timed region
@@ -395,6 +437,7 @@ def main():
     ap.add_argument("--shard", default="batch", choices=["batch", "angle"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-side-legs", action="store_true")
+    ap.add_argument("--no-train-leg", action="store_true")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -69,6 +69,22 @@ def test_adjoint_matches_oracle(cp, orc, B, X, Y, A, pad, interp, mode):
     assert rel_l2(got.cpu().numpy(), want) <= TOL
 
 
+@pytest.mark.parametrize("B,X,Y,A,pad", [(1, 1024, 1024, 3, True), (2, 300, 700, 5, False), (3, 700, 300, 5, True)])
+def test_large_and_rectangular_frames(cp, orc, B, X, Y, A, pad):
+    """Detector wider than one CTA (P = 1452 -> two detector chunks), wide strips, non-square frames."""
+    rng = np.random.default_rng(7)
+    img = rng.random((B, X, Y), dtype=np.float32)
+    th = np.array([0.3, 1.1, 2.5, 0.0, np.pi / 2])[:A]
+    W = orc.frame_of(X, Y, pad)[1]
+    y = rng.random((B, A, W), dtype=np.float32)
+    for interp in INTERPS:
+        got = cp.project_tf_fast(torch.from_numpy(img).cuda().unsqueeze(-1), th, pad=pad, dim=2, integrate_vae=True,
+                                 interpolation=interp)[..., 0]
+        assert rel_l2(got.cpu().numpy(), orc.forward(img, th, pad, IID[interp])) <= TOL
+        g = cp.backproject(torch.from_numpy(y).cuda(), th, X, Y, pad=pad, interpolation=interp)
+        assert rel_l2(g.cpu().numpy(), orc.adjoint_exact(y, th, X, Y, pad, IID[interp])) <= TOL
+
+
 def test_random_angles_and_signs(cp, orc):
     rng = np.random.default_rng(2)
     th = rng.uniform(-7, 7, 23)

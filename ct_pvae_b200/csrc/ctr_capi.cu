@@ -88,7 +88,8 @@ struct ctr_plan {
     std::vector<CtrRay> rays;
     int n_cls[2] = {0, 0};
     CtrClassGeom geom[2];
-    ctr::FwdConfig fc;
+    ctr::FwdConfig fc;    // 4 images per pixel record (any detector)
+    ctr::FwdConfig fcd;   // depth-first: 16 images per record, detectors <= 256 bins (R == 0: unavailable)
     float* d_t = nullptr;
     float* d_tinv = nullptr;
     CtrRay* d_rays = nullptr;
@@ -214,6 +215,7 @@ int ctr_plan_create(const double* theta, int A, int X, int Y, int pad, int devic
     cudaError_t e = cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if (e != cudaSuccess) { int rc = fail_cuda(e, "cudaDeviceGetAttribute"); delete p; return rc; }
     p->fc = ctr::fwd_config(p->W, p->geom, smem_optin - 2048);
+    p->fcd = ctr::fwd_config_depth(p->W, p->geom, smem_optin - 2048);
     if (p->fc.R < 1) { delete p; return fail(CTR_EUNSUPPORTED, "ctr_plan_create: image rows too wide for the shared-memory strips"); }
     const size_t tb = (size_t)A * 8 * sizeof(float);
     if ((e = cudaMalloc(&p->d_t, tb)) != cudaSuccess || (e = cudaMalloc(&p->d_tinv, tb)) != cudaSuccess ||
@@ -260,10 +262,19 @@ int ctr_plan_tables(const ctr_plan* p, float* fwd, float* inv)
     return CTR_OK;
 }
 
+// which forward shape serves a batch of B: depth-first when the detector allows it and the
+// batch fills at least most of a 16-image record
+static const ctr::FwdConfig& fwd_cfg_for(const ctr_plan* p, int B)
+{
+    static const bool no_depth = getenv("CTR_FWD_NODEPTH") != nullptr;   // developer switch for A/B timing
+    return (!no_depth && p->fcd.R >= 1 && B >= 12) ? p->fcd : p->fc;
+}
+
 static size_t pack_bytes(const ctr_plan* p, int B)
 {
-    const size_t G = (size_t)(B + ctr::kFwdNB - 1) / ctr::kFwdNB;
-    return align_up(G * (size_t)(p->X + 2) * (size_t)(p->Y + 2) * ctr::kFwdNB * sizeof(float), 256);
+    const size_t rec = (size_t)ctr::kFwdNB * fwd_cfg_for(p, B).depth;
+    const size_t G = ((size_t)B + rec - 1) / rec;
+    return align_up(G * (size_t)(p->X + 2) * (size_t)(p->Y + 2) * rec * sizeof(float), 256);
 }
 
 size_t ctr_forward_workspace_bytes(const ctr_plan* p, int B)
@@ -292,10 +303,12 @@ struct LoglikArgs {
 
 static size_t loglik_partial_bytes(const ctr_plan* p, int B)
 {
-    const int NA = p->fc.NS * p->fc.KA;
+    const ctr::FwdConfig& fc = fwd_cfg_for(p, B);
+    const int NA = fc.NS * fc.KA;
     const size_t chunks = (size_t)(p->n_cls[0] + NA - 1) / NA + (size_t)(p->n_cls[1] + NA - 1) / NA;
-    const size_t G = (size_t)(B + ctr::kFwdNB - 1) / ctr::kFwdNB;
-    return align_up(chunks * p->fc.jchunks * G * ctr::kFwdNB * sizeof(float), 256);
+    const size_t rec = (size_t)ctr::kFwdNB * fc.depth;
+    const size_t G = ((size_t)B + rec - 1) / rec;
+    return align_up(chunks * fc.jchunks * G * rec * sizeof(float), 256);
 }
 
 static int forward_impl(const ctr_plan* p, const float* img, float* out, int B, int interp, const LoglikArgs* ll,
@@ -310,13 +323,15 @@ static int forward_impl(const ctr_plan* p, const float* img, float* out, int B, 
     DeviceGuard guard(p->device);
     if (!guard.ok) return fail_cuda(guard.err, "cudaSetDevice");
     cudaStream_t st = (cudaStream_t)stream;
-    const int G = (B + ctr::kFwdNB - 1) / ctr::kFwdNB;
+    const ctr::FwdConfig& fc = fwd_cfg_for(p, B);
+    const int rec = ctr::kFwdNB * fc.depth;
+    const int G = (B + rec - 1) / rec;            // pixel records along the batch (super-groups)
     float* pk0 = p->n_cls[0] ? (float*)ws : nullptr;
     float* pk1 = p->n_cls[1] ? (float*)((char*)ws + pack_bytes(p, B)) : nullptr;
     {
-        dim3 grid((p->Y + 2 + 31) / 32, (p->X + 2 + 31) / 32, G), block(32, 8);
+        dim3 grid((p->Y + 2 + 31) / 32, (p->X + 2 + 31) / 32, G * fc.depth), block(32, 8);
         ProfScope prof(CTR_K_PACK_IMAGE, st);
-        ctr::ctr_pack_image_kernel<ctr::kFwdNB><<<grid, block, 0, st>>>(img, B, p->X, p->Y, pk0, pk1);
+        ctr::ctr_pack_image_kernel<ctr::kFwdNB><<<grid, block, 0, st>>>(img, B, p->X, p->Y, pk0, pk1, fc.depth);
         ctr::launch_counter()++;
         CTR_CUDA(cudaGetLastError());
     }
@@ -325,18 +340,18 @@ static int forward_impl(const ctr_plan* p, const float* img, float* out, int B, 
     fp.geom[0] = p->geom[0]; fp.geom[1] = p->geom[1];
     fp.rays = p->d_rays;
     fp.n_cls[0] = p->n_cls[0]; fp.n_cls[1] = p->n_cls[1];
-    const int NA = p->fc.NS * p->fc.KA;
+    const int NA = fc.NS * fc.KA;
     fp.chunks0 = (p->n_cls[0] + NA - 1) / NA;
     const int chunks = fp.chunks0 + (p->n_cls[1] + NA - 1) / NA;
     fp.H = p->H; fp.W = p->W; fp.A = p->A; fp.B = B;
-    fp.R = p->fc.R;
+    fp.R = fc.R;
     fp.sino = out;
     fp.mask = nullptr; fp.meas = nullptr; fp.amap = nullptr; fp.A_all = p->A; fp.pnm = 1.f; fp.sqrt_reg = 0.f; fp.partial = nullptr;
     cudaError_t e;
     if (!ll) {
         ProfScope prof(CTR_K_FORWARD, st);
-        e = (interp == CTR_INTERP_NEAREST) ? ctr::launch_fwd_ka<CTR_NEAREST, 0>(fp, p->fc, G, chunks, st)
-                                           : ctr::launch_fwd_ka<CTR_BILINEAR, 0>(fp, p->fc, G, chunks, st);
+        e = (interp == CTR_INTERP_NEAREST) ? ctr::launch_fwd_ka<CTR_NEAREST, 0>(fp, fc, G, chunks, st)
+                                           : ctr::launch_fwd_ka<CTR_BILINEAR, 0>(fp, fc, G, chunks, st);
         if (e != cudaSuccess) return fail_cuda(e, "ctr_fwd_kernel launch");
         return CTR_OK;
     }
@@ -344,11 +359,11 @@ static int forward_impl(const ctr_plan* p, const float* img, float* out, int B, 
     fp.partial = (float*)((char*)ws + 2 * pack_bytes(p, B));
     {
         ProfScope prof(CTR_K_FORWARD, st);
-        e = (interp == CTR_INTERP_NEAREST) ? ctr::launch_fwd_ka<CTR_NEAREST, 1>(fp, p->fc, G, chunks, st)
-                                           : ctr::launch_fwd_ka<CTR_BILINEAR, 1>(fp, p->fc, G, chunks, st);
+        e = (interp == CTR_INTERP_NEAREST) ? ctr::launch_fwd_ka<CTR_NEAREST, 1>(fp, fc, G, chunks, st)
+                                           : ctr::launch_fwd_ka<CTR_BILINEAR, 1>(fp, fc, G, chunks, st);
     }
     if (e != cudaSuccess) return fail_cuda(e, "ctr_fwd_kernel<loglik> launch");
-    ctr::ctr_loglik_reduce_kernel<<<(B + 127) / 128, 128, 0, st>>>(fp.partial, chunks * p->fc.jchunks, G * ctr::kFwdNB, B, ll->loglik);
+    ctr::ctr_loglik_reduce_kernel<<<(B + 127) / 128, 128, 0, st>>>(fp.partial, chunks * fc.jchunks, G * rec, B, ll->loglik);
     ctr::launch_counter()++;
     CTR_CUDA(cudaGetLastError());
     return CTR_OK;

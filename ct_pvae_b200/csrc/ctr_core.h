@@ -183,7 +183,9 @@ CTR_HD void ctr_ray_begin(const CtrRay& r, const CtrClassGeom& g, int j, int H, 
 // the march, so successive strips partition the ray exactly.
 //   vend  = (float)(row0p + R + offv)   first key row that belongs to the next strip
 //   rbase = row0p + offv                key row of strip row 0
-template <int NB, int INTERP>
+// REC = floats per packed pixel record (NB, or NB*DEPTH when DEPTH image groups share a
+// record and `strip` already points at this thread's group inside the record).
+template <int NB, int INTERP, int REC = NB>
 CTR_HD void ctr_march(const float* __restrict__ strip, int Up, float vend, int rbase, int offu,
                       const CtrRay& r, CtrRayState& s, float* __restrict__ acc)
 {
@@ -197,7 +199,7 @@ CTR_HD void ctr_march(const float* __restrict__ strip, int Up, float vend, int r
             if (kvf >= vend) break;
             ctr_round_fi(u, kuf, kui);
             float a[NB];
-            ctr_ldv<NB>(strip + ((kvi - rbase) * Up + (kui - offu)) * NB, a);
+            ctr_ldv<NB>(strip + ((kvi - rbase) * Up + (kui - offu)) * REC, a);
 #pragma unroll
             for (int q = 0; q < NB; ++q) acc[q] += a[q];
         } else {
@@ -207,11 +209,11 @@ CTR_HD void ctr_march(const float* __restrict__ strip, int Up, float vend, int r
             const float fu = CTR_SUB(u, kuf), gu = CTR_SUB(CTR_ADD(kuf, 1.f), u);
             const float fv = CTR_SUB(v, kvf), gv = CTR_SUB(CTR_ADD(kvf, 1.f), v);
             const float w00 = gv * gu, w01 = gv * fu, w10 = fv * gu, w11 = fv * fu;
-            const float* p0 = strip + ((kvi - rbase) * Up + (kui - offu)) * NB;
-            const float* p1 = p0 + Up * NB;
+            const float* p0 = strip + ((kvi - rbase) * Up + (kui - offu)) * REC;
+            const float* p1 = p0 + Up * REC;
             float a00[NB], a01[NB], a10[NB], a11[NB];
-            ctr_ldv<NB>(p0, a00); ctr_ldv<NB>(p0 + NB, a01);
-            ctr_ldv<NB>(p1, a10); ctr_ldv<NB>(p1 + NB, a11);
+            ctr_ldv<NB>(p0, a00); ctr_ldv<NB>(p0 + REC, a01);
+            ctr_ldv<NB>(p1, a10); ctr_ldv<NB>(p1 + REC, a11);
 #pragma unroll
             for (int q = 0; q < NB; ++q)
                 acc[q] = fmaf(w11, a11[q], fmaf(w10, a10[q], fmaf(w01, a01[q], fmaf(w00, a00[q], acc[q]))));

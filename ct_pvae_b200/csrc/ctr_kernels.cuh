@@ -87,12 +87,16 @@ __host__ __device__ static inline int round_up(int v, int m) { return (v + m - 1
 // grid (ceil((Y+2)/32), ceil((X+2)/32), G), block (32, 8).  Reads are coalesced along
 // image rows; both packs are written with 16-byte-per-lane coalesced stores, the
 // transposed one through a padded shared-memory tile.
+// `depth` image groups of NB share one pixel record of depth*NB floats (depth-first pack):
+// blockIdx.z = super-group * depth + sub; this block fills chunk `sub` of every record.
 template <int NB>
 __global__ void __launch_bounds__(256) ctr_pack_image_kernel(const float* __restrict__ img, int B, int X, int Y,
-                                                             float* __restrict__ pk0, float* __restrict__ pk1)
+                                                             float* __restrict__ pk0, float* __restrict__ pk1, int depth)
 {
     __shared__ float tile[NB][32][33];
-    const int g = blockIdx.z;
+    const int g = blockIdx.z;                       // image group of NB
+    const int sg = g / depth, sub = g - sg * depth; // super-group (one pixel record) and chunk inside it
+    const int rec = NB * depth;
     const int pr0 = blockIdx.y * 32, pc0 = blockIdx.x * 32;
     const int tx = threadIdx.x, ty = threadIdx.y;
 #pragma unroll
@@ -110,7 +114,7 @@ __global__ void __launch_bounds__(256) ctr_pack_image_kernel(const float* __rest
         for (int rr = ty; rr < 32; rr += 8) {
             const int pr = pr0 + rr, pc = pc0 + tx;
             if (pr < X + 2 && pc < Y + 2) {
-                float* dst = pk0 + (((size_t)g * (X + 2) + pr) * (Y + 2) + pc) * NB;
+                float* dst = pk0 + (((size_t)sg * (X + 2) + pr) * (Y + 2) + pc) * rec + sub * NB;
 #pragma unroll
                 for (int q = 0; q < NB / 4; ++q)
                     reinterpret_cast<float4*>(dst)[q] = make_float4(tile[4 * q][rr][tx], tile[4 * q + 1][rr][tx],
@@ -122,7 +126,7 @@ __global__ void __launch_bounds__(256) ctr_pack_image_kernel(const float* __rest
         for (int cc = ty; cc < 32; cc += 8) {
             const int pc = pc0 + cc, pr = pr0 + tx;
             if (pr < X + 2 && pc < Y + 2) {
-                float* dst = pk1 + (((size_t)g * (Y + 2) + pc) * (X + 2) + pr) * NB;
+                float* dst = pk1 + (((size_t)sg * (Y + 2) + pc) * (X + 2) + pr) * rec + sub * NB;
 #pragma unroll
                 for (int q = 0; q < NB / 4; ++q)
                     reinterpret_cast<float4*>(dst)[q] = make_float4(tile[4 * q][tx][cc], tile[4 * q + 1][tx][cc],
@@ -176,14 +180,19 @@ struct FwdParams {
 // One CTA = (angle chunk of NS*KA same-class angles) x (image group of NB) x (detector chunk of JW bins).
 // thread (tx, ty): detector bin j = blockIdx.z*JW + tx, angles ty*KA .. ty*KA+KA-1 of the chunk.
 // All threads walk the image group's strips in lock step; thread 0 drives the TMA double buffer.
-template <int NB, int KA, int INTERP, int EPI>
-__global__ void __launch_bounds__(kFwdMaxThreads, 1) ctr_fwd_kernel(const FwdParams p)
+// DEPTH > 1 is the depth-first variant: DEPTH image groups share one pixel record and the
+// lanes of a quarter-warp are (8/DEPTH rays) x (DEPTH groups), so a quarter-warp's LDS.128
+// touches 8/DEPTH records of DEPTH*16 contiguous bytes -- shared-memory bank conflicts drop
+// from ~1.7x (8 rays spaced 1/cos(theta) > 1 chunks apart) to ~1.2x at DEPTH = 4.
+template <int NB, int KA, int INTERP, int EPI, int DEPTH>
+__global__ void __launch_bounds__(DEPTH > 1 ? 1024 : kFwdMaxThreads, 1) ctr_fwd_kernel(const FwdParams p)
 {
+    constexpr int REC = NB * DEPTH;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int JW = blockDim.x, NS = blockDim.y;
+    const int JW = blockDim.x / DEPTH, NS = blockDim.y;   // detector bins per CTA, angle slots
     const int NA = NS * KA;
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    const int tid = ty * JW + tx, nthreads = JW * NS;
+    const int tx = threadIdx.x / DEPTH, gsub = threadIdx.x % DEPTH, ty = threadIdx.y;
+    const int tid = ty * blockDim.x + threadIdx.x, nthreads = blockDim.x * NS;
 
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);                 // 2 mbarriers
     CtrRay* rays_s = reinterpret_cast<CtrRay*>(smem_raw + 128);              // NA rays
@@ -196,11 +205,11 @@ __global__ void __launch_bounds__(kFwdMaxThreads, 1) ctr_fwd_kernel(const FwdPar
     const int g = blockIdx.y;
     const CtrClassGeom geom = cls ? p.geom[1] : p.geom[0];  // static indices: stays in registers
     const int R = p.R;
-    const int strip_floats = (R + 1) * geom.Up * NB;
+    const int strip_floats = (R + 1) * geom.Up * REC;
     float* buf0 = reinterpret_cast<float*>(smem_raw + 128 + rays_bytes);
     float* buf1 = buf0 + strip_floats;
     const int K = (geom.Vp + R - 1) / R;
-    const float* pkg = (cls ? p.pk[1] : p.pk[0]) + (size_t)g * geom.Vp * geom.Up * NB;
+    const float* pkg = (cls ? p.pk[1] : p.pk[0]) + (size_t)g * geom.Vp * geom.Up * REC;
 
     for (int k = tid; k < cnt; k += nthreads) rays_s[k] = p.rays[first + k];
     if (tid == 0) {
@@ -212,10 +221,10 @@ __global__ void __launch_bounds__(kFwdMaxThreads, 1) ctr_fwd_kernel(const FwdPar
 
     auto issue = [&](int k) {
         const int rows = min(R + 1, geom.Vp - k * R);
-        const uint32_t bytes = (uint32_t)rows * geom.Up * NB * 4u;
+        const uint32_t bytes = (uint32_t)rows * geom.Up * REC * 4u;
         uint64_t* bar = &full[k & 1];
         mbar_arrive_expect_tx(bar, bytes);
-        bulk_g2s((k & 1) ? buf1 : buf0, pkg + (size_t)k * R * geom.Up * NB, bytes, bar);
+        bulk_g2s((k & 1) ? buf1 : buf0, pkg + (size_t)k * R * geom.Up * REC, bytes, bar);
     };
     if (tid == 0) {
         issue(0);
@@ -244,7 +253,7 @@ __global__ void __launch_bounds__(kFwdMaxThreads, 1) ctr_fwd_kernel(const FwdPar
 
     for (int k = 0; k < K; ++k) {
         mbar_wait(&full[k & 1], (uint32_t)((k >> 1) & 1));
-        const float* strip = (k & 1) ? buf1 : buf0;
+        const float* strip = ((k & 1) ? buf1 : buf0) + gsub * NB;
         const float vend = (float)((k + 1) * R + geom.offv);
         const int rbase = k * R + geom.offv;
 #pragma unroll
@@ -257,7 +266,7 @@ __global__ void __launch_bounds__(kFwdMaxThreads, 1) ctr_fwd_kernel(const FwdPar
                 s.fi = ri[q];
                 s.n = rn[q];
                 s.dfi = (r.v1 >= 0.f) ? 1.f : -1.f;
-                ctr_march<NB, INTERP>(strip, geom.Up, vend, rbase, geom.offu, r, s, acc[q]);
+                ctr_march<NB, INTERP, REC>(strip, geom.Up, vend, rbase, geom.offu, r, s, acc[q]);
                 ri[q] = s.fi;
                 rn[q] = s.n;
             }
@@ -277,7 +286,7 @@ __global__ void __launch_bounds__(kFwdMaxThreads, 1) ctr_fwd_kernel(const FwdPar
             const int ao = (EPI && p.amap) ? p.amap[a] : a;
 #pragma unroll
             for (int n = 0; n < NB; ++n) {
-                const int b = g * NB + n;
+                const int b = (g * DEPTH + gsub) * NB + n;
                 if (b < p.B) {
                     float outv = acc[q][n];
                     if (EPI) {
@@ -300,15 +309,15 @@ __global__ void __launch_bounds__(kFwdMaxThreads, 1) ctr_fwd_kernel(const FwdPar
         for (int n = 0; n < NB; ++n) {
             float v = lsum[n];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-            if (lane == 0) red[warp * NB + n] = v;
+            for (int o = 16; o >= DEPTH; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);   // lanes of equal gsub
+            if (lane < DEPTH) red[(warp * DEPTH + lane) * NB + n] = v;
         }
         __syncthreads();
-        if (tid < NB) {
+        if (tid < REC) {   // tid = gsub * NB + n
             float v = 0.f;
-            for (int w = 0; w < nwarps; ++w) v += red[w * NB + tid];
+            for (int w = 0; w < nwarps; ++w) v += red[w * REC + tid];
             const size_t cta = (size_t)blockIdx.z * gridDim.x + blockIdx.x;
-            p.partial[cta * ((size_t)gridDim.y * NB) + (size_t)g * NB + tid] = v;
+            p.partial[cta * ((size_t)gridDim.y * REC) + (size_t)g * REC + tid] = v;
         }
     }
 }
@@ -505,15 +514,18 @@ __global__ void __launch_bounds__(256) ctr_fbp_filter_kernel(const float* __rest
 
 // ------------------------------------------------------------------------------------------ launchers
 struct FwdConfig {
-    int JW, NS, KA, R, jchunks;
+    int JW, NS, KA, R, jchunks, depth;
     size_t smem;
 };
 
 // Shape the forward CTA: JW detector bins x NS angle slots x KA angles per slot, and the
 // largest strip height R whose double buffer fits the shared-memory budget.
+inline FwdConfig fwd_config_depth(int W, const CtrClassGeom geom[2], int smem_budget);
+
 inline FwdConfig fwd_config(int W, const CtrClassGeom geom[2], int smem_budget)
 {
     FwdConfig c;
+    c.depth = 1;
     c.JW = round_up(W, 32);
     if (c.JW > kFwdMaxThreads) c.JW = kFwdMaxThreads;
     c.jchunks = (W + c.JW - 1) / c.JW;
@@ -544,17 +556,53 @@ inline FwdConfig fwd_config(int W, const CtrClassGeom geom[2], int smem_budget)
     return c;
 }
 
+// Depth-first shape (DEPTH = 4, 16 images per CTA): one 1024-thread-max CTA covers the whole
+// detector (x 4 image groups), two angles per thread; only for detectors of <= 256 bins.
+constexpr int kFwdDepth = 4;
+inline FwdConfig fwd_config_depth(int W, const CtrClassGeom geom[2], int smem_budget)
+{
+    FwdConfig c;
+    c.depth = kFwdDepth;
+    c.JW = round_up(W, 8);
+    c.jchunks = 1;
+    c.NS = 1;
+    c.KA = 2;
+    c.R = 0;
+    c.smem = 0;
+    if (c.JW * kFwdDepth > 1024) return c;   // R = 0: not available for this detector width
+    const int fixed = 128 + round_up(c.NS * c.KA * (int)sizeof(CtrRay), 128);
+    const int Upmax = geom[0].Up > geom[1].Up ? geom[0].Up : geom[1].Up;
+    const int Vpmax = geom[0].Vp > geom[1].Vp ? geom[0].Vp : geom[1].Vp;
+    const int row_bytes = Upmax * kFwdNB * kFwdDepth * 4;
+    int rows = (smem_budget - fixed) / (2 * row_bytes);
+    if (rows > Vpmax) rows = Vpmax;
+    if (rows > 33) rows = 33;
+    if (const char* e = getenv("CTR_FWD_R")) { int v = atoi(e); if (v >= 1 && v + 1 <= rows) rows = v + 1; }
+    c.R = rows - 1;
+    if (c.R < 1) c.R = 0;
+    c.smem = (size_t)fixed + 2ull * (size_t)(c.R + 1) * row_bytes;
+    return c;
+}
+
 template <int INTERP, int EPI>
 inline cudaError_t launch_fwd_ka(const FwdParams& p, const FwdConfig& c, int G, int chunks, cudaStream_t st)
 {
-    dim3 grid(chunks, G, c.jchunks), block(c.JW, c.NS);
+    dim3 grid(chunks, G, c.jchunks), block(c.JW * c.depth, c.NS);
     cudaError_t e;
-#define CTR_FWD_CASE(KA_)                                                                                               \
-    case KA_:                                                                                                           \
-        e = cudaFuncSetAttribute(ctr_fwd_kernel<kFwdNB, KA_, INTERP, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                 (int)c.smem);                                                                          \
-        if (e != cudaSuccess) return e;                                                                                 \
-        ctr_fwd_kernel<kFwdNB, KA_, INTERP, EPI><<<grid, block, c.smem, st>>>(p);                                       \
+    if (c.depth == kFwdDepth) {   // G counts super-groups of kFwdNB * kFwdDepth images here
+        e = cudaFuncSetAttribute(ctr_fwd_kernel<kFwdNB, 2, INTERP, EPI, kFwdDepth>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+        if (e != cudaSuccess) return e;
+        ctr_fwd_kernel<kFwdNB, 2, INTERP, EPI, kFwdDepth><<<grid, block, c.smem, st>>>(p);
+        launch_counter()++;
+        return cudaGetLastError();
+    }
+#define CTR_FWD_CASE(KA_)                                                                                                  \
+    case KA_:                                                                                                              \
+        e = cudaFuncSetAttribute(ctr_fwd_kernel<kFwdNB, KA_, INTERP, EPI, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                 (int)c.smem);                                                                             \
+        if (e != cudaSuccess) return e;                                                                                    \
+        ctr_fwd_kernel<kFwdNB, KA_, INTERP, EPI, 1><<<grid, block, c.smem, st>>>(p);                                       \
         break;
     switch (c.KA) {
         CTR_FWD_CASE(1)

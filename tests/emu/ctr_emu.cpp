@@ -17,19 +17,22 @@ namespace {
 
 constexpr int NB = 4;
 
-// [G][Vp][Up][NB] packs of both classes, zero halos (mirrors ctr_pack_image_kernel).
+// [G][Vp][Up][DEPTH*NB] packs of both classes, zero halos (mirrors ctr_pack_image_kernel):
+// DEPTH image groups of NB share one pixel record.
+template <int DEPTH>
 void pack_images(const float* img, int B, int X, int Y, std::vector<float>& pk0, std::vector<float>& pk1)
 {
-    const int G = (B + NB - 1) / NB;
-    pk0.assign((size_t)G * (X + 2) * (Y + 2) * NB, 0.f);
-    pk1.assign((size_t)G * (Y + 2) * (X + 2) * NB, 0.f);
+    constexpr int REC = NB * DEPTH;
+    const int G = (B + REC - 1) / REC;
+    pk0.assign((size_t)G * (X + 2) * (Y + 2) * REC, 0.f);
+    pk1.assign((size_t)G * (Y + 2) * (X + 2) * REC, 0.f);
     for (int b = 0; b < B; ++b) {
-        const int g = b / NB, n = b % NB;
+        const int g = b / REC, n = b % REC;
         for (int r = 0; r < X; ++r)
             for (int c = 0; c < Y; ++c) {
                 const float v = img[((size_t)b * X + r) * Y + c];
-                pk0[(((size_t)g * (X + 2) + r + 1) * (Y + 2) + c + 1) * NB + n] = v;
-                pk1[(((size_t)g * (Y + 2) + c + 1) * (X + 2) + r + 1) * NB + n] = v;
+                pk0[(((size_t)g * (X + 2) + r + 1) * (Y + 2) + c + 1) * REC + n] = v;
+                pk1[(((size_t)g * (Y + 2) + c + 1) * (X + 2) + r + 1) * REC + n] = v;
             }
     }
 }
@@ -49,38 +52,40 @@ void pack_sino(const float* y, int B, int A, int W, std::vector<float>& spk)
             }
 }
 
-template <int INTERP>
+template <int INTERP, int DEPTH>
 void forward_impl(const float* img, int B, int X, int Y, int H, int W, int padx, int pady,
                   const float* t, int A, int R, float* sino)
 {
+    constexpr int REC = NB * DEPTH;
     std::vector<float> pk[2];
-    pack_images(img, B, X, Y, pk[0], pk[1]);
+    pack_images<DEPTH>(img, B, X, Y, pk[0], pk[1]);
     CtrClassGeom geom[2];
     ctr_h_class_geom(X, Y, padx, pady, geom);
     std::vector<CtrRay> rays;
     int n0 = 0;
     ctr_h_build_rays(t, A, rays, n0);
-    const int G = (B + NB - 1) / NB;
+    const int G = (B + REC - 1) / REC;
     for (int g = 0; g < G; ++g) {
         for (size_t ri = 0; ri < rays.size(); ++ri) {
             const CtrRay& r = rays[ri];
             const CtrClassGeom& cg = geom[r.cls];
-            const float* pkg = pk[r.cls].data() + (size_t)g * cg.Vp * cg.Up * NB;
+            const float* pkg = pk[r.cls].data() + (size_t)g * cg.Vp * cg.Up * REC;
             const int K = (cg.Vp + R - 1) / R;
-            for (int j = 0; j < W; ++j) {
+            for (int j = 0; j < W; ++j)
+              for (int gsub = 0; gsub < DEPTH; ++gsub) {   // the DEPTH lanes that share ray j
                 CtrRayState s;
                 ctr_ray_begin(r, cg, j, H, s);
                 float acc[NB] = {0, 0, 0, 0};
                 for (int k = 0; k < K; ++k) {
                     // the strip buffer the TMA bulk copy would have filled: rows [kR, kR+R+1)
                     const int rows = std::min(R + 1, cg.Vp - k * R);
-                    std::vector<float> strip((size_t)(R + 1) * cg.Up * NB, -1e30f);  // poison what is not loaded
-                    std::memcpy(strip.data(), pkg + (size_t)k * R * cg.Up * NB, sizeof(float) * rows * cg.Up * NB);
-                    ctr_march<NB, INTERP>(strip.data(), cg.Up, (float)((k + 1) * R + cg.offv), k * R + cg.offv,
-                                          cg.offu, r, s, acc);
+                    std::vector<float> strip((size_t)(R + 1) * cg.Up * REC, -1e30f);  // poison what is not loaded
+                    std::memcpy(strip.data(), pkg + (size_t)k * R * cg.Up * REC, sizeof(float) * rows * cg.Up * REC);
+                    ctr_march<NB, INTERP, REC>(strip.data() + gsub * NB, cg.Up, (float)((k + 1) * R + cg.offv),
+                                               k * R + cg.offv, cg.offu, r, s, acc);
                 }
                 for (int n = 0; n < NB; ++n) {
-                    const int b = g * NB + n;
+                    const int b = (g * DEPTH + gsub) * NB + n;
                     if (b < B) sino[((size_t)b * A + r.angle) * W + j] = acc[n];
                 }
             }
@@ -157,8 +162,16 @@ int emu_num_proj_pix(int X, int Y) { return ctr_h_num_proj_pix(X, Y); }
 void emu_forward(const float* img, int B, int X, int Y, int H, int W, int padx, int pady, const float* t, int A,
                  int interp, int R, float* sino)
 {
-    if (interp == CTR_NEAREST) forward_impl<CTR_NEAREST>(img, B, X, Y, H, W, padx, pady, t, A, R, sino);
-    else forward_impl<CTR_BILINEAR>(img, B, X, Y, H, W, padx, pady, t, A, R, sino);
+    if (interp == CTR_NEAREST) forward_impl<CTR_NEAREST, 1>(img, B, X, Y, H, W, padx, pady, t, A, R, sino);
+    else forward_impl<CTR_BILINEAR, 1>(img, B, X, Y, H, W, padx, pady, t, A, R, sino);
+}
+
+// depth-first pack: 4 image groups share a pixel record (ctr_fwd_kernel<..., DEPTH = 4>)
+void emu_forward_depth(const float* img, int B, int X, int Y, int H, int W, int padx, int pady, const float* t, int A,
+                       int interp, int R, float* sino)
+{
+    if (interp == CTR_NEAREST) forward_impl<CTR_NEAREST, 4>(img, B, X, Y, H, W, padx, pady, t, A, R, sino);
+    else forward_impl<CTR_BILINEAR, 4>(img, B, X, Y, H, W, padx, pady, t, A, R, sino);
 }
 
 // mode 0: exact (table = forward transforms); mode 1: tf-compat (table = inverted transforms)

@@ -46,6 +46,9 @@ def test_emulated_kernels_match_oracle(emu, orc, B, X, Y, A, pad, R, TW, TH, win
         s = np.full((B, A, W), np.nan, np.float32)
         emu.emu_forward(P(img), B, X, Y, H, W, padx, pady, P(t), A, interp, R, P(s))
         assert rel_l2(s, orc.forward(img, th, pad, interp)) <= 1e-6
+        sd = np.full((B, A, W), np.nan, np.float32)       # depth-first records (16 images per record)
+        emu.emu_forward_depth(P(img), B, X, Y, H, W, padx, pady, P(t), A, interp, R, P(sd))
+        np.testing.assert_array_equal(sd, s)
         g = np.full((B, X, Y), np.nan, np.float32)
         emu.emu_adjoint(P(y), B, X, Y, H, W, padx, pady, P(t), A, interp, 0, TW, TH, win, P(g))
         assert rel_l2(g, orc.adjoint_exact(y, th, X, Y, pad, interp)) <= 1e-6

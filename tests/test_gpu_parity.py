@@ -26,6 +26,11 @@ SHAPES = [
     (9, 64, 64, 24, True),
     (4, 128, 128, 20, True),
     (1, 200, 200, 7, True),
+    # B >= 12 with a detector of <= 256 bins: the depth-first forward (16 images per pixel record)
+    (13, 16, 16, 12, True),
+    (17, 33, 20, 9, True),
+    (16, 64, 64, 8, False),
+    (37, 128, 128, 6, True),
 ]
 
 
@@ -226,7 +231,7 @@ def test_pinned_host_batch_goes_through_the_chunked_pipeline(cp, orc):
 def test_fused_loglik_matches_oracle(cp, orc, interp, gather):
     """projector + mask + Normal log-prob + reduction in one pass, and its gradient."""
     rng = np.random.default_rng(9)
-    B, X, A_all = 6, 32, 20
+    B, X, A_all = (18 if gather else 6), 32, 20     # 18: depth-first forward, 6: 4-image records
     th = _theta(A_all)
     angles_i = rng.permutation(A_all)[:7] if gather else None
     pnm, sreg = 1e4, float(np.finfo(np.float32).eps)

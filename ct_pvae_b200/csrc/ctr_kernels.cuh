@@ -556,24 +556,31 @@ inline FwdConfig fwd_config(int W, const CtrClassGeom geom[2], int smem_budget)
     return c;
 }
 
-// Depth-first shape (DEPTH = 4, 16 images per CTA): one 1024-thread-max CTA covers the whole
-// detector (x 4 image groups), two angles per thread; only for detectors of <= 256 bins.
+// Depth-first shapes: DEPTH image groups of 4 per pixel record, (up to) 1024-thread CTAs of
+// JW detector bins x DEPTH groups.  DEPTH = 4 (16 images, two angles per thread) is the
+// default for detectors of <= 256 bins; DEPTH = 8 (32 images, conflict-free, four angles per
+// thread, detector split into chunks of <= 128 bins) is selectable for experiments.
 constexpr int kFwdDepth = 4;
 inline FwdConfig fwd_config_depth(int W, const CtrClassGeom geom[2], int smem_budget)
 {
     FwdConfig c;
     c.depth = kFwdDepth;
+    if (const char* e = getenv("CTR_FWD_DEPTH")) { int v = atoi(e); if (v == 4 || v == 8) c.depth = v; }
     c.JW = round_up(W, 8);
-    c.jchunks = 1;
     c.NS = 1;
-    c.KA = 2;
+    c.KA = (c.depth == 8) ? 4 : 2;
     c.R = 0;
     c.smem = 0;
-    if (c.JW * kFwdDepth > 1024) return c;   // R = 0: not available for this detector width
+    c.jchunks = 1;
+    if (c.depth == 8) {
+        if (c.JW > 128) { c.jchunks = (W + 127) / 128; c.JW = round_up((W + c.jchunks - 1) / c.jchunks, 8); }
+    } else if (c.JW * c.depth > 1024) {
+        return c;   // R = 0: not available for this detector width
+    }
     const int fixed = 128 + round_up(c.NS * c.KA * (int)sizeof(CtrRay), 128);
     const int Upmax = geom[0].Up > geom[1].Up ? geom[0].Up : geom[1].Up;
     const int Vpmax = geom[0].Vp > geom[1].Vp ? geom[0].Vp : geom[1].Vp;
-    const int row_bytes = Upmax * kFwdNB * kFwdDepth * 4;
+    const int row_bytes = Upmax * kFwdNB * c.depth * 4;
     int rows = (smem_budget - fixed) / (2 * row_bytes);
     if (rows > Vpmax) rows = Vpmax;
     if (rows > 33) rows = 33;
@@ -589,11 +596,17 @@ inline cudaError_t launch_fwd_ka(const FwdParams& p, const FwdConfig& c, int G, 
 {
     dim3 grid(chunks, G, c.jchunks), block(c.JW * c.depth, c.NS);
     cudaError_t e;
-    if (c.depth == kFwdDepth) {   // G counts super-groups of kFwdNB * kFwdDepth images here
-        e = cudaFuncSetAttribute(ctr_fwd_kernel<kFwdNB, 2, INTERP, EPI, kFwdDepth>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+    if (c.depth == 4) {   // G counts super-groups of kFwdNB * depth images here
+        e = cudaFuncSetAttribute(ctr_fwd_kernel<kFwdNB, 2, INTERP, EPI, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
         if (e != cudaSuccess) return e;
-        ctr_fwd_kernel<kFwdNB, 2, INTERP, EPI, kFwdDepth><<<grid, block, c.smem, st>>>(p);
+        ctr_fwd_kernel<kFwdNB, 2, INTERP, EPI, 4><<<grid, block, c.smem, st>>>(p);
+        launch_counter()++;
+        return cudaGetLastError();
+    }
+    if (c.depth == 8) {
+        e = cudaFuncSetAttribute(ctr_fwd_kernel<kFwdNB, 4, INTERP, EPI, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+        if (e != cudaSuccess) return e;
+        ctr_fwd_kernel<kFwdNB, 4, INTERP, EPI, 8><<<grid, block, c.smem, st>>>(p);
         launch_counter()++;
         return cudaGetLastError();
     }

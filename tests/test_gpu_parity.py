@@ -246,7 +246,9 @@ def test_fused_loglik_matches_oracle(cp, orc, interp, gather):
     per = cp.log_prob_M_given_R_sum(x, torch.from_numpy(mask).cuda(), torch.from_numpy(meas).cuda(), pnm, sreg, theta=th,
                                     angles_i=ai, pad=True, interpolation=interp, per_image=True)
     want = logp.sum(axis=(1, 2))
-    np.testing.assert_allclose(per.detach().cpu().numpy(), want, rtol=2e-5)
+    # float32 terms of both signs: the error budget scales with sum |terms|, not with the (cancelling) sum
+    budget = 2e-6 * np.abs(logp).sum(axis=(1, 2)) + 2e-5 * np.abs(want)
+    assert (np.abs(per.detach().cpu().numpy() - want) <= budget).all()
     per.sum().backward()
     th_sub = th if angles_i is None else th[angles_i].astype(np.float32).astype(np.float64)
     gwant = orc.adjoint_exact(dproj.astype(np.float32), th_sub, X, X, True, IID[interp])
@@ -255,7 +257,7 @@ def test_fused_loglik_matches_oracle(cp, orc, interp, gather):
     full = cp.calculate_log_prob_M_given_R(x.detach(), torch.from_numpy(mask).cuda(), torch.from_numpy(meas).cuda(), pnm, sreg,
                                            theta=th, angles_i=ai, pad=True, interpolation=interp)
     assert full.shape == (B, logp.shape[1], P, 1)
-    np.testing.assert_allclose(full[..., 0].double().sum(dim=(1, 2)).cpu().numpy(), want, rtol=2e-5)
+    assert (np.abs(full[..., 0].double().sum(dim=(1, 2)).cpu().numpy() - want) <= budget).all()
 
 
 def test_golden_fixtures(cp):

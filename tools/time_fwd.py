@@ -1,0 +1,19 @@
+"""Time the forward kernel alone on C2 / C4-slice (developer tool; honours CTR_FWD_* overrides)."""
+import os, sys
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from ct_pvae_b200 import _lib, ops
+for (B, X, A) in ((256, 128, 180), (16, 512, 720)):
+    th = np.linspace(0, np.pi, A, endpoint=False)
+    plan = _lib.get_plan(th, X, X, True, 0)
+    img = torch.rand((B, X, X), device="cuda")
+    out = []
+    for iid in (1, 0):
+        for _ in range(3): ops.radon_forward(img, plan, iid)
+        torch.cuda.synchronize(); ts = []
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); ops.radon_forward(img, plan, iid); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+        out.append(min(ts))
+    print(f"B={B} X={X} A={A}: bilinear {out[0]:.3f} ms  nearest {out[1]:.3f} ms   env=" +
+          " ".join(f"{k}={v}" for k, v in os.environ.items() if k.startswith("CTR_FWD")), flush=True)

@@ -304,7 +304,7 @@ struct LoglikArgs {
 static size_t loglik_partial_bytes(const ctr_plan* p, int B)
 {
     const ctr::FwdConfig& fc = fwd_cfg_for(p, B);
-    const int NA = fc.NS * fc.KA;
+    const int NA = fc.angles_per_cta();
     const size_t chunks = (size_t)(p->n_cls[0] + NA - 1) / NA + (size_t)(p->n_cls[1] + NA - 1) / NA;
     const size_t rec = (size_t)ctr::kFwdNB * fc.depth;
     const size_t G = ((size_t)B + rec - 1) / rec;
@@ -340,7 +340,8 @@ static int forward_impl(const ctr_plan* p, const float* img, float* out, int B, 
     fp.geom[0] = p->geom[0]; fp.geom[1] = p->geom[1];
     fp.rays = p->d_rays;
     fp.n_cls[0] = p->n_cls[0]; fp.n_cls[1] = p->n_cls[1];
-    const int NA = fc.NS * fc.KA;
+    const int NA = fc.angles_per_cta();
+    fp.kbins = fc.kbins;
     fp.chunks0 = (p->n_cls[0] + NA - 1) / NA;
     const int chunks = fp.chunks0 + (p->n_cls[1] + NA - 1) / NA;
     fp.H = p->H; fp.W = p->W; fp.A = p->A; fp.B = B;

@@ -167,6 +167,7 @@ struct FwdParams {
     int chunks0;            // CTAs (along grid.x) that serve class 0
     int H, W, A, B;
     int R;                  // key rows per strip (strip holds R+1 packed rows)
+    int kbins;              // 1: a thread's KA rays are KA detector bins (JW apart) of ONE angle; 0: KA angles of one bin
     float* sino;            // [B][A][W]   (EPI 0: ray sums; EPI 1: d loglik / d proj, the adjoint's cotangent)
     // fused measurement log-likelihood epilogue (EPI 1), helper_functions.py:355-368
     const float* mask;      // [B][A_all]
@@ -189,8 +190,11 @@ __global__ void __launch_bounds__(DEPTH > 1 ? 1024 : kFwdMaxThreads, 1) ctr_fwd_
 {
     constexpr int REC = NB * DEPTH;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int JW = blockDim.x / DEPTH, NS = blockDim.y;   // detector bins per CTA, angle slots
-    const int NA = NS * KA;
+    const int JW = blockDim.x / DEPTH, NS = blockDim.y;   // detector bin slots per CTA, angle slots
+    // kbins: thread (tx,ty) owns bins tx, tx+JW, .. of angle slot ty.  A central (long) ray is
+    // paired with an edge (short) one, so the threads of a CTA carry near-equal work per strip.
+    const bool kb = p.kbins != 0;
+    const int NA = kb ? NS : NS * KA;
     const int tx = threadIdx.x / DEPTH, gsub = threadIdx.x % DEPTH, ty = threadIdx.y;
     const int tid = ty * blockDim.x + threadIdx.x, nthreads = blockDim.x * NS;
 
@@ -232,13 +236,14 @@ __global__ void __launch_bounds__(DEPTH > 1 ? 1024 : kFwdMaxThreads, 1) ctr_fwd_
     }
 
     // per-ray state: next step and steps left (coefficients are re-read from smem per strip)
-    const int j = blockIdx.z * JW + tx;
+    const int jb = kb ? blockIdx.z * (JW * KA) + tx : blockIdx.z * JW + tx;
+    const int jstep = kb ? JW : 0, lbase = kb ? ty : ty * KA, lstep = kb ? 0 : 1;
     float ri[KA];
     int rn[KA];
     float acc[KA][NB];
 #pragma unroll
     for (int q = 0; q < KA; ++q) {
-        const int la = ty * KA + q;
+        const int la = lbase + q * lstep, j = jb + q * jstep;
         ri[q] = 0.f;
         rn[q] = 0;
         if (la < cnt && j < p.W) {
@@ -259,7 +264,8 @@ __global__ void __launch_bounds__(DEPTH > 1 ? 1024 : kFwdMaxThreads, 1) ctr_fwd_
 #pragma unroll
         for (int q = 0; q < KA; ++q) {
             if (rn[q] > 0) {
-                const CtrRay r = rays_s[ty * KA + q];
+                const CtrRay r = rays_s[lbase + q * lstep];
+                const int j = jb + q * jstep;
                 CtrRayState s;
                 s.pu = CTR_MUL(r.u0, (float)j);
                 s.pv = CTR_MUL(r.v0, (float)j);
@@ -280,7 +286,7 @@ __global__ void __launch_bounds__(DEPTH > 1 ? 1024 : kFwdMaxThreads, 1) ctr_fwd_
     for (int n = 0; n < NB; ++n) lsum[n] = 0.f;
 #pragma unroll
     for (int q = 0; q < KA; ++q) {
-        const int la = ty * KA + q;
+        const int la = lbase + q * lstep, j = jb + q * jstep;
         if (la < cnt && j < p.W) {
             const int a = rays_s[la].angle;
             const int ao = (EPI && p.amap) ? p.amap[a] : a;
@@ -514,9 +520,16 @@ __global__ void __launch_bounds__(256) ctr_fbp_filter_kernel(const float* __rest
 
 // ------------------------------------------------------------------------------------------ launchers
 struct FwdConfig {
-    int JW, NS, KA, R, jchunks, depth;
+    int JW, NS, KA, R, jchunks, depth, kbins;
     size_t smem;
+    int angles_per_cta() const { return kbins ? NS : NS * KA; }
 };
+
+inline bool fwd_use_kbins()
+{
+    static const bool off = getenv("CTR_FWD_NOKBINS") != nullptr;   // developer switch for A/B timing
+    return !off;
+}
 
 // Shape the forward CTA: JW detector bins x NS angle slots x KA angles per slot, and the
 // largest strip height R whose double buffer fits the shared-memory budget.
@@ -526,14 +539,21 @@ inline FwdConfig fwd_config(int W, const CtrClassGeom geom[2], int smem_budget)
 {
     FwdConfig c;
     c.depth = 1;
-    c.JW = round_up(W, 32);
-    if (c.JW > kFwdMaxThreads) c.JW = kFwdMaxThreads;
-    c.jchunks = (W + c.JW - 1) / c.JW;
-    // r1 sweep (tools/sweep_fwd.py): several small CTAs per SM beat one big one (their
-    // strip barriers and ragged ray ends overlap), so one angle slot per CTA unless the
-    // detector is tiny, two angles per thread, and the shared memory split 4 / 2 / 1 ways.
-    c.NS = (c.JW >= 128) ? 1 : 128 / c.JW;
+    c.kbins = fwd_use_kbins() ? 1 : 0;
     c.KA = 2;
+    if (c.kbins) {
+        // two bins per thread (tx and tx + JW) of one angle, NS angle slots per CTA
+        c.JW = round_up((W + 1) / 2, 32);
+        if (c.JW > kFwdMaxThreads / 2) c.JW = kFwdMaxThreads / 2;
+        c.jchunks = (W + c.JW * c.KA - 1) / (c.JW * c.KA);
+        c.NS = (c.JW >= 128) ? 2 : 256 / c.JW;
+        if (c.NS > 8) c.NS = 8;
+    } else {
+        c.JW = round_up(W, 32);
+        if (c.JW > kFwdMaxThreads) c.JW = kFwdMaxThreads;
+        c.jchunks = (W + c.JW - 1) / c.JW;
+        c.NS = (c.JW >= 128) ? 1 : 128 / c.JW;
+    }
     const int threads = c.JW * c.NS;
     const int ctas_per_sm = threads <= 256 ? 4 : (threads <= 512 ? 2 : 1);
     if (smem_budget > (228 * 1024) / ctas_per_sm - 1024) smem_budget = (228 * 1024) / ctas_per_sm - 1024;
@@ -541,7 +561,7 @@ inline FwdConfig fwd_config(int W, const CtrClassGeom geom[2], int smem_budget)
     if (const char* e = getenv("CTR_FWD_NS")) { int v = atoi(e); if (v >= 1 && v * c.JW <= kFwdMaxThreads) c.NS = v; }
     if (const char* e = getenv("CTR_FWD_KA")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4) c.KA = v; }
     if (const char* e = getenv("CTR_FWD_SMEM")) { int v = atoi(e); if (v >= 16384 && v < smem_budget) smem_budget = v; }
-    const int NA = c.NS * c.KA;
+    const int NA = c.NS * c.KA;   // upper bound on angles per CTA in either mapping
     const int fixed = 128 + round_up(NA * (int)sizeof(CtrRay), 128);
     const int Upmax = geom[0].Up > geom[1].Up ? geom[0].Up : geom[1].Up;
     const int Vpmax = geom[0].Vp > geom[1].Vp ? geom[0].Vp : geom[1].Vp;
@@ -566,16 +586,22 @@ inline FwdConfig fwd_config_depth(int W, const CtrClassGeom geom[2], int smem_bu
     FwdConfig c;
     c.depth = kFwdDepth;
     if (const char* e = getenv("CTR_FWD_DEPTH")) { int v = atoi(e); if (v == 4 || v == 8) c.depth = v; }
-    c.JW = round_up(W, 8);
+    c.kbins = (fwd_use_kbins() && c.depth == 4) ? 1 : 0;
     c.NS = 1;
     c.KA = (c.depth == 8) ? 4 : 2;
     c.R = 0;
     c.smem = 0;
     c.jchunks = 1;
     if (c.depth == 8) {
+        c.JW = round_up(W, 8);
         if (c.JW > 128) { c.jchunks = (W + 127) / 128; c.JW = round_up((W + c.jchunks - 1) / c.jchunks, 8); }
-    } else if (c.JW * c.depth > 1024) {
-        return c;   // R = 0: not available for this detector width
+    } else if (c.kbins) {
+        c.JW = round_up((W + 1) / 2, 8);      // bins tx and tx + JW of one angle per thread, two angle slots
+        c.NS = 2;
+        if (c.JW * c.depth * c.NS > 1024) return c;   // R = 0: not available for this detector width
+    } else {
+        c.JW = round_up(W, 8);
+        if (c.JW * c.depth > 1024) return c;
     }
     const int fixed = 128 + round_up(c.NS * c.KA * (int)sizeof(CtrRay), 128);
     const int Upmax = geom[0].Up > geom[1].Up ? geom[0].Up : geom[1].Up;

@@ -525,10 +525,13 @@ struct FwdConfig {
     int angles_per_cta() const { return kbins ? NS : NS * KA; }
 };
 
+// r1 measurement: pairing a central with an edge bin per thread (kbins) balances the work per
+// strip but costs more in SIMT efficiency at the shadow edge (C2 0.645 vs 0.600 ms, C4 3.06 vs
+// 2.91 ms), so it stays an opt-in experiment.
 inline bool fwd_use_kbins()
 {
-    static const bool off = getenv("CTR_FWD_NOKBINS") != nullptr;   // developer switch for A/B timing
-    return !off;
+    static const bool on = getenv("CTR_FWD_KBINS") != nullptr;
+    return on;
 }
 
 // Shape the forward CTA: JW detector bins x NS angle slots x KA angles per slot, and the

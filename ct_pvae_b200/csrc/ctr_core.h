@@ -183,41 +183,81 @@ CTR_HD void ctr_ray_begin(const CtrRay& r, const CtrClassGeom& g, int j, int H, 
 // the march, so successive strips partition the ray exactly.
 //   vend  = (float)(row0p + R + offv)   first key row that belongs to the next strip
 //   rbase = row0p + offv                key row of strip row 0
+// One sample of one ray: coordinates -> (key row, packed offsets, weights).  Split out so the
+// march loop can put two samples in flight at once.
+template <int INTERP>
+struct CtrSample {
+    float kvf;           // key row as float (floor / round of v)
+    int off;             // (row, col) offset of the first tap in pixels, relative to the strip
+    float w00, w01, w10, w11;
+};
+
+template <int INTERP>
+CTR_HD void ctr_sample(const CtrRay& r, float pu, float pv, float fi, int Up, int rbase, int offu, CtrSample<INTERP>& o)
+{
+    const float u = ctr_coord(pu, r.u1, fi, r.u2);
+    const float v = ctr_coord(pv, r.v1, fi, r.v2);
+    float kuf;
+    int kvi, kui;
+    if (INTERP == CTR_NEAREST) {
+        ctr_round_fi(v, o.kvf, kvi);
+        ctr_round_fi(u, kuf, kui);
+    } else {
+        ctr_floor_fi(v, o.kvf, kvi);
+        ctr_floor_fi(u, kuf, kui);
+        // TF: (x - floor(x)) and (floor(x)+1 - x); the latter equals 1 - (x - floor(x)) exactly
+        const float fu = CTR_SUB(u, kuf), gu = CTR_SUB(1.f, fu);
+        const float fv = CTR_SUB(v, o.kvf), gv = CTR_SUB(1.f, fv);
+        o.w00 = gv * gu; o.w01 = gv * fu; o.w10 = fv * gu; o.w11 = fv * fu;
+    }
+    o.off = (kvi - rbase) * Up + (kui - offu);
+}
+
+template <int NB, int INTERP, int REC>
+CTR_HD void ctr_gather(const float* __restrict__ strip, int Up, const CtrSample<INTERP>& o, float* __restrict__ acc)
+{
+    const float* p0 = strip + o.off * REC;
+    if (INTERP == CTR_NEAREST) {
+        float a[NB];
+        ctr_ldv<NB>(p0, a);
+#pragma unroll
+        for (int q = 0; q < NB; ++q) acc[q] += a[q];
+    } else {
+        const float* p1 = p0 + Up * REC;
+        float a00[NB], a01[NB], a10[NB], a11[NB];
+        ctr_ldv<NB>(p0, a00); ctr_ldv<NB>(p0 + REC, a01);
+        ctr_ldv<NB>(p1, a10); ctr_ldv<NB>(p1 + REC, a11);
+#pragma unroll
+        for (int q = 0; q < NB; ++q)
+            acc[q] = fmaf(o.w11, a11[q], fmaf(o.w10, a10[q], fmaf(o.w01, a01[q], fmaf(o.w00, a00[q], acc[q]))));
+    }
+}
+
 // REC = floats per packed pixel record (NB, or NB*DEPTH when DEPTH image groups share a
 // record and `strip` already points at this thread's group inside the record).
+// Two samples are evaluated per trip while both belong to this strip (independent address
+// and load chains -> twice the shared-memory loads in flight per warp), then a single-step
+// tail.  Sample values and their summation order per ray are unchanged.
 template <int NB, int INTERP, int REC = NB>
 CTR_HD void ctr_march(const float* __restrict__ strip, int Up, float vend, int rbase, int offu,
                       const CtrRay& r, CtrRayState& s, float* __restrict__ acc)
 {
+    while (s.n >= 2) {
+        CtrSample<INTERP> a, b;
+        const float fib = s.fi + s.dfi;
+        ctr_sample<INTERP>(r, s.pu, s.pv, s.fi, Up, rbase, offu, a);
+        ctr_sample<INTERP>(r, s.pu, s.pv, fib, Up, rbase, offu, b);
+        if (b.kvf >= vend) break;           // keys grow along the march: a.kvf <= b.kvf
+        ctr_gather<NB, INTERP, REC>(strip, Up, a, acc);
+        ctr_gather<NB, INTERP, REC>(strip, Up, b, acc);
+        s.fi = fib + s.dfi;
+        s.n -= 2;
+    }
     while (s.n > 0) {
-        const float u = ctr_coord(s.pu, r.u1, s.fi, r.u2);
-        const float v = ctr_coord(s.pv, r.v1, s.fi, r.v2);
-        float kvf, kuf;
-        int kvi, kui;
-        if (INTERP == CTR_NEAREST) {
-            ctr_round_fi(v, kvf, kvi);
-            if (kvf >= vend) break;
-            ctr_round_fi(u, kuf, kui);
-            float a[NB];
-            ctr_ldv<NB>(strip + ((kvi - rbase) * Up + (kui - offu)) * REC, a);
-#pragma unroll
-            for (int q = 0; q < NB; ++q) acc[q] += a[q];
-        } else {
-            ctr_floor_fi(v, kvf, kvi);
-            if (kvf >= vend) break;
-            ctr_floor_fi(u, kuf, kui);
-            const float fu = CTR_SUB(u, kuf), gu = CTR_SUB(CTR_ADD(kuf, 1.f), u);
-            const float fv = CTR_SUB(v, kvf), gv = CTR_SUB(CTR_ADD(kvf, 1.f), v);
-            const float w00 = gv * gu, w01 = gv * fu, w10 = fv * gu, w11 = fv * fu;
-            const float* p0 = strip + ((kvi - rbase) * Up + (kui - offu)) * REC;
-            const float* p1 = p0 + Up * REC;
-            float a00[NB], a01[NB], a10[NB], a11[NB];
-            ctr_ldv<NB>(p0, a00); ctr_ldv<NB>(p0 + REC, a01);
-            ctr_ldv<NB>(p1, a10); ctr_ldv<NB>(p1 + REC, a11);
-#pragma unroll
-            for (int q = 0; q < NB; ++q)
-                acc[q] = fmaf(w11, a11[q], fmaf(w10, a10[q], fmaf(w01, a01[q], fmaf(w00, a00[q], acc[q]))));
-        }
+        CtrSample<INTERP> a;
+        ctr_sample<INTERP>(r, s.pu, s.pv, s.fi, Up, rbase, offu, a);
+        if (a.kvf >= vend) break;
+        ctr_gather<NB, INTERP, REC>(strip, Up, a, acc);
         s.fi += s.dfi;
         --s.n;
     }

@@ -186,7 +186,7 @@ struct FwdParams {
 // touches 8/DEPTH records of DEPTH*16 contiguous bytes -- shared-memory bank conflicts drop
 // from ~1.7x (8 rays spaced 1/cos(theta) > 1 chunks apart) to ~1.2x at DEPTH = 4.
 template <int NB, int KA, int INTERP, int EPI, int DEPTH>
-__global__ void __launch_bounds__(DEPTH > 1 ? 1024 : kFwdMaxThreads, 1) ctr_fwd_kernel(const FwdParams p)
+__global__ void __launch_bounds__(kFwdMaxThreads, 1) ctr_fwd_kernel(const FwdParams p)
 {
     constexpr int REC = NB * DEPTH;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -581,7 +581,7 @@ inline FwdConfig fwd_config(int W, const CtrClassGeom geom[2], int smem_budget)
 
 // Depth-first shapes: DEPTH image groups of 4 per pixel record, (up to) 1024-thread CTAs of
 // JW detector bins x DEPTH groups.  DEPTH = 4 (16 images, two angles per thread) is the
-// default for detectors of <= 256 bins; DEPTH = 8 (32 images, conflict-free, four angles per
+// default for detectors of <= 192 bins (768 threads: 85 registers each); DEPTH = 8 (32 images, conflict-free, four angles per
 // thread, detector split into chunks of <= 128 bins) is selectable for experiments.
 constexpr int kFwdDepth = 4;
 inline FwdConfig fwd_config_depth(int W, const CtrClassGeom geom[2], int smem_budget)
@@ -597,14 +597,14 @@ inline FwdConfig fwd_config_depth(int W, const CtrClassGeom geom[2], int smem_bu
     c.jchunks = 1;
     if (c.depth == 8) {
         c.JW = round_up(W, 8);
-        if (c.JW > 128) { c.jchunks = (W + 127) / 128; c.JW = round_up((W + c.jchunks - 1) / c.jchunks, 8); }
+        if (c.JW > 96) { c.jchunks = (W + 95) / 96; c.JW = round_up((W + c.jchunks - 1) / c.jchunks, 8); }
     } else if (c.kbins) {
         c.JW = round_up((W + 1) / 2, 8);      // bins tx and tx + JW of one angle per thread, two angle slots
         c.NS = 2;
-        if (c.JW * c.depth * c.NS > 1024) return c;   // R = 0: not available for this detector width
+        if (c.JW * c.depth * c.NS > kFwdMaxThreads) return c;   // R = 0: not available for this detector width
     } else {
         c.JW = round_up(W, 8);
-        if (c.JW * c.depth > 1024) return c;
+        if (c.JW * c.depth > kFwdMaxThreads) return c;
     }
     const int fixed = 128 + round_up(c.NS * c.KA * (int)sizeof(CtrRay), 128);
     const int Upmax = geom[0].Up > geom[1].Up ? geom[0].Up : geom[1].Up;

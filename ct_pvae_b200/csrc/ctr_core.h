@@ -235,24 +235,12 @@ CTR_HD void ctr_gather(const float* __restrict__ strip, int Up, const CtrSample<
 
 // REC = floats per packed pixel record (NB, or NB*DEPTH when DEPTH image groups share a
 // record and `strip` already points at this thread's group inside the record).
-// Two samples are evaluated per trip while both belong to this strip (independent address
-// and load chains -> twice the shared-memory loads in flight per warp), then a single-step
-// tail.  Sample values and their summation order per ray are unchanged.
+// (A two-samples-per-trip variant was measured in r1 and was not faster: the loop is bound by
+// the shared-memory and issue pipes, not by latency.)
 template <int NB, int INTERP, int REC = NB>
 CTR_HD void ctr_march(const float* __restrict__ strip, int Up, float vend, int rbase, int offu,
                       const CtrRay& r, CtrRayState& s, float* __restrict__ acc)
 {
-    while (s.n >= 2) {
-        CtrSample<INTERP> a, b;
-        const float fib = s.fi + s.dfi;
-        ctr_sample<INTERP>(r, s.pu, s.pv, s.fi, Up, rbase, offu, a);
-        ctr_sample<INTERP>(r, s.pu, s.pv, fib, Up, rbase, offu, b);
-        if (b.kvf >= vend) break;           // keys grow along the march: a.kvf <= b.kvf
-        ctr_gather<NB, INTERP, REC>(strip, Up, a, acc);
-        ctr_gather<NB, INTERP, REC>(strip, Up, b, acc);
-        s.fi = fib + s.dfi;
-        s.n -= 2;
-    }
     while (s.n > 0) {
         CtrSample<INTERP> a;
         ctr_sample<INTERP>(r, s.pu, s.pv, s.fi, Up, rbase, offu, a);

@@ -90,6 +90,7 @@ struct ctr_plan {
     CtrClassGeom geom[2];
     ctr::FwdConfig fc;    // 4 images per pixel record (any detector)
     ctr::FwdConfig fcd;   // depth-first: 16 images per record, detectors <= 256 bins (R == 0: unavailable)
+    void* d_block = nullptr;   // one device allocation: [t | tinv | rays]
     float* d_t = nullptr;
     float* d_tinv = nullptr;
     CtrRay* d_rays = nullptr;
@@ -217,17 +218,22 @@ int ctr_plan_create(const double* theta, int A, int X, int Y, int pad, int devic
     p->fc = ctr::fwd_config(p->W, p->geom, smem_optin - 2048);
     p->fcd = ctr::fwd_config_depth(p->W, p->geom, smem_optin - 2048);
     if (p->fc.R < 1) { delete p; return fail(CTR_EUNSUPPORTED, "ctr_plan_create: image rows too wide for the shared-memory strips"); }
-    const size_t tb = (size_t)A * 8 * sizeof(float);
-    if ((e = cudaMalloc(&p->d_t, tb)) != cudaSuccess || (e = cudaMalloc(&p->d_tinv, tb)) != cudaSuccess ||
-        (e = cudaMalloc(&p->d_rays, (size_t)A * sizeof(CtrRay))) != cudaSuccess ||
-        (e = cudaMemcpy(p->d_t, p->t.data(), tb, cudaMemcpyHostToDevice)) != cudaSuccess ||
-        (e = cudaMemcpy(p->d_tinv, p->tinv.data(), tb, cudaMemcpyHostToDevice)) != cudaSuccess ||
-        (e = cudaMemcpy(p->d_rays, p->rays.data(), (size_t)A * sizeof(CtrRay), cudaMemcpyHostToDevice)) != cudaSuccess) {
+    // one allocation + one upload for the three tables (plans are created per angle minibatch in training)
+    const size_t tb = (size_t)A * 8 * sizeof(float), rb = (size_t)A * sizeof(CtrRay);
+    std::vector<unsigned char> host(2 * tb + rb);
+    std::memcpy(host.data(), p->t.data(), tb);
+    std::memcpy(host.data() + tb, p->tinv.data(), tb);
+    std::memcpy(host.data() + 2 * tb, p->rays.data(), rb);
+    if ((e = cudaMalloc(&p->d_block, host.size())) != cudaSuccess ||
+        (e = cudaMemcpy(p->d_block, host.data(), host.size(), cudaMemcpyHostToDevice)) != cudaSuccess) {
         int rc = fail_cuda(e, "ctr_plan_create: table upload");
-        cudaFree(p->d_t); cudaFree(p->d_tinv); cudaFree(p->d_rays);
+        cudaFree(p->d_block);
         delete p;
         return rc;
     }
+    p->d_t = (float*)p->d_block;
+    p->d_tinv = (float*)((char*)p->d_block + tb);
+    p->d_rays = (CtrRay*)((char*)p->d_block + 2 * tb);
     *out = p;
     return CTR_OK;
 }
@@ -236,7 +242,7 @@ int ctr_plan_destroy(ctr_plan* p)
 {
     if (!p) return CTR_OK;
     DeviceGuard guard(p->device);
-    cudaFree(p->d_t); cudaFree(p->d_tinv); cudaFree(p->d_rays);
+    cudaFree(p->d_block);
     delete p;
     return CTR_OK;
 }

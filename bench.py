@@ -52,6 +52,15 @@ def env_int(name, default):
         return default
 
 
+def ncu_traffic(workload, kernel):
+    """Per-launch DRAM bytes of `kernel` from the committed ncu capture (profiles/), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_dram_traffic.json")) as f:
+            return json.load(f)[workload].get(kernel)
+    except Exception:
+        return None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -411,7 +420,8 @@ def run_ours(args, wl):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": ncu_traffic(args.workload, dom[0]) if not angle_mode else None,
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "note": "gather/issue-bound stencil: HBM fraction is small by construction (SURVEY 8d); see extra.fwd_smem_roofline"},
             "extra": extra,

@@ -348,6 +348,8 @@ static int forward_impl(const ctr_plan* p, const float* img, float* out, int B, 
     fp.n_cls[0] = p->n_cls[0]; fp.n_cls[1] = p->n_cls[1];
     const int NA = fc.angles_per_cta();
     fp.kbins = fc.kbins;
+    fp.jwd = fc.JW * fc.depth;
+    fp.ns = fc.NS;
     fp.chunks0 = (p->n_cls[0] + NA - 1) / NA;
     const int chunks = fp.chunks0 + (p->n_cls[1] + NA - 1) / NA;
     fp.H = p->H; fp.W = p->W; fp.A = p->A; fp.B = B;

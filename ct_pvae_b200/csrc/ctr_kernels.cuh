@@ -79,7 +79,8 @@ inline std::atomic<long long>& launch_counter()
 
 constexpr int kFwdNB = 4;   // images interleaved per forward CTA (one LDS.128 per tap)
 constexpr int kBpTW = 32, kBpAB = 8;
-constexpr int kFwdMaxThreads = 768;
+constexpr int kFwdMaxThreads = 768;                  // block size incl. the producer warp
+constexpr int kFwdMaxConsumers = kFwdMaxThreads - 32;  // 736 = 23 warps
 
 __host__ __device__ static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
@@ -168,6 +169,7 @@ struct FwdParams {
     int H, W, A, B;
     int R;                  // key rows per strip (strip holds R+1 packed rows)
     int kbins;              // 1: a thread's KA rays are KA detector bins (JW apart) of ONE angle; 0: KA angles of one bin
+    int jwd, ns;            // consumer threads per angle slot (JW bins x DEPTH groups) and angle slots; block = jwd*ns + 32
     float* sino;            // [B][A][W]   (EPI 0: ray sums; EPI 1: d loglik / d proj, the adjoint's cotangent)
     // fused measurement log-likelihood epilogue (EPI 1), helper_functions.py:355-368
     const float* mask;      // [B][A_all]
@@ -190,15 +192,19 @@ __global__ void __launch_bounds__(kFwdMaxThreads, 1) ctr_fwd_kernel(const FwdPar
 {
     constexpr int REC = NB * DEPTH;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int JW = blockDim.x / DEPTH, NS = blockDim.y;   // detector bin slots per CTA, angle slots
-    // kbins: thread (tx,ty) owns bins tx, tx+JW, .. of angle slot ty.  A central (long) ray is
-    // paired with an edge (short) one, so the threads of a CTA carry near-equal work per strip.
+    // block = JWD * NS consumer threads (JWD = JW bins x DEPTH image groups per angle slot) + one producer warp
+    const int JWD = p.jwd, NS = p.ns, JW = JWD / DEPTH;
+    const int nconsumers = JWD * NS;
+    const int tid = threadIdx.x;
+    const bool producer = tid >= nconsumers;                 // last warp: drives the TMA strip pipeline
+    const int ty = producer ? 0 : tid / JWD;
+    const int tx = (tid - ty * JWD) / DEPTH, gsub = (tid - ty * JWD) % DEPTH;
+    // kbins: thread (tx,ty) owns bins tx, tx+JW, .. of angle slot ty (opt-in experiment, see fwd_use_kbins)
     const bool kb = p.kbins != 0;
     const int NA = kb ? NS : NS * KA;
-    const int tx = threadIdx.x / DEPTH, gsub = threadIdx.x % DEPTH, ty = threadIdx.y;
-    const int tid = ty * blockDim.x + threadIdx.x, nthreads = blockDim.x * NS;
 
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);                 // 2 mbarriers
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);                 // [2] strip landed (TMA complete_tx)
+    uint64_t* empty = full + 2;                                             // [2] strip consumed (one arrive per consumer warp)
     CtrRay* rays_s = reinterpret_cast<CtrRay*>(smem_raw + 128);              // NA rays
     const int rays_bytes = round_up(NA * (int)sizeof(CtrRay), 128);
 
@@ -215,115 +221,129 @@ __global__ void __launch_bounds__(kFwdMaxThreads, 1) ctr_fwd_kernel(const FwdPar
     const int K = (geom.Vp + R - 1) / R;
     const float* pkg = (cls ? p.pk[1] : p.pk[0]) + (size_t)g * geom.Vp * geom.Up * REC;
 
-    for (int k = tid; k < cnt; k += nthreads) rays_s[k] = p.rays[first + k];
+    for (int k = tid; k < cnt; k += blockDim.x) rays_s[k] = p.rays[first + k];
     if (tid == 0) {
         mbar_init(&full[0], 1);
         mbar_init(&full[1], 1);
+        mbar_init(&empty[0], nconsumers / 32);
+        mbar_init(&empty[1], nconsumers / 32);
         fence_barrier_init();
     }
     __syncthreads();
 
-    auto issue = [&](int k) {
-        const int rows = min(R + 1, geom.Vp - k * R);
-        const uint32_t bytes = (uint32_t)rows * geom.Up * REC * 4u;
-        uint64_t* bar = &full[k & 1];
-        mbar_arrive_expect_tx(bar, bytes);
-        bulk_g2s((k & 1) ? buf1 : buf0, pkg + (size_t)k * R * geom.Up * REC, bytes, bar);
-    };
-    if (tid == 0) {
-        issue(0);
-        if (K > 1) issue(1);
-    }
-
-    // per-ray state: next step and steps left (coefficients are re-read from smem per strip)
-    const int jb = kb ? blockIdx.z * (JW * KA) + tx : blockIdx.z * JW + tx;
-    const int jstep = kb ? JW : 0, lbase = kb ? ty : ty * KA, lstep = kb ? 0 : 1;
-    float ri[KA];
-    int rn[KA];
-    float acc[KA][NB];
-#pragma unroll
-    for (int q = 0; q < KA; ++q) {
-        const int la = lbase + q * lstep, j = jb + q * jstep;
-        ri[q] = 0.f;
-        rn[q] = 0;
-        if (la < cnt && j < p.W) {
-            CtrRayState s;
-            ctr_ray_begin(rays_s[la], geom, j, p.H, s);
-            ri[q] = s.fi;
-            rn[q] = s.n;
+    // ---- producer warp: strip k goes to buffer k&1 as soon as every consumer warp has released
+    // strip k-2.  No CTA-wide barrier in the loop: a warp that finishes a strip early moves on to the
+    // next (already resident) one, so the ragged ends of the strips overlap instead of idling the SM.
+    if (producer) {
+        if ((tid & 31) == 0) {
+            for (int k = 0; k < K; ++k) {
+                if (k >= 2) mbar_wait(&empty[k & 1], (uint32_t)(((k - 2) >> 1) & 1));
+                const int rows = min(R + 1, geom.Vp - k * R);
+                const uint32_t bytes = (uint32_t)rows * geom.Up * REC * 4u;
+                uint64_t* bar = &full[k & 1];
+                mbar_arrive_expect_tx(bar, bytes);
+                bulk_g2s((k & 1) ? buf1 : buf0, pkg + (size_t)k * R * geom.Up * REC, bytes, bar);
+            }
         }
-#pragma unroll
-        for (int n = 0; n < NB; ++n) acc[q][n] = 0.f;
-    }
-
-    for (int k = 0; k < K; ++k) {
-        mbar_wait(&full[k & 1], (uint32_t)((k >> 1) & 1));
-        const float* strip = ((k & 1) ? buf1 : buf0) + gsub * NB;
-        const float vend = (float)((k + 1) * R + geom.offv);
-        const int rbase = k * R + geom.offv;
+    } else {
+        // ---- consumers.  per-ray state: next step and steps left (coefficients are re-read per strip)
+        const int jb = kb ? blockIdx.z * (JW * KA) + tx : blockIdx.z * JW + tx;
+        const int jstep = kb ? JW : 0, lbase = kb ? ty : ty * KA, lstep = kb ? 0 : 1;
+        float ri[KA];
+        int rn[KA];
+        float acc[KA][NB];
 #pragma unroll
         for (int q = 0; q < KA; ++q) {
-            if (rn[q] > 0) {
-                const CtrRay r = rays_s[lbase + q * lstep];
-                const int j = jb + q * jstep;
+            const int la = lbase + q * lstep, j = jb + q * jstep;
+            ri[q] = 0.f;
+            rn[q] = 0;
+            if (la < cnt && j < p.W) {
                 CtrRayState s;
-                s.pu = CTR_MUL(r.u0, (float)j);
-                s.pv = CTR_MUL(r.v0, (float)j);
-                s.fi = ri[q];
-                s.n = rn[q];
-                s.dfi = (r.v1 >= 0.f) ? 1.f : -1.f;
-                ctr_march<NB, INTERP, REC>(strip, geom.Up, vend, rbase, geom.offu, r, s, acc[q]);
+                ctr_ray_begin(rays_s[la], geom, j, p.H, s);
                 ri[q] = s.fi;
                 rn[q] = s.n;
             }
+#pragma unroll
+            for (int n = 0; n < NB; ++n) acc[q][n] = 0.f;
         }
-        __syncthreads();  // every thread is done reading this buffer -> it may be refilled
-        if (tid == 0 && k + 2 < K) issue(k + 2);
-    }
 
-    float lsum[NB];
+        for (int k = 0; k < K; ++k) {
+            mbar_wait(&full[k & 1], (uint32_t)((k >> 1) & 1));
+            const float* strip = ((k & 1) ? buf1 : buf0) + gsub * NB;
+            const float vend = (float)((k + 1) * R + geom.offv);
+            const int rbase = k * R + geom.offv;
 #pragma unroll
-    for (int n = 0; n < NB; ++n) lsum[n] = 0.f;
+            for (int q = 0; q < KA; ++q) {
+                if (rn[q] > 0) {
+                    const CtrRay r = rays_s[lbase + q * lstep];
+                    const int j = jb + q * jstep;
+                    CtrRayState s;
+                    s.pu = CTR_MUL(r.u0, (float)j);
+                    s.pv = CTR_MUL(r.v0, (float)j);
+                    s.fi = ri[q];
+                    s.n = rn[q];
+                    s.dfi = (r.v1 >= 0.f) ? 1.f : -1.f;
+                    ctr_march<NB, INTERP, REC>(strip, geom.Up, vend, rbase, geom.offu, r, s, acc[q]);
+                    ri[q] = s.fi;
+                    rn[q] = s.n;
+                }
+            }
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(&empty[k & 1]);   // this warp is done reading the buffer
+        }
+
+        float lsum[NB];
 #pragma unroll
-    for (int q = 0; q < KA; ++q) {
-        const int la = lbase + q * lstep, j = jb + q * jstep;
-        if (la < cnt && j < p.W) {
-            const int a = rays_s[la].angle;
-            const int ao = (EPI && p.amap) ? p.amap[a] : a;
+        for (int n = 0; n < NB; ++n) lsum[n] = 0.f;
 #pragma unroll
-            for (int n = 0; n < NB; ++n) {
-                const int b = (g * DEPTH + gsub) * NB + n;
-                if (b < p.B) {
-                    float outv = acc[q][n];
-                    if (EPI) {
-                        const size_t ma = (size_t)b * p.A_all + ao;
-                        float lp;
-                        ctr_loglik_term(acc[q][n], __ldg(p.mask + ma), __ldg(p.meas + ma * p.W + j), p.pnm, p.sqrt_reg, lp, outv);
-                        lsum[n] += lp;
+        for (int q = 0; q < KA; ++q) {
+            const int la = lbase + q * lstep, j = jb + q * jstep;
+            if (la < cnt && j < p.W) {
+                const int a = rays_s[la].angle;
+                const int ao = (EPI && p.amap) ? p.amap[a] : a;
+#pragma unroll
+                for (int n = 0; n < NB; ++n) {
+                    const int b = (g * DEPTH + gsub) * NB + n;
+                    if (b < p.B) {
+                        float outv = acc[q][n];
+                        if (EPI) {
+                            const size_t ma = (size_t)b * p.A_all + ao;
+                            float lp;
+                            ctr_loglik_term(acc[q][n], __ldg(p.mask + ma), __ldg(p.meas + ma * p.W + j), p.pnm, p.sqrt_reg, lp, outv);
+                            lsum[n] += lp;
+                        }
+                        p.sino[((size_t)b * p.A + a) * p.W + j] = outv;
                     }
-                    p.sino[((size_t)b * p.A + a) * p.W + j] = outv;
                 }
             }
         }
-    }
-    if (EPI) {
-        // deterministic CTA reduction of the log-likelihood: shuffles, then one partial per CTA and image.
-        // The strip buffers are free now (the loop above ended on a __syncthreads).
-        float* red = buf0;
-        const int lane = tid & 31, warp = tid >> 5, nwarps = (nthreads + 31) >> 5;
+        if (EPI) {
+            // warp-level part of the deterministic log-likelihood reduction (lanes of equal gsub)
 #pragma unroll
-        for (int n = 0; n < NB; ++n) {
-            float v = lsum[n];
+            for (int n = 0; n < NB; ++n) {
+                float v = lsum[n];
 #pragma unroll
-            for (int o = 16; o >= DEPTH; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);   // lanes of equal gsub
-            if (lane < DEPTH) red[(warp * DEPTH + lane) * NB + n] = v;
+                for (int o = 16; o >= DEPTH; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+                lsum[n] = v;
+            }
         }
-        __syncthreads();
-        if (tid < REC) {   // tid = gsub * NB + n
-            float v = 0.f;
-            for (int w = 0; w < nwarps; ++w) v += red[w * REC + tid];
-            const size_t cta = (size_t)blockIdx.z * gridDim.x + blockIdx.x;
-            p.partial[cta * ((size_t)gridDim.y * REC) + (size_t)g * REC + tid] = v;
+        if (EPI) {
+            // every consumer warp has left the strip buffers only after this barrier (named barrier 1,
+            // consumers only: the producer warp has nothing to add and may already have exited)
+            asm volatile("bar.sync 1, %0;" ::"r"(nconsumers) : "memory");
+            float* red = buf0;
+            const int lane = tid & 31, warp = tid >> 5, nwarps = nconsumers >> 5;
+            if (lane < DEPTH) {
+#pragma unroll
+                for (int n = 0; n < NB; ++n) red[(warp * DEPTH + lane) * NB + n] = lsum[n];
+            }
+            asm volatile("bar.sync 1, %0;" ::"r"(nconsumers) : "memory");
+            if (tid < REC) {   // tid = gsub * NB + n
+                float v = 0.f;
+                for (int w = 0; w < nwarps; ++w) v += red[w * REC + tid];
+                const size_t cta = (size_t)blockIdx.z * gridDim.x + blockIdx.x;
+                p.partial[cta * ((size_t)gridDim.y * REC) + (size_t)g * REC + tid] = v;
+            }
         }
     }
 }
@@ -547,21 +567,21 @@ inline FwdConfig fwd_config(int W, const CtrClassGeom geom[2], int smem_budget)
     if (c.kbins) {
         // two bins per thread (tx and tx + JW) of one angle, NS angle slots per CTA
         c.JW = round_up((W + 1) / 2, 32);
-        if (c.JW > kFwdMaxThreads / 2) c.JW = kFwdMaxThreads / 2;
+        if (c.JW > 352) c.JW = 352;   // two bins per thread, consumers <= 736, multiple of 32
         c.jchunks = (W + c.JW * c.KA - 1) / (c.JW * c.KA);
         c.NS = (c.JW >= 128) ? 2 : 256 / c.JW;
         if (c.NS > 8) c.NS = 8;
     } else {
         c.JW = round_up(W, 32);
-        if (c.JW > kFwdMaxThreads) c.JW = kFwdMaxThreads;
+        if (c.JW > kFwdMaxConsumers) c.JW = kFwdMaxConsumers;
         c.jchunks = (W + c.JW - 1) / c.JW;
         c.NS = (c.JW >= 128) ? 1 : 128 / c.JW;
     }
-    const int threads = c.JW * c.NS;
+    const int threads = c.JW * c.NS + 32;
     const int ctas_per_sm = threads <= 256 ? 4 : (threads <= 512 ? 2 : 1);
     if (smem_budget > (228 * 1024) / ctas_per_sm - 1024) smem_budget = (228 * 1024) / ctas_per_sm - 1024;
     // developer overrides for tuning sweeps (tools/sweep_fwd.py); not part of the API
-    if (const char* e = getenv("CTR_FWD_NS")) { int v = atoi(e); if (v >= 1 && v * c.JW <= kFwdMaxThreads) c.NS = v; }
+    if (const char* e = getenv("CTR_FWD_NS")) { int v = atoi(e); if (v >= 1 && v * c.JW <= kFwdMaxConsumers) c.NS = v; }
     if (const char* e = getenv("CTR_FWD_KA")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4) c.KA = v; }
     if (const char* e = getenv("CTR_FWD_SMEM")) { int v = atoi(e); if (v >= 16384 && v < smem_budget) smem_budget = v; }
     const int NA = c.NS * c.KA;   // upper bound on angles per CTA in either mapping
@@ -581,7 +601,7 @@ inline FwdConfig fwd_config(int W, const CtrClassGeom geom[2], int smem_budget)
 
 // Depth-first shapes: DEPTH image groups of 4 per pixel record, (up to) 1024-thread CTAs of
 // JW detector bins x DEPTH groups.  DEPTH = 4 (16 images, two angles per thread) is the
-// default for detectors of <= 192 bins (768 threads: 85 registers each); DEPTH = 8 (32 images, conflict-free, four angles per
+// default for detectors of <= 184 bins (736 consumer threads + the producer warp, 85 registers each); DEPTH = 8 (32 images, conflict-free, four angles per
 // thread, detector split into chunks of <= 128 bins) is selectable for experiments.
 constexpr int kFwdDepth = 4;
 inline FwdConfig fwd_config_depth(int W, const CtrClassGeom geom[2], int smem_budget)
@@ -601,10 +621,10 @@ inline FwdConfig fwd_config_depth(int W, const CtrClassGeom geom[2], int smem_bu
     } else if (c.kbins) {
         c.JW = round_up((W + 1) / 2, 8);      // bins tx and tx + JW of one angle per thread, two angle slots
         c.NS = 2;
-        if (c.JW * c.depth * c.NS > kFwdMaxThreads) return c;   // R = 0: not available for this detector width
+        if (c.JW * c.depth * c.NS > kFwdMaxConsumers) return c;   // R = 0: not available for this detector width
     } else {
         c.JW = round_up(W, 8);
-        if (c.JW * c.depth > kFwdMaxThreads) return c;
+        if (c.JW * c.depth > kFwdMaxConsumers) return c;
     }
     const int fixed = 128 + round_up(c.NS * c.KA * (int)sizeof(CtrRay), 128);
     const int Upmax = geom[0].Up > geom[1].Up ? geom[0].Up : geom[1].Up;
@@ -623,7 +643,7 @@ inline FwdConfig fwd_config_depth(int W, const CtrClassGeom geom[2], int smem_bu
 template <int INTERP, int EPI>
 inline cudaError_t launch_fwd_ka(const FwdParams& p, const FwdConfig& c, int G, int chunks, cudaStream_t st)
 {
-    dim3 grid(chunks, G, c.jchunks), block(c.JW * c.depth, c.NS);
+    dim3 grid(chunks, G, c.jchunks), block(c.JW * c.depth * c.NS + 32);   // + the producer warp
     cudaError_t e;
     if (c.depth == 4) {   // G counts super-groups of kFwdNB * depth images here
         e = cudaFuncSetAttribute(ctr_fwd_kernel<kFwdNB, 2, INTERP, EPI, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);

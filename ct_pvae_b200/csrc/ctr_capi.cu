@@ -350,6 +350,7 @@ static int forward_impl(const ctr_plan* p, const float* img, float* out, int B, 
     fp.kbins = fc.kbins;
     fp.jwd = fc.JW * fc.depth;
     fp.ns = fc.NS;
+    fp.stages = fc.stages;
     fp.chunks0 = (p->n_cls[0] + NA - 1) / NA;
     const int chunks = fp.chunks0 + (p->n_cls[1] + NA - 1) / NA;
     fp.H = p->H; fp.W = p->W; fp.A = p->A; fp.B = B;

@@ -170,6 +170,7 @@ struct FwdParams {
     int R;                  // key rows per strip (strip holds R+1 packed rows)
     int kbins;              // 1: a thread's KA rays are KA detector bins (JW apart) of ONE angle; 0: KA angles of one bin
     int jwd, ns;            // consumer threads per angle slot (JW bins x DEPTH groups) and angle slots; block = jwd*ns + 32
+    int stages;             // strip buffers in the shared-memory ring (2..4)
     float* sino;            // [B][A][W]   (EPI 0: ray sums; EPI 1: d loglik / d proj, the adjoint's cotangent)
     // fused measurement log-likelihood epilogue (EPI 1), helper_functions.py:355-368
     const float* mask;      // [B][A_all]
@@ -203,8 +204,9 @@ __global__ void __launch_bounds__(kFwdMaxThreads, 1) ctr_fwd_kernel(const FwdPar
     const bool kb = p.kbins != 0;
     const int NA = kb ? NS : NS * KA;
 
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);                 // [2] strip landed (TMA complete_tx)
-    uint64_t* empty = full + 2;                                             // [2] strip consumed (one arrive per consumer warp)
+    const int S = p.stages;                                                 // ring depth (<= 4)
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);                 // [S] strip landed (TMA complete_tx)
+    uint64_t* empty = full + 4;                                             // [S] strip consumed (one arrive per consumer warp)
     CtrRay* rays_s = reinterpret_cast<CtrRay*>(smem_raw + 128);              // NA rays
     const int rays_bytes = round_up(NA * (int)sizeof(CtrRay), 128);
 
@@ -216,33 +218,32 @@ __global__ void __launch_bounds__(kFwdMaxThreads, 1) ctr_fwd_kernel(const FwdPar
     const CtrClassGeom geom = cls ? p.geom[1] : p.geom[0];  // static indices: stays in registers
     const int R = p.R;
     const int strip_floats = (R + 1) * geom.Up * REC;
-    float* buf0 = reinterpret_cast<float*>(smem_raw + 128 + rays_bytes);
-    float* buf1 = buf0 + strip_floats;
+    float* buf0 = reinterpret_cast<float*>(smem_raw + 128 + rays_bytes);   // S strip buffers, strip_floats apart
     const int K = (geom.Vp + R - 1) / R;
     const float* pkg = (cls ? p.pk[1] : p.pk[0]) + (size_t)g * geom.Vp * geom.Up * REC;
 
     for (int k = tid; k < cnt; k += blockDim.x) rays_s[k] = p.rays[first + k];
     if (tid == 0) {
-        mbar_init(&full[0], 1);
-        mbar_init(&full[1], 1);
-        mbar_init(&empty[0], nconsumers / 32);
-        mbar_init(&empty[1], nconsumers / 32);
+        for (int b = 0; b < S; ++b) {
+            mbar_init(&full[b], 1);
+            mbar_init(&empty[b], nconsumers / 32);
+        }
         fence_barrier_init();
     }
     __syncthreads();
 
-    // ---- producer warp: strip k goes to buffer k&1 as soon as every consumer warp has released
-    // strip k-2.  No CTA-wide barrier in the loop: a warp that finishes a strip early moves on to the
+    // ---- producer warp: strip k goes to buffer k%S as soon as every consumer warp has released
+    // strip k-S.  No CTA-wide barrier in the loop: a warp that finishes a strip early moves on to the
     // next (already resident) one, so the ragged ends of the strips overlap instead of idling the SM.
     if (producer) {
         if ((tid & 31) == 0) {
-            for (int k = 0; k < K; ++k) {
-                if (k >= 2) mbar_wait(&empty[k & 1], (uint32_t)(((k - 2) >> 1) & 1));
+            for (int k = 0, b = 0, use = 0; k < K; ++k) {      // b = k % S, use = k / S
+                if (use > 0) mbar_wait(&empty[b], (uint32_t)((use - 1) & 1));
                 const int rows = min(R + 1, geom.Vp - k * R);
                 const uint32_t bytes = (uint32_t)rows * geom.Up * REC * 4u;
-                uint64_t* bar = &full[k & 1];
-                mbar_arrive_expect_tx(bar, bytes);
-                bulk_g2s((k & 1) ? buf1 : buf0, pkg + (size_t)k * R * geom.Up * REC, bytes, bar);
+                mbar_arrive_expect_tx(&full[b], bytes);
+                bulk_g2s(buf0 + (size_t)b * strip_floats, pkg + (size_t)k * R * geom.Up * REC, bytes, &full[b]);
+                if (++b == S) { b = 0; ++use; }
             }
         }
     } else {
@@ -267,9 +268,9 @@ __global__ void __launch_bounds__(kFwdMaxThreads, 1) ctr_fwd_kernel(const FwdPar
             for (int n = 0; n < NB; ++n) acc[q][n] = 0.f;
         }
 
-        for (int k = 0; k < K; ++k) {
-            mbar_wait(&full[k & 1], (uint32_t)((k >> 1) & 1));
-            const float* strip = ((k & 1) ? buf1 : buf0) + gsub * NB;
+        for (int k = 0, b = 0, use = 0; k < K; ++k) {
+            mbar_wait(&full[b], (uint32_t)(use & 1));
+            const float* strip = buf0 + (size_t)b * strip_floats + gsub * NB;
             const float vend = (float)((k + 1) * R + geom.offv);
             const int rbase = k * R + geom.offv;
 #pragma unroll
@@ -289,7 +290,8 @@ __global__ void __launch_bounds__(kFwdMaxThreads, 1) ctr_fwd_kernel(const FwdPar
                 }
             }
             __syncwarp();
-            if ((tid & 31) == 0) mbar_arrive(&empty[k & 1]);   // this warp is done reading the buffer
+            if ((tid & 31) == 0) mbar_arrive(&empty[b]);       // this warp is done reading the buffer
+            if (++b == S) { b = 0; ++use; }
         }
 
         float lsum[NB];
@@ -540,7 +542,7 @@ __global__ void __launch_bounds__(256) ctr_fbp_filter_kernel(const float* __rest
 
 // ------------------------------------------------------------------------------------------ launchers
 struct FwdConfig {
-    int JW, NS, KA, R, jchunks, depth, kbins;
+    int JW, NS, KA, R, jchunks, depth, kbins, stages;
     size_t smem;
     int angles_per_cta() const { return kbins ? NS : NS * KA; }
 };
@@ -548,6 +550,12 @@ struct FwdConfig {
 // r1 measurement: pairing a central with an edge bin per thread (kbins) balances the work per
 // strip but costs more in SIMT efficiency at the shadow edge (C2 0.645 vs 0.600 ms, C4 3.06 vs
 // 2.91 ms), so it stays an opt-in experiment.
+inline int fwd_stages()
+{
+    if (const char* e = getenv("CTR_FWD_STAGES")) { int v = atoi(e); if (v >= 2 && v <= 4) return v; }
+    return 2;
+}
+
 inline bool fwd_use_kbins()
 {
     static const bool on = getenv("CTR_FWD_KBINS") != nullptr;
@@ -589,13 +597,14 @@ inline FwdConfig fwd_config(int W, const CtrClassGeom geom[2], int smem_budget)
     const int Upmax = geom[0].Up > geom[1].Up ? geom[0].Up : geom[1].Up;
     const int Vpmax = geom[0].Vp > geom[1].Vp ? geom[0].Vp : geom[1].Vp;
     const int row_bytes = Upmax * kFwdNB * 4;
-    int rows = (smem_budget - fixed) / (2 * row_bytes);   // rows per buffer = R + 1
+    c.stages = fwd_stages();
+    int rows = (smem_budget - fixed) / (c.stages * row_bytes);   // rows per buffer = R + 1
     if (rows > Vpmax) rows = Vpmax;
     if (rows > 33) rows = 33;   // bigger strips only lengthen the un-overlapped first load
     if (const char* e = getenv("CTR_FWD_R")) { int v = atoi(e); if (v >= 1 && v + 1 <= rows) rows = v + 1; }
     c.R = rows - 1;
     if (c.R < 1) c.R = 0;  // caller treats 0 as "image too wide for the strip buffers"
-    c.smem = (size_t)fixed + 2ull * (size_t)(c.R + 1) * row_bytes;
+    c.smem = (size_t)fixed + (size_t)c.stages * (size_t)(c.R + 1) * row_bytes;
     return c;
 }
 
@@ -636,7 +645,7 @@ inline FwdConfig fwd_config_depth(int W, const CtrClassGeom geom[2], int smem_bu
     if (const char* e = getenv("CTR_FWD_R")) { int v = atoi(e); if (v >= 1 && v + 1 <= rows) rows = v + 1; }
     c.R = rows - 1;
     if (c.R < 1) c.R = 0;
-    c.smem = (size_t)fixed + 2ull * (size_t)(c.R + 1) * row_bytes;
+    c.smem = (size_t)fixed + (size_t)c.stages * (size_t)(c.R + 1) * row_bytes;
     return c;
 }
 

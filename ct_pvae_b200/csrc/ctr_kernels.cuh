@@ -568,7 +568,7 @@ inline FwdConfig fwd_config_depth(int W, const CtrClassGeom geom[2], int smem_bu
 
 inline FwdConfig fwd_config(int W, const CtrClassGeom geom[2], int smem_budget)
 {
-    FwdConfig c;
+    FwdConfig c{};
     c.depth = 1;
     c.kbins = fwd_use_kbins() ? 1 : 0;
     c.KA = 2;
@@ -615,8 +615,9 @@ inline FwdConfig fwd_config(int W, const CtrClassGeom geom[2], int smem_budget)
 constexpr int kFwdDepth = 4;
 inline FwdConfig fwd_config_depth(int W, const CtrClassGeom geom[2], int smem_budget)
 {
-    FwdConfig c;
+    FwdConfig c{};
     c.depth = kFwdDepth;
+    c.stages = 2;
     if (const char* e = getenv("CTR_FWD_DEPTH")) { int v = atoi(e); if (v == 4 || v == 8) c.depth = v; }
     c.kbins = (fwd_use_kbins() && c.depth == 4) ? 1 : 0;
     c.NS = 1;
@@ -639,7 +640,8 @@ inline FwdConfig fwd_config_depth(int W, const CtrClassGeom geom[2], int smem_bu
     const int Upmax = geom[0].Up > geom[1].Up ? geom[0].Up : geom[1].Up;
     const int Vpmax = geom[0].Vp > geom[1].Vp ? geom[0].Vp : geom[1].Vp;
     const int row_bytes = Upmax * kFwdNB * c.depth * 4;
-    int rows = (smem_budget - fixed) / (2 * row_bytes);
+    c.stages = fwd_stages();
+    int rows = (smem_budget - fixed) / (c.stages * row_bytes);
     if (rows > Vpmax) rows = Vpmax;
     if (rows > 33) rows = 33;
     if (const char* e = getenv("CTR_FWD_R")) { int v = atoi(e); if (v >= 1 && v + 1 <= rows) rows = v + 1; }

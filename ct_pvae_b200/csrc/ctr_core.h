@@ -128,18 +128,28 @@ CTR_HD void ctr_round_fi(float v, float& f, int& i)
 #endif
 }
 
-// Smallest i in [0,H] with sgn*coord(i) > bound (strict) or >= bound.  float32
-// rounding is monotone, so coord(i) is monotone in i and the predicate flips once.
+// Smallest i in [0,H] with sgn*coord(i) > bound (strict) or >= bound.  float32 rounding is
+// monotone, so coord(i) is monotone in i and the predicate flips once: a closed-form estimate
+// of the crossing is corrected with the exact float32 predicate (usually 1-2 evaluations; a ray
+// almost parallel to the bound may walk further, still at most H steps).
 CTR_HD int ctr_search(float p0j, float c1, float c2, float sgn, float bound, bool strict, int H)
 {
-    int lo = 0, hi = H;
-    while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        float g = sgn * ctr_coord(p0j, c1, (float)mid, c2);
-        bool p = strict ? (g > bound) : (g >= bound);
-        if (p) hi = mid; else lo = mid + 1;
+    const float base = sgn * CTR_ADD(p0j, c2);          // g(i) ~ base + |c1| * i
+    const float slope = fabsf(c1);
+    if (slope == 0.f)                                   // coordinate does not depend on i: all or nothing
+        return (strict ? (base > bound) : (base >= bound)) ? 0 : H;
+    int i = 0;
+    {
+        float x = (bound - base) / slope;               // g(i) > bound  <=>  i > x   (real arithmetic)
+        x = fminf(fmaxf(x, -1.f), (float)H);            // also maps +-inf into range; NaN -> -1
+        i = (int)floorf(x) + 1;
+        if (i > H) i = H;
     }
-    return lo;
+#define CTR_PRED(ii) (strict ? (sgn * ctr_coord(p0j, c1, (float)(ii), c2) > bound) : (sgn * ctr_coord(p0j, c1, (float)(ii), c2) >= bound))
+    while (i > 0 && CTR_PRED(i - 1)) --i;
+    while (i < H && !CTR_PRED(i)) ++i;
+#undef CTR_PRED
+    return i;
 }
 
 // [ib, ie): the steps i of ray j whose sample lies strictly inside the footprint

@@ -427,7 +427,8 @@ int ctr_radon_adjoint_scaled(const ctr_plan* p, const float* dsino, float* dimg,
     {
         dim3 grid((p->W + 2 + 127) / 128, p->A, G), block(128);
         ProfScope prof(CTR_K_PACK_SINO, st);
-        if (NBb == 16) ctr::ctr_pack_sino_kernel<16><<<grid, block, 0, st>>>(dsino, B, p->A, p->W, spk);
+        if (NBb == 32) ctr::ctr_pack_sino_kernel<32><<<grid, block, 0, st>>>(dsino, B, p->A, p->W, spk);
+        else if (NBb == 16) ctr::ctr_pack_sino_kernel<16><<<grid, block, 0, st>>>(dsino, B, p->A, p->W, spk);
         else ctr::ctr_pack_sino_kernel<8><<<grid, block, 0, st>>>(dsino, B, p->A, p->W, spk);
         ctr::launch_counter()++;
         CTR_CUDA(cudaGetLastError());
@@ -460,7 +461,7 @@ int ctr_fbp_plan_create(const double* theta, int A, int P, int x_size, int y_siz
     *out = nullptr;
     if (!theta || !fr || A <= 0 || P <= 0 || x_size <= 0 || y_size <= 0)
         return fail(CTR_EINVAL, "ctr_fbp_plan_create: bad argument");
-    if ((size_t)P * (16 + 2) * 4 > 200 * 1024) return fail(CTR_EUNSUPPORTED, "ctr_fbp_plan_create: P too large for the smem filter");
+    if ((size_t)P * (32 + 2) * 4 > 200 * 1024) return fail(CTR_EUNSUPPORTED, "ctr_fbp_plan_create: P too large for the smem filter");
     ctr_fbp_plan* p = new (std::nothrow) ctr_fbp_plan();
     if (!p) return fail(CTR_EINVAL, "ctr_fbp_plan_create: out of host memory");
     p->device = device; p->A = A; p->P = P; p->x_size = x_size; p->y_size = y_size;
@@ -518,7 +519,10 @@ int ctr_fbp(const ctr_fbp_plan* p, const float* sino, int A, float* recon, int B
         const size_t smem = (size_t)p->P * (NBb + 2) * sizeof(float);
         dim3 grid(p->A, G), block(256);
         ProfScope prof(CTR_K_FBP_FILTER, st);
-        if (NBb == 16) {
+        if (NBb == 32) {
+            CTR_CUDA(cudaFuncSetAttribute(ctr::ctr_fbp_filter_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ctr::ctr_fbp_filter_kernel<32><<<grid, block, smem, st>>>(sino, p->d_h, B, p->A, p->P, spk);
+        } else if (NBb == 16) {
             CTR_CUDA(cudaFuncSetAttribute(ctr::ctr_fbp_filter_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             ctr::ctr_fbp_filter_kernel<16><<<grid, block, smem, st>>>(sino, p->d_h, B, p->A, p->P, spk);
         } else {

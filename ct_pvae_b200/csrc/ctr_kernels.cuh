@@ -693,10 +693,15 @@ inline size_t bp_smem_bytes(int win, int NB)
     return 128 + 2 * kBpAB * 8 * 4 + 2 * kBpAB * 2 * 8 + 2ull * kBpAB * (size_t)win * NB * 4;
 }
 
-// Two shapes: 16 images per thread on 32x8-pixel tiles for real batches, 8 images on
-// 32x16 tiles when the batch is tiny (fewer idle accumulator lanes).
-inline int bp_nb_for_batch(int B) { return B > 8 ? 16 : 8; }
-inline int bp_th_for_batch(int B) { return B > 8 ? 8 : 16; }
+// Three shapes: the per-pixel geometry (~130 instructions for the exact adjoint) is shared by
+// all images of a thread, so big batches take 32 images per thread, medium ones 16 (both on
+// 32x8-pixel tiles), tiny ones 8 on 32x16 tiles (fewer idle accumulator lanes).
+inline int bp_nb_for_batch(int B)
+{
+    static const int forced = getenv("CTR_BP_NB") ? atoi(getenv("CTR_BP_NB")) : 0;   // developer override
+    if (forced == 8 || forced == 16 || forced == 32) return forced;
+    return B >= 24 ? 32 : (B > 8 ? 16 : 8);
+}
 
 template <int NB, int TH, int MINB, int MODE, int INTERP>
 inline cudaError_t launch_bp_cfg(BpParams p, cudaStream_t st)
@@ -716,7 +721,9 @@ inline cudaError_t launch_bp_cfg(BpParams p, cudaStream_t st)
 template <int MODE, int INTERP>
 inline cudaError_t launch_bp(const BpParams& p, cudaStream_t st)
 {
-    if (bp_nb_for_batch(p.B) == 16) return launch_bp_cfg<16, 8, 3, MODE, INTERP>(p, st);
+    const int nb = bp_nb_for_batch(p.B);
+    if (nb == 32) return launch_bp_cfg<32, 8, 2, MODE, INTERP>(p, st);
+    if (nb == 16) return launch_bp_cfg<16, 8, 3, MODE, INTERP>(p, st);
     return launch_bp_cfg<8, 16, 2, MODE, INTERP>(p, st);
 }
 

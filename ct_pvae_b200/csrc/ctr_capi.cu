@@ -289,11 +289,17 @@ size_t ctr_forward_workspace_bytes(const ctr_plan* p, int B)
     return 2 * pack_bytes(p, B);
 }
 
+// sinogram pack bytes; the exact adjoint may use wider image groups than the 2-tap gathers,
+// so size for the larger padding
 static size_t spk_bytes(int B, int A, int W)
 {
-    const size_t NB = (size_t)ctr::bp_nb_for_batch(B);
-    const size_t G = ((size_t)B + NB - 1) / NB;
-    return align_up(G * (size_t)A * (size_t)(W + 2) * NB * sizeof(float), 256);
+    size_t best = 0;
+    for (int mode : {CTR_ADJ_EXACT, CTR_ADJ_TF}) {
+        const size_t NB = (size_t)ctr::bp_nb_for_batch(B, mode);
+        const size_t G = ((size_t)B + NB - 1) / NB;
+        best = std::max(best, G * (size_t)A * (size_t)(W + 2) * NB * sizeof(float));
+    }
+    return align_up(best, 256);
 }
 
 size_t ctr_adjoint_workspace_bytes(const ctr_plan* p, int B)
@@ -421,7 +427,7 @@ int ctr_radon_adjoint_scaled(const ctr_plan* p, const float* dsino, float* dimg,
     DeviceGuard guard(p->device);
     if (!guard.ok) return fail_cuda(guard.err, "cudaSetDevice");
     cudaStream_t st = (cudaStream_t)stream;
-    const int NBb = ctr::bp_nb_for_batch(B);
+    const int NBb = ctr::bp_nb_for_batch(B, mode == CTR_ADJOINT_EXACT ? CTR_ADJ_EXACT : CTR_ADJ_TF);
     const int G = (B + NBb - 1) / NBb;
     float* spk = (float*)ws;
     {
@@ -512,7 +518,7 @@ int ctr_fbp(const ctr_fbp_plan* p, const float* sino, int A, float* recon, int B
     DeviceGuard guard(p->device);
     if (!guard.ok) return fail_cuda(guard.err, "cudaSetDevice");
     cudaStream_t st = (cudaStream_t)stream;
-    const int NBb = ctr::bp_nb_for_batch(B);
+    const int NBb = ctr::bp_nb_for_batch(B, CTR_ADJ_FBP);
     const int G = (B + NBb - 1) / NBb;
     float* spk = (float*)ws;
     {

@@ -374,6 +374,8 @@ struct BpParams {
 
 // bins a 32 x TH pixel tile can touch for one angle: |u| extent sqrt(31^2+(TH-1)^2) + 6 bins of slack
 __host__ __device__ constexpr int bp_win(int TH) { return TH <= 8 ? 40 : 44; }
+// angles staged per batch: 4 for the small 32x4 tiles (4 CTAs per SM must fit in shared memory)
+__host__ __device__ constexpr int bp_ab(int TH) { return TH <= 4 ? 4 : kBpAB; }
 
 // One CTA = 32 x TH pixel tile x image group of NB.  Angles are processed in batches
 // of AB: lanes 0..AB-1 of warp 0 each own one angle of the batch -- they compute the
@@ -384,7 +386,7 @@ __host__ __device__ constexpr int bp_win(int TH) { return TH <= 8 ? 40 : 44; }
 template <int NB, int TH, int MINB, int MODE, int INTERP>
 __global__ void __launch_bounds__(kBpTW * TH, MINB) ctr_bp_kernel(const BpParams p)
 {
-    constexpr int TW = kBpTW, AB = kBpAB, NBP = NB / 4;
+    constexpr int TW = kBpTW, AB = bp_ab(TH), NBP = NB / 4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);            // [2]
     int* jb = reinterpret_cast<int*>(smem_raw + 16);                   // [2][AB]
@@ -688,19 +690,22 @@ inline cudaError_t launch_fwd_ka(const FwdParams& p, const FwdConfig& c, int G, 
     return cudaGetLastError();
 }
 
-inline size_t bp_smem_bytes(int win, int NB)
+inline size_t bp_smem_bytes(int win, int NB, int AB)
 {
-    return 128 + 2 * kBpAB * 8 * 4 + 2 * kBpAB * 2 * 8 + 2ull * kBpAB * (size_t)win * NB * 4;
+    return 128 + 2 * kBpAB * 8 * 4 + 2 * kBpAB * 2 * 8 + 2ull * AB * (size_t)win * NB * 4;
 }
 
 // Three shapes: the per-pixel geometry (~130 instructions for the exact adjoint) is shared by
 // all images of a thread, so big batches take 32 images per thread, medium ones 16 (both on
 // 32x8-pixel tiles), tiny ones 8 on 32x16 tiles (fewer idle accumulator lanes).
-inline int bp_nb_for_batch(int B)
+// (r1: 32 images pay off only for the geometry-heavy exact adjoint -- C4 5.63 -> 4.64 ms;
+// the 2-tap TF-compat and FBP gathers lose occupancy and stay at 16.)
+inline int bp_nb_for_batch(int B, int mode)
 {
     static const int forced = getenv("CTR_BP_NB") ? atoi(getenv("CTR_BP_NB")) : 0;   // developer override
     if (forced == 8 || forced == 16 || forced == 32) return forced;
-    return B >= 24 ? 32 : (B > 8 ? 16 : 8);
+    if (B <= 8) return 8;
+    return (mode == CTR_ADJ_EXACT && B >= 24) ? 32 : 16;
 }
 
 template <int NB, int TH, int MINB, int MODE, int INTERP>
@@ -709,7 +714,7 @@ inline cudaError_t launch_bp_cfg(BpParams p, cudaStream_t st)
     const int G = (p.B + NB - 1) / NB;
     dim3 grid((p.Y + kBpTW - 1) / kBpTW, (p.X + TH - 1) / TH, G), block(kBpTW, TH);
     if (p.win > bp_win(TH)) p.win = bp_win(TH);
-    const size_t smem = bp_smem_bytes(p.win, NB);
+    const size_t smem = bp_smem_bytes(p.win, NB, bp_ab(TH));
     cudaError_t e = cudaFuncSetAttribute(ctr_bp_kernel<NB, TH, MINB, MODE, INTERP>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -721,8 +726,12 @@ inline cudaError_t launch_bp_cfg(BpParams p, cudaStream_t st)
 template <int MODE, int INTERP>
 inline cudaError_t launch_bp(const BpParams& p, cudaStream_t st)
 {
-    const int nb = bp_nb_for_batch(p.B);
-    if (nb == 32) return launch_bp_cfg<32, 8, 2, MODE, INTERP>(p, st);
+    const int nb = bp_nb_for_batch(p.B, MODE);
+    if (nb == 32) {
+        static const bool small_tiles = getenv("CTR_BP_TH4") != nullptr;   // developer switch
+        if (small_tiles) return launch_bp_cfg<32, 4, 4, MODE, INTERP>(p, st);
+        return launch_bp_cfg<32, 8, 2, MODE, INTERP>(p, st);
+    }
     if (nb == 16) return launch_bp_cfg<16, 8, 3, MODE, INTERP>(p, st);
     return launch_bp_cfg<8, 16, 2, MODE, INTERP>(p, st);
 }

@@ -218,7 +218,7 @@ def run_reference(args, wl):
     print(json.dumps(line), flush=True)
 
 
-def vae_training_leg(dev, iters=20, warm=3):
+def vae_training_leg(dev, iters=20, warm=3, seed=0, world=1):
     """End-to-end VAE training it/s on BASELINE configs[0] (README quick-start: 50 foam images
     128x128, 180 angles, -b 5 --nsa 20 --api 20 --ns 2 --pnm 1e4 --normal --random), with the
     torch restatement of the reference's networks/loss (ct_pvae_b200/vae.py) around the fused
@@ -227,19 +227,20 @@ def vae_training_leg(dev, iters=20, warm=3):
 
     from ct_pvae_b200 import vae
 
-    torch.manual_seed(0)
+    torch.manual_seed(0)            # identical initial weights on every rank
     N, X, A, b, nsa, api, ns, pnm = 50, 128, 180, 5, 20, 20, 2, 1e4
     theta = np.linspace(0, np.pi, A, endpoint=False)
-    imgs = synthetic_foam_torch(N, X, dev, seed=123)
+    imgs = synthetic_foam_torch(N, X, dev, seed=123 + seed)
     sino = vae.create_sinogram(imgs, theta, pad=True, interpolation="bilinear")
     masks, meas = vae.create_all_masks(sino, A, pnm, num_sparse_angles=nsa, random=True)
     enc_in = vae.iradon_all(meas, masks, theta, X, X)
     model = vae.CTVAE(X, X, num_filters=1).to(dev)
-    g = torch.Generator().manual_seed(1)
+    g = torch.Generator().manual_seed(1 + seed)
+    ga = torch.Generator().manual_seed(7)      # the angle minibatch is shared by all ranks
 
     def one():
         idx = torch.randint(0, N, (b,), generator=g).to(dev)
-        angles_i = torch.randperm(A, generator=g)[:api]
+        angles_i = torch.randperm(A, generator=ga)[:api]
         loss, _, _, _ = model.train_step(meas[idx], masks[idx], enc_in[idx], pnm, theta, angles_i=angles_i, num_samples=ns)
         return loss
 
@@ -251,8 +252,9 @@ def vae_training_leg(dev, iters=20, warm=3):
         loss = one()
     torch.cuda.synchronize(dev)
     dt = time.perf_counter() - t0
-    return {"it_per_s": iters / dt, "ms_per_it": dt / iters * 1e3, "final_loss": float(loss),
-            "config": "README quick-start: b=5, 128x128, 180 angles, nsa=20, api=20, ns=2, pnm=1e4, --normal --random"}
+    return {"it_per_s": iters / dt, "ms_per_it": dt / iters * 1e3, "final_loss": float(loss), "global_batch": b * world,
+            "config": "README quick-start: b=5 per GPU, 128x128, 180 angles, nsa=20, api=20, ns=2, pnm=1e4, --normal --random"
+                      + ("; batch-sharded, gradients averaged with one NCCL all-reduce" if world > 1 else "")}
 
 
 # ----------------------------------------------------------------------------------------- GPU arm
@@ -359,11 +361,14 @@ def run_ours(args, wl):
         side["fbp_ms"] = best_ms(lambda: ops.fbp(cot, fplan))
         side["fbp_gupdates_per_s"] = B * A_loc * X * X / (side["fbp_ms"] * 1e-3) / 1e9
         side["fwd_nearest_gray_sums_per_s"] = B * A_loc * P / (side["fwd_nearest_ms"] * 1e-3) / 1e9
-        if not args.no_train_leg:
-            try:
-                side["vae_train"] = vae_training_leg(dev)
-            except Exception as exc:  # the restated VAE is a caller, never a reason to lose the headline
-                side["vae_train"] = {"error": repr(exc)[:200]}
+    if not args.no_side_legs and not args.no_train_leg and (rank == 0 or world > 1):
+        # world > 1: every rank trains on its own batch slice, gradients averaged over NCCL
+        try:
+            leg = vae_training_leg(dev, seed=rank, world=world)
+            if rank == 0:
+                side["vae_train"] = leg
+        except Exception as exc:  # the restated VAE is a caller, never a reason to lose the headline
+            side["vae_train"] = {"error": repr(exc)[:200]}
     sync_all()
 
     # ---- e2e: the public API with pinned HOST buffers, copies inside the timed region

@@ -235,6 +235,7 @@ class CTVAE(nn.Module):
         if training:
             self.optimizer.zero_grad(set_to_none=True)
             loss.backward()
+            self._average_gradients()
             for p in self.parameters():
                 if p.grad is not None:
                     torch.nan_to_num_(p.grad, nan=0.0)
@@ -243,6 +244,25 @@ class CTVAE(nn.Module):
                         p.grad.mul_(norm / n)
             self.optimizer.step()
         return loss.detach(), out_dists, kl.detach(), loglik.detach()
+
+
+    def _average_gradients(self):
+        """Batch-sharded data parallelism (BASELINE configs[2]): every rank holds its own slice of
+        the batch; one flat all-reduce averages the network gradients.  The projector itself
+        needs no collective in this mode."""
+        import torch.distributed as dist
+
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return
+        grads = [p.grad for p in self.parameters() if p.grad is not None]
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        dist.all_reduce(flat)
+        flat /= dist.get_world_size()
+        off = 0
+        for g in grads:
+            n = g.numel()
+            g.copy_(flat[off:off + n].view_as(g))
+            off += n
 
 
 # ---------------------------------------------------------------------------------- data preparation

@@ -290,10 +290,19 @@ def run_ours(args, wl):
 
     def step():
         s = ops.radon_forward(img, plan, iid)
-        g = ops.radon_adjoint(cot, plan, iid, mid)
-        if angle_mode:
-            dist.all_reduce(g)  # sum of the partial back-projections over the angle shards
-        return s, g
+        if not angle_mode:
+            return s, ops.radon_adjoint(cot, plan, iid, mid)
+        # angle-sharded: sum the partial back-projections over the angle shards.  The batch is cut in
+        # two so the NCCL all-reduce of one half overlaps the adjoint kernels of the other.
+        half = max(32, (B // 2 + 31) // 32 * 32)
+        parts, works = [], []
+        for lo in range(0, B, half):
+            g = ops.radon_adjoint(cot[lo:lo + half], plan, iid, mid)
+            works.append(dist.all_reduce(g, async_op=True))
+            parts.append(g)
+        for w in works:
+            w.wait()
+        return s, parts
 
     def sync_all():
         torch.cuda.synchronize(dev)

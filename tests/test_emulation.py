@@ -67,3 +67,34 @@ def test_emulated_kernels_random_angles(emu, orc):
         s = np.full((2, 9, W), np.nan, np.float32)
         emu.emu_forward(P(img), 2, 40, 40, H, W, padx, pady, P(t), 9, interp, 7, P(s))
         assert rel_l2(s, orc.forward(img, th, True, interp)) <= 1e-6
+
+
+# ---- property-based sweep: random shapes, angles (any sign / magnitude), pad, strip and tile sizes ----
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=30, deadline=None)
+@given(B=st.integers(1, 6), X=st.integers(1, 28), Y=st.integers(1, 28), pad=st.booleans(), R=st.integers(1, 9),
+       th=st.lists(st.floats(-7.0, 7.0, allow_nan=False, width=32), min_size=1, max_size=6), seed=st.integers(0, 2 ** 16))
+def test_emulated_kernels_property(emu, orc, B, X, Y, pad, R, th, seed):
+    rng = np.random.default_rng(seed)
+    img = rng.random((B, X, Y), dtype=np.float32)
+    th = np.asarray(th, np.float64)
+    A = len(th)
+    H, W, padx, pady = orc.frame_of(X, Y, pad)
+    t = orc.make_transforms(th, H, W)
+    ti = orc.invert_transforms(t)
+    y = rng.random((B, A, W), dtype=np.float32)
+    for interp in (0, 1):
+        want = orc.forward(img, th, pad, interp)
+        s = np.full((B, A, W), np.nan, np.float32)
+        emu.emu_forward(P(img), B, X, Y, H, W, padx, pady, P(t), A, interp, R, P(s))
+        assert np.abs(s - want).max() <= 2e-5 * max(1.0, np.abs(want).max())
+        sd = np.full((B, A, W), np.nan, np.float32)
+        emu.emu_forward_depth(P(img), B, X, Y, H, W, padx, pady, P(t), A, interp, R, P(sd))
+        np.testing.assert_array_equal(sd, s)
+        for mode, table, fn in ((0, t, orc.adjoint_exact), (1, ti, orc.adjoint_tf)):
+            g = np.full((B, X, Y), np.nan, np.float32)
+            emu.emu_adjoint(P(y), B, X, Y, H, W, padx, pady, P(table), A, interp, mode, 32, 8, 40, P(g))
+            gw = fn(y, th, X, Y, pad, interp)
+            assert np.abs(g - gw).max() <= 2e-5 * max(1.0, np.abs(gw).max())

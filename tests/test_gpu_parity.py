@@ -90,6 +90,27 @@ def test_large_and_rectangular_frames(cp, orc, B, X, Y, A, pad):
         assert rel_l2(g.cpu().numpy(), orc.adjoint_exact(y, th, X, Y, pad, IID[interp])) <= TOL
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_randomised_shapes(cp, orc, seed):
+    """Random batch / image / angle-set shapes (ragged against every internal group size)."""
+    rng = np.random.default_rng(100 + seed)
+    B, X, Y, A = int(rng.integers(1, 41)), int(rng.integers(1, 90)), int(rng.integers(1, 90)), int(rng.integers(1, 14))
+    pad = bool(rng.integers(0, 2))
+    th = rng.uniform(-4, 4, A)
+    img = rng.random((B, X, Y), dtype=np.float32)
+    W = orc.frame_of(X, Y, pad)[1]
+    y = rng.random((B, A, W), dtype=np.float32)
+    for interp in INTERPS:
+        got = cp.project_tf_fast(torch.from_numpy(img).cuda().unsqueeze(-1), th, pad=pad, dim=2, integrate_vae=True,
+                                 interpolation=interp)[..., 0].cpu().numpy()
+        want = orc.forward(img, th, pad, IID[interp])
+        assert np.abs(got - want).max() <= 2e-5 * max(1.0, np.abs(want).max())
+        for mode, fn in (("exact", orc.adjoint_exact), ("tf_compat", orc.adjoint_tf)):
+            g = cp.backproject(torch.from_numpy(y).cuda(), th, X, Y, pad=pad, interpolation=interp, adjoint=mode).cpu().numpy()
+            gw = fn(y, th, X, Y, pad, IID[interp])
+            assert np.abs(g - gw).max() <= 2e-5 * max(1.0, np.abs(gw).max())
+
+
 def test_random_angles_and_signs(cp, orc):
     rng = np.random.default_rng(2)
     th = rng.uniform(-7, 7, 23)

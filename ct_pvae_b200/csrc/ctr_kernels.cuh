@@ -1,9 +1,11 @@
 // ctr_kernels.cuh -- sm_100a kernels of the Radon path and their launchers.
 //
-//   K0  ctr_pack_image_kernel   [B,X,Y] -> batch-interleaved, halo-padded packs (row-major + transposed)
-//   K0' ctr_pack_sino_kernel    [B,A,W] -> [G,A,W+2,NB] interleaved sinogram rows with zero halo bins
+//   K0  ctr_pack_image_kernel   [B,X,Y] -> batch-interleaved, halo-padded packs (row-major + transposed),
+//                               4 or 16 images per pixel record
+//   K0' ctr_pack_sino_kernel    [B,A,W] -> [G,A,NB/4,W+2,4] sinogram planes with zero halo bins
 //   K1  ctr_fwd_kernel          ray-driven forward projector (project_tf_fast / project_tf_low_mem,
-//                               /root/reference/ctvae/forward_functions.py:80-123, :49-78)
+//                               /root/reference/ctvae/forward_functions.py:80-123, :49-78), optionally with
+//                               the fused measurement log-likelihood epilogue (helper_functions.py:355-368)
 //   K2  ctr_bp_kernel<EXACT>    pixel-driven gather adjoint, the exact transpose of K1 (no atomics)
 //   K2' ctr_bp_kernel<TF>       TensorFlow's registered gradient of the projector graph
 //   K3a ctr_fbp_filter_kernel   circular row filter in shared memory (fbp_tensorflow.py:49-50)
@@ -11,10 +13,12 @@
 //
 // Data movement: image strips (K1) and sinogram bin windows (K2/K3b) are staged in
 // shared memory by the TMA engine with 1-D bulk copies (cp.async.bulk, SASS UBLKCP)
-// completing on mbarriers, double buffered.  The packs exist so that every staged
-// block is ONE contiguous, 16-byte aligned range in HBM and so that one 128-bit
-// shared-memory load serves 4 images: the per-sample geometry (coordinates, floor,
-// weights, address) is computed once per NB images.
+// completing on mbarriers.  K1 runs a producer warp / consumer warps ring (full + empty
+// mbarriers per strip buffer, no CTA-wide barrier in the loop); K2/K3b double-buffer
+// batches of 8 angles.  The packs exist so that every staged block is ONE contiguous,
+// 16-byte aligned range in HBM and so that one 128-bit shared-memory load serves 4
+// images: the per-sample geometry (coordinates, floor, weights, address) is computed
+// once per 4 (K1) or 16-32 (K2) images.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -161,7 +165,7 @@ __global__ void __launch_bounds__(128) ctr_pack_sino_kernel(const float* __restr
 
 // ------------------------------------------------------------------------------------------ K1 forward
 struct FwdParams {
-    const float* pk[2];     // packed images per class  [G][Vp][Up][NB]
+    const float* pk[2];     // packed images per class  [G][Vp][Up][NB*DEPTH]
     CtrClassGeom geom[2];
     const CtrRay* rays;     // class-sorted ray table [A]
     int n_cls[2];           // angles per class
@@ -178,7 +182,7 @@ struct FwdParams {
     const int* amap;        // [A] plan angle -> column of mask/meas (the angles_i gather), or null = identity
     int A_all;
     float pnm, sqrt_reg;    // poisson_noise_multiplier, sqrt_reg
-    float* partial;         // [gridDim.z*gridDim.x][G*NB] per-CTA log-likelihood sums
+    float* partial;         // [gridDim.z*gridDim.x][G*NB*DEPTH] per-CTA log-likelihood sums
 };
 
 // One CTA = (angle chunk of NS*KA same-class angles) x (image group of NB) x (detector chunk of JW bins).

@@ -273,7 +273,7 @@ int ctr_plan_tables(const ctr_plan* p, float* fwd, float* inv)
 static const ctr::FwdConfig& fwd_cfg_for(const ctr_plan* p, int B)
 {
     static const bool no_depth = getenv("CTR_FWD_NODEPTH") != nullptr;   // developer switch for A/B timing
-    return (!no_depth && p->fcd.R >= 1 && B >= 12) ? p->fcd : p->fc;
+    return (!no_depth && p->fcd.R >= 1 && B >= 3 * p->fcd.depth) ? p->fcd : p->fc;
 }
 
 static size_t pack_bytes(const ctr_plan* p, int B)

@@ -614,17 +614,18 @@ inline FwdConfig fwd_config(int W, const CtrClassGeom geom[2], int smem_budget)
     return c;
 }
 
-// Depth-first shapes: DEPTH image groups of 4 per pixel record, (up to) 1024-thread CTAs of
-// JW detector bins x DEPTH groups.  DEPTH = 4 (16 images, two angles per thread) is the
-// default for detectors of <= 184 bins (736 consumer threads + the producer warp, 85 registers each); DEPTH = 8 (32 images, conflict-free, four angles per
+// Depth-first shapes: DEPTH image groups of 4 per pixel record, CTAs of JW detector bins x
+// DEPTH groups (<= 736 consumer threads + the producer warp, 85 registers each).  DEPTH = 4
+// (16 images, two angles per thread) for detectors of <= 184 bins, DEPTH = 2 (8 images) up to 368 bins; DEPTH = 8 (32 images, conflict-free, four angles per
 // thread, detector split into chunks of <= 128 bins) is selectable for experiments.
 constexpr int kFwdDepth = 4;
 inline FwdConfig fwd_config_depth(int W, const CtrClassGeom geom[2], int smem_budget)
 {
     FwdConfig c{};
-    c.depth = kFwdDepth;
+    // 16 images per record while 4 lanes per bin fit the CTA (P <= 184), else 8 images (P <= 368)
+    c.depth = (round_up(W, 8) * kFwdDepth <= kFwdMaxConsumers) ? kFwdDepth : 2;
     c.stages = 2;
-    if (const char* e = getenv("CTR_FWD_DEPTH")) { int v = atoi(e); if (v == 4 || v == 8) c.depth = v; }
+    if (const char* e = getenv("CTR_FWD_DEPTH")) { int v = atoi(e); if (v == 2 || v == 4 || v == 8) c.depth = v; }
     c.kbins = (fwd_use_kbins() && c.depth == 4) ? 1 : 0;
     c.NS = 1;
     c.KA = (c.depth == 8) ? 4 : 2;
@@ -639,7 +640,7 @@ inline FwdConfig fwd_config_depth(int W, const CtrClassGeom geom[2], int smem_bu
         c.NS = 2;
         if (c.JW * c.depth * c.NS > kFwdMaxConsumers) return c;   // R = 0: not available for this detector width
     } else {
-        c.JW = round_up(W, 8);
+        c.JW = round_up(W, 32 / c.depth);
         if (c.JW * c.depth > kFwdMaxConsumers) return c;
     }
     const int fixed = 128 + round_up(c.NS * c.KA * (int)sizeof(CtrRay), 128);
@@ -666,6 +667,13 @@ inline cudaError_t launch_fwd_ka(const FwdParams& p, const FwdConfig& c, int G, 
         e = cudaFuncSetAttribute(ctr_fwd_kernel<kFwdNB, 2, INTERP, EPI, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
         if (e != cudaSuccess) return e;
         ctr_fwd_kernel<kFwdNB, 2, INTERP, EPI, 4><<<grid, block, c.smem, st>>>(p);
+        launch_counter()++;
+        return cudaGetLastError();
+    }
+    if (c.depth == 2) {
+        e = cudaFuncSetAttribute(ctr_fwd_kernel<kFwdNB, 2, INTERP, EPI, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+        if (e != cudaSuccess) return e;
+        ctr_fwd_kernel<kFwdNB, 2, INTERP, EPI, 2><<<grid, block, c.smem, st>>>(p);
         launch_counter()++;
         return cudaGetLastError();
     }

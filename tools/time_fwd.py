@@ -1,9 +1,12 @@
-"""Time the forward kernel alone on C2 / C4-slice (developer tool; honours CTR_FWD_* overrides)."""
+"""Time the forward kernel alone (developer tool; honours CTR_FWD_* overrides)."""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ct_pvae_b200 import _lib, ops
-for (B, X, A) in ((256, 128, 180), (16, 512, 720)):
+shapes = [(256, 128, 180), (16, 512, 720)]
+if os.environ.get("TIME_FWD_SHAPES"):
+    shapes = [tuple(int(v) for v in s.split("x")) for s in os.environ["TIME_FWD_SHAPES"].split(",")]
+for (B, X, A) in shapes:
     th = np.linspace(0, np.pi, A, endpoint=False)
     plan = _lib.get_plan(th, X, X, True, 0)
     img = torch.rand((B, X, X), device="cuda")
@@ -15,5 +18,5 @@ for (B, X, A) in ((256, 128, 180), (16, 512, 720)):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); ops.radon_forward(img, plan, iid); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
         out.append(min(ts))
-    print(f"B={B} X={X} A={A}: bilinear {out[0]:.3f} ms  nearest {out[1]:.3f} ms   env=" +
+    print(f"B={B} X={X} A={A} P={plan.W}: bilinear {out[0]:.3f} ms  nearest {out[1]:.3f} ms   env=" +
           " ".join(f"{k}={v}" for k, v in os.environ.items() if k.startswith("CTR_FWD")), flush=True)

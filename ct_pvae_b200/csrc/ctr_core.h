@@ -352,11 +352,12 @@ CTR_HD void ctr_adj_tf(const float* ti, int H, int W, float px, float py,
             float y0[NB], y1[NB];
             ctr_ld_bins<NB>(ywin, pstride, (int)xf + 1 - jbase_p, y0);
             ctr_ld_bins<NB>(ywin, pstride, (int)xf + 2 - jbase_p, y1);
+            // TF: (yc-y)*v_f + (y-yf)*v_c with v_f = v_c = the row interpolation (the cotangent is
+            // constant along rows), i.e. (wyf + wyc) * (wxf*y0 + wxc*y1); fused here (<= 1 ulp apart)
+            const float wy = wyf + wyc;
+            const float a0 = wy * wxf, a1 = wy * wxc;
 #pragma unroll
-            for (int q = 0; q < NB; ++q) {
-                const float vrow = CTR_ADD(CTR_MUL(wxf, y0[q]), CTR_MUL(wxc, y1[q]));
-                acc[q] += CTR_ADD(CTR_MUL(wyf, vrow), CTR_MUL(wyc, vrow));
-            }
+            for (int q = 0; q < NB; ++q) acc[q] = fmaf(a1, y1[q], fmaf(a0, y0[q], acc[q]));
         }
     }
 }
@@ -380,8 +381,9 @@ CTR_HD void ctr_adj_fbp(const double* cs, int P, double xpr, double ypr,
     float yb[NB], ya[NB];
     ctr_ld_bins<NB>(ywin, pstride, (int)below + 1 - jbase_p, yb);
     ctr_ld_bins<NB>(ywin, pstride, (int)above + 1 - jbase_p, ya);
+    const float beta = 1.f - alpha;
 #pragma unroll
-    for (int q = 0; q < NB; ++q) acc[q] += (1.f - alpha) * yb[q] + alpha * ya[q];
+    for (int q = 0; q < NB; ++q) acc[q] = fmaf(alpha, ya[q], fmaf(beta, yb[q], acc[q]));
 }
 
 // Measurement log-likelihood of one ray-sum (ctvae/helper_functions.py:359-368):

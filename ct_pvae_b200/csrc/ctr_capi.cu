@@ -280,7 +280,8 @@ static size_t pack_bytes(const ctr_plan* p, int B)
 {
     const size_t rec = (size_t)ctr::kFwdNB * fwd_cfg_for(p, B).depth;
     const size_t G = ((size_t)B + rec - 1) / rec;
-    return align_up(G * (size_t)(p->X + 2) * (size_t)(p->Y + 2) * rec * sizeof(float), 256);
+    const size_t px0 = (size_t)p->geom[0].Vp * p->geom[0].Up, px1 = (size_t)p->geom[1].Vp * p->geom[1].Up;
+    return align_up(G * std::max(px0, px1) * rec * sizeof(float), 256);
 }
 
 size_t ctr_forward_workspace_bytes(const ctr_plan* p, int B)
@@ -341,9 +342,10 @@ static int forward_impl(const ctr_plan* p, const float* img, float* out, int B, 
     float* pk0 = p->n_cls[0] ? (float*)ws : nullptr;
     float* pk1 = p->n_cls[1] ? (float*)((char*)ws + pack_bytes(p, B)) : nullptr;
     {
-        dim3 grid((p->Y + 2 + 31) / 32, (p->X + 2 + 31) / 32, G * fc.depth), block(32, 8);
+        const int up0 = p->geom[0].Up, up1 = p->geom[1].Up;   // tiles cover the padded row lengths of both packs
+        dim3 grid((up0 + 31) / 32, (up1 + 31) / 32, G * fc.depth), block(32, 8);
         ProfScope prof(CTR_K_PACK_IMAGE, st);
-        ctr::ctr_pack_image_kernel<ctr::kFwdNB><<<grid, block, 0, st>>>(img, B, p->X, p->Y, pk0, pk1, fc.depth);
+        ctr::ctr_pack_image_kernel<ctr::kFwdNB><<<grid, block, 0, st>>>(img, B, p->X, p->Y, pk0, pk1, fc.depth, up0, up1);
         ctr::launch_counter()++;
         CTR_CUDA(cudaGetLastError());
     }
@@ -357,6 +359,7 @@ static int forward_impl(const ctr_plan* p, const float* img, float* out, int B, 
     fp.jwd = fc.JW * fc.depth;
     fp.ns = fc.NS;
     fp.stages = fc.stages;
+    fp.isync = fc.isync;
     fp.chunks0 = (p->n_cls[0] + NA - 1) / NA;
     const int chunks = fp.chunks0 + (p->n_cls[1] + NA - 1) / NA;
     fp.H = p->H; fp.W = p->W; fp.A = p->A; fp.B = B;

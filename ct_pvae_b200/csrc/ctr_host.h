@@ -76,14 +76,19 @@ inline void ctr_h_invert_transforms(const float* t, int A, float* tinv)
 
 // Packed-image geometry of the two classes (see CtrRay): class 0 strips run over
 // image rows (v = y), class 1 over image columns (v = x, transposed pack).
+// Packed rows are padded (with zeros) to a multiple of 8 pixels so that a row of 16-byte
+// chunks starts at bank group 0 whatever the record depth: samples of a quarter-warp that
+// sit in different rows then only collide when they share a column (see tools/bank_sim.py).
+inline int ctr_h_row_pixels(int n) { return (n + 2 + 7) / 8 * 8; }
+
 inline void ctr_h_class_geom(int X, int Y, int padx, int pady, CtrClassGeom g[2])
 {
     g[0].ulo = (float)(pady - 1); g[0].uhi = (float)(pady + Y);
     g[0].vlo = (float)(padx - 1); g[0].vhi = (float)(padx + X);
-    g[0].offu = pady - 1; g[0].offv = padx - 1; g[0].Up = Y + 2; g[0].Vp = X + 2;
+    g[0].offu = pady - 1; g[0].offv = padx - 1; g[0].Up = ctr_h_row_pixels(Y); g[0].Vp = X + 2;
     g[1].ulo = (float)(padx - 1); g[1].uhi = (float)(padx + X);
     g[1].vlo = (float)(pady - 1); g[1].vhi = (float)(pady + Y);
-    g[1].offu = padx - 1; g[1].offv = pady - 1; g[1].Up = X + 2; g[1].Vp = Y + 2;
+    g[1].offu = padx - 1; g[1].offv = pady - 1; g[1].Up = ctr_h_row_pixels(X); g[1].Vp = Y + 2;
 }
 
 // Class-sorted ray table: class-0 angles first (n0 of them), then class 1.

@@ -89,14 +89,15 @@ constexpr int kFwdMaxConsumers = kFwdMaxThreads - 32;  // 736 = 23 warps
 __host__ __device__ static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 // ------------------------------------------------------------------------------------------ K0 packs
-// grid (ceil((Y+2)/32), ceil((X+2)/32), G), block (32, 8).  Reads are coalesced along
+// grid (ceil(up0/32), ceil(up1/32), G*depth), block (32, 8).  Reads are coalesced along
 // image rows; both packs are written with 16-byte-per-lane coalesced stores, the
 // transposed one through a padded shared-memory tile.
 // `depth` image groups of NB share one pixel record of depth*NB floats (depth-first pack):
 // blockIdx.z = super-group * depth + sub; this block fills chunk `sub` of every record.
 template <int NB>
 __global__ void __launch_bounds__(256) ctr_pack_image_kernel(const float* __restrict__ img, int B, int X, int Y,
-                                                             float* __restrict__ pk0, float* __restrict__ pk1, int depth)
+                                                             float* __restrict__ pk0, float* __restrict__ pk1, int depth,
+                                                             int up0, int up1)   // packed row lengths (pixels) of the two packs
 {
     __shared__ float tile[NB][32][33];
     const int g = blockIdx.z;                       // image group of NB
@@ -118,8 +119,8 @@ __global__ void __launch_bounds__(256) ctr_pack_image_kernel(const float* __rest
     if (pk0) {
         for (int rr = ty; rr < 32; rr += 8) {
             const int pr = pr0 + rr, pc = pc0 + tx;
-            if (pr < X + 2 && pc < Y + 2) {
-                float* dst = pk0 + (((size_t)sg * (X + 2) + pr) * (Y + 2) + pc) * rec + sub * NB;
+            if (pr < X + 2 && pc < up0) {          // columns Y+2 .. up0-1 are zero padding
+                float* dst = pk0 + (((size_t)sg * (X + 2) + pr) * up0 + pc) * rec + sub * NB;
 #pragma unroll
                 for (int q = 0; q < NB / 4; ++q)
                     reinterpret_cast<float4*>(dst)[q] = make_float4(tile[4 * q][rr][tx], tile[4 * q + 1][rr][tx],
@@ -130,8 +131,8 @@ __global__ void __launch_bounds__(256) ctr_pack_image_kernel(const float* __rest
     if (pk1) {
         for (int cc = ty; cc < 32; cc += 8) {
             const int pc = pc0 + cc, pr = pr0 + tx;
-            if (pr < X + 2 && pc < Y + 2) {
-                float* dst = pk1 + (((size_t)sg * (Y + 2) + pc) * (X + 2) + pr) * rec + sub * NB;
+            if (pc < Y + 2 && pr < up1) {
+                float* dst = pk1 + (((size_t)sg * (Y + 2) + pc) * up1 + pr) * rec + sub * NB;
 #pragma unroll
                 for (int q = 0; q < NB / 4; ++q)
                     reinterpret_cast<float4*>(dst)[q] = make_float4(tile[4 * q][tx][cc], tile[4 * q + 1][tx][cc],
@@ -164,6 +165,39 @@ __global__ void __launch_bounds__(128) ctr_pack_sino_kernel(const float* __restr
 }
 
 // ------------------------------------------------------------------------------------------ K1 forward
+// i-synchronous march (4-image records): the 8 lanes of a quarter-warp (8 adjacent rays of one
+// angle) take the SAME step index in every trip, a lane sitting out the trips in which that step
+// is not its own.  Their samples are then spaced (cos, sin) <= 1 pixel apart along the packed row
+// instead of 1/cos > 1 as when every lane follows its own row, which removes the wrap-around
+// bank conflicts of an LDS.128 quarter (model: 1.57 -> 1.30 wavefronts per quarter-warp load).
+// Warp-collective: every lane calls it, rays without work pass s.n == 0.
+template <int NB, int INTERP, int REC>
+__device__ __forceinline__ void ctr_march_isync(const float* __restrict__ strip, int Up, float vend, int rbase, int offu,
+                                                const CtrRay& r, CtrRayState& s, float* __restrict__ acc)
+{
+    float mine = (s.n > 0) ? s.fi * s.dfi : 3.0e38f;   // marching coordinate of my next sample (+1 per step)
+    float m = mine;
+    m = fminf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+    m = fminf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+    m = fminf(m, __shfl_xor_sync(0xffffffffu, m, 4));  // the quarter-warp starts at its earliest lane
+    bool live = s.n > 0;                                // may still own samples of this strip
+    while (__any_sync(0xffffffffu, live)) {
+        if (live && mine == m) {
+            CtrSample<INTERP> a;
+            ctr_sample<INTERP>(r, s.pu, s.pv, s.fi, Up, rbase, offu, a);
+            if (a.kvf >= vend) {
+                live = false;                           // the rest of this ray belongs to later strips
+            } else {
+                ctr_gather<NB, INTERP, REC>(strip, Up, a, acc);
+                s.fi += s.dfi;
+                mine += 1.f;
+                live = --s.n > 0;
+            }
+        }
+        m += 1.f;
+    }
+}
+
 struct FwdParams {
     const float* pk[2];     // packed images per class  [G][Vp][Up][NB*DEPTH]
     CtrClassGeom geom[2];
@@ -175,6 +209,7 @@ struct FwdParams {
     int kbins;              // 1: a thread's KA rays are KA detector bins (JW apart) of ONE angle; 0: KA angles of one bin
     int jwd, ns;            // consumer threads per angle slot (JW bins x DEPTH groups) and angle slots; block = jwd*ns + 32
     int stages;             // strip buffers in the shared-memory ring (2..4)
+    int isync;              // 1: quarter-warps march step-synchronously (4-image records only)
     float* sino;            // [B][A][W]   (EPI 0: ray sums; EPI 1: d loglik / d proj, the adjoint's cotangent)
     // fused measurement log-likelihood epilogue (EPI 1), helper_functions.py:355-368
     const float* mask;      // [B][A_all]
@@ -279,8 +314,10 @@ __global__ void __launch_bounds__(kFwdMaxThreads, 1) ctr_fwd_kernel(const FwdPar
             const int rbase = k * R + geom.offv;
 #pragma unroll
             for (int q = 0; q < KA; ++q) {
-                if (rn[q] > 0) {
-                    const CtrRay r = rays_s[lbase + q * lstep];
+                const bool isync = (DEPTH == 1) && p.isync && !kb;    // warp-uniform
+                if (isync || rn[q] > 0) {
+                    const int la = min(lbase + q * lstep, NA - 1);    // (slots past cnt carry rn == 0)
+                    const CtrRay r = rays_s[la];
                     const int j = jb + q * jstep;
                     CtrRayState s;
                     s.pu = CTR_MUL(r.u0, (float)j);
@@ -288,7 +325,8 @@ __global__ void __launch_bounds__(kFwdMaxThreads, 1) ctr_fwd_kernel(const FwdPar
                     s.fi = ri[q];
                     s.n = rn[q];
                     s.dfi = (r.v1 >= 0.f) ? 1.f : -1.f;
-                    ctr_march<NB, INTERP, REC>(strip, geom.Up, vend, rbase, geom.offu, r, s, acc[q]);
+                    if (isync) ctr_march_isync<NB, INTERP, REC>(strip, geom.Up, vend, rbase, geom.offu, r, s, acc[q]);
+                    else ctr_march<NB, INTERP, REC>(strip, geom.Up, vend, rbase, geom.offu, r, s, acc[q]);
                     ri[q] = s.fi;
                     rn[q] = s.n;
                 }
@@ -548,7 +586,7 @@ __global__ void __launch_bounds__(256) ctr_fbp_filter_kernel(const float* __rest
 
 // ------------------------------------------------------------------------------------------ launchers
 struct FwdConfig {
-    int JW, NS, KA, R, jchunks, depth, kbins, stages;
+    int JW, NS, KA, R, jchunks, depth, kbins, stages, isync;
     size_t smem;
     int angles_per_cta() const { return kbins ? NS : NS * KA; }
 };
@@ -577,6 +615,7 @@ inline FwdConfig fwd_config(int W, const CtrClassGeom geom[2], int smem_budget)
     FwdConfig c{};
     c.depth = 1;
     c.kbins = fwd_use_kbins() ? 1 : 0;
+    c.isync = (getenv("CTR_FWD_NOISYNC") == nullptr && !c.kbins) ? 1 : 0;
     c.KA = 2;
     if (c.kbins) {
         // two bins per thread (tx and tx + JW) of one angle, NS angle slots per CTA

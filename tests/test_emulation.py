@@ -49,6 +49,9 @@ def test_emulated_kernels_match_oracle(emu, orc, B, X, Y, A, pad, R, TW, TH, win
         sd = np.full((B, A, W), np.nan, np.float32)       # depth-first records (16 images per record)
         emu.emu_forward_depth(P(img), B, X, Y, H, W, padx, pady, P(t), A, interp, R, P(sd))
         np.testing.assert_array_equal(sd, s)
+        si = np.full((B, A, W), np.nan, np.float32)       # i-synchronous quarter-warps: same samples, same order per ray
+        emu.emu_forward_isync(P(img), B, X, Y, H, W, padx, pady, P(t), A, interp, R, P(si))
+        np.testing.assert_array_equal(si, s)
         g = np.full((B, X, Y), np.nan, np.float32)
         emu.emu_adjoint(P(y), B, X, Y, H, W, padx, pady, P(t), A, interp, 0, TW, TH, win, P(g))
         assert rel_l2(g, orc.adjoint_exact(y, th, X, Y, pad, interp)) <= 1e-6
@@ -93,6 +96,9 @@ def test_emulated_kernels_property(emu, orc, B, X, Y, pad, R, th, seed):
         sd = np.full((B, A, W), np.nan, np.float32)
         emu.emu_forward_depth(P(img), B, X, Y, H, W, padx, pady, P(t), A, interp, R, P(sd))
         np.testing.assert_array_equal(sd, s)
+        si = np.full((B, A, W), np.nan, np.float32)
+        emu.emu_forward_isync(P(img), B, X, Y, H, W, padx, pady, P(t), A, interp, R, P(si))
+        np.testing.assert_array_equal(si, s)
         for mode, table, fn in ((0, t, orc.adjoint_exact), (1, ti, orc.adjoint_tf)):
             g = np.full((B, X, Y), np.nan, np.float32)
             emu.emu_adjoint(P(y), B, X, Y, H, W, padx, pady, P(table), A, interp, mode, 32, 8, 40, P(g))

@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(128) ctr_pack_sino_kernel(const float* __restr
 }
 
 // ------------------------------------------------------------------------------------------ K1 forward
-// i-synchronous march (4-image records): the 8 lanes of a quarter-warp (8 adjacent rays of one
+// EXPERIMENT (opt-in, CTR_FWD_ISYNC): i-synchronous march (4-image records): the 8 lanes of a quarter-warp (8 adjacent rays of one
 // angle) take the SAME step index in every trip, a lane sitting out the trips in which that step
 // is not its own.  Their samples are then spaced (cos, sin) <= 1 pixel apart along the packed row
 // instead of 1/cos > 1 as when every lane follows its own row, which removes the wrap-around
@@ -615,7 +615,9 @@ inline FwdConfig fwd_config(int W, const CtrClassGeom geom[2], int smem_budget)
     FwdConfig c{};
     c.depth = 1;
     c.kbins = fwd_use_kbins() ? 1 : 0;
-    c.isync = (getenv("CTR_FWD_NOISYNC") == nullptr && !c.kbins) ? 1 : 0;
+    // r1 measurement: the i-synchronous march loses (C4 slice 3.95 vs 2.50 ms, nearest 3.81 vs 1.49):
+    // the sit-out trips and the vote per trip cost more issue slots than the conflicts they remove.
+    c.isync = (getenv("CTR_FWD_ISYNC") != nullptr && !c.kbins) ? 1 : 0;
     c.KA = 2;
     if (c.kbins) {
         // two bins per thread (tx and tx + JW) of one angle, NS angle slots per CTA

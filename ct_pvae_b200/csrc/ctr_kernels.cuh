@@ -417,7 +417,7 @@ struct BpParams {
 // bins a 32 x TH pixel tile can touch for one angle: |u| extent sqrt(31^2+(TH-1)^2) + 6 bins of slack
 __host__ __device__ constexpr int bp_win(int TH) { return TH <= 8 ? 40 : 44; }
 // angles staged per batch: 4 for the small 32x4 tiles (4 CTAs per SM must fit in shared memory)
-__host__ __device__ constexpr int bp_ab(int TH) { return TH <= 4 ? 4 : kBpAB; }
+__host__ __device__ constexpr int bp_ab(int TH, int NB = 16, int MINB = 2) { return (TH <= 4 || (NB >= 32 && MINB >= 3)) ? 4 : kBpAB; }
 
 // One CTA = 32 x TH pixel tile x image group of NB.  Angles are processed in batches
 // of AB: lanes 0..AB-1 of warp 0 each own one angle of the batch -- they compute the
@@ -428,7 +428,7 @@ __host__ __device__ constexpr int bp_ab(int TH) { return TH <= 4 ? 4 : kBpAB; }
 template <int NB, int TH, int MINB, int MODE, int INTERP>
 __global__ void __launch_bounds__(kBpTW * TH, MINB) ctr_bp_kernel(const BpParams p)
 {
-    constexpr int TW = kBpTW, AB = bp_ab(TH), NBP = NB / 4;
+    constexpr int TW = kBpTW, AB = bp_ab(TH, NB, MINB), NBP = NB / 4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);            // [2]
     int* jb = reinterpret_cast<int*>(smem_raw + 16);                   // [2][AB]
@@ -767,7 +767,7 @@ inline cudaError_t launch_bp_cfg(BpParams p, cudaStream_t st)
     const int G = (p.B + NB - 1) / NB;
     dim3 grid((p.Y + kBpTW - 1) / kBpTW, (p.X + TH - 1) / TH, G), block(kBpTW, TH);
     if (p.win > bp_win(TH)) p.win = bp_win(TH);
-    const size_t smem = bp_smem_bytes(p.win, NB, bp_ab(TH));
+    const size_t smem = bp_smem_bytes(p.win, NB, bp_ab(TH, NB, MINB));
     cudaError_t e = cudaFuncSetAttribute(ctr_bp_kernel<NB, TH, MINB, MODE, INTERP>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -783,6 +783,8 @@ inline cudaError_t launch_bp(const BpParams& p, cudaStream_t st)
     if (nb == 32) {
         static const bool small_tiles = getenv("CTR_BP_TH4") != nullptr;   // developer switch
         if (small_tiles) return launch_bp_cfg<32, 4, 4, MODE, INTERP>(p, st);
+        static const bool occ3 = getenv("CTR_BP_OCC3") != nullptr;          // developer switch: 3 CTAs/SM (85 regs)
+        if (occ3) return launch_bp_cfg<32, 8, 3, MODE, INTERP>(p, st);
         return launch_bp_cfg<32, 8, 2, MODE, INTERP>(p, st);
     }
     if (nb == 16) return launch_bp_cfg<16, 8, 3, MODE, INTERP>(p, st);

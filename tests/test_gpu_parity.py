@@ -281,6 +281,20 @@ def test_fused_loglik_matches_oracle(cp, orc, interp, gather):
     assert (np.abs(full[..., 0].double().sum(dim=(1, 2)).cpu().numpy() - want) <= budget).all()
 
 
+def test_dataset_helpers_on_the_projector(cp, orc, tmp_path):
+    """scripts/images_to_sinograms.py on the B200 projector + the on-disk format round trip."""
+    from ct_pvae_b200 import datasets
+
+    rng = np.random.default_rng(11)
+    imgs = rng.random((6, 20, 20), dtype=np.float32)
+    th = _theta(9)
+    s = datasets.images_to_sinograms(imgs, th, pad=True, save_path=str(tmp_path))
+    assert rel_l2(s, orc.forward(imgs, th, True, 1)) <= TOL
+    got, th2, P = datasets.get_sinograms(str(tmp_path))
+    assert P == s.shape[2] and np.array_equal(th2, th) and np.array_equal(got, np.where(s < 0, 0, s))
+    assert datasets.reconstruction_size(cp.num_proj_pix(128, 128)) == (128, 128)
+
+
 def test_golden_fixtures(cp):
     import os
 

@@ -86,3 +86,22 @@ def test_shard_range_partitions_exactly():
             assert all(b[1] == c[0] for b, c in zip(blocks, blocks[1:]))
             sizes = [hi - lo for lo, hi in blocks]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_tf_bridge_is_import_guarded():
+    from ct_pvae_b200 import tf_bridge
+
+    if tf_bridge.available():
+        pytest.skip("TensorFlow present")
+    with pytest.raises(RuntimeError, match="TensorFlow is not installed"):
+        tf_bridge.project_tf_fast(np.zeros((2, 4, 4, 1), np.float32), np.zeros(3), integrate_vae=True)
+
+
+def test_host_pipeline_eligibility():
+    from ct_pvae_b200 import hostpipe
+
+    x = torch.zeros(40, 8, 8)
+    assert not hostpipe.eligible(x)                       # pageable memory: plain path
+    assert not hostpipe.eligible(torch.zeros(40, 8, 8, dtype=torch.float64))
+    assert not hostpipe.eligible(torch.zeros(4, 8, 8))    # small batches are not worth chunking
+    assert not hostpipe.eligible(torch.zeros(40, 8, 8, requires_grad=True))

@@ -682,7 +682,14 @@ inline FwdConfig fwd_config_depth(int W, const CtrClassGeom geom[2], int smem_bu
         if (c.JW * c.depth * c.NS > kFwdMaxConsumers) return c;   // R = 0: not available for this detector width
     } else {
         c.JW = round_up(W, 32 / c.depth);
-        if (c.JW * c.depth > kFwdMaxConsumers) return c;
+        if (c.JW * c.depth > kFwdMaxConsumers) {
+            // experiment (CTR_FWD_WIDE_DEPTH): 8-image records on a wide detector, split in chunks of 368
+            // bins that each stream the full-width strips, four angles per thread to pay for the re-reads
+            if (c.depth != 2 || getenv("CTR_FWD_WIDE_DEPTH") == nullptr) return c;
+            c.JW = kFwdMaxConsumers / 2;
+            c.jchunks = (W + c.JW - 1) / c.JW;
+            c.KA = 4;
+        }
     }
     const int fixed = 128 + round_up(c.NS * c.KA * (int)sizeof(CtrRay), 128);
     const int Upmax = geom[0].Up > geom[1].Up ? geom[0].Up : geom[1].Up;
@@ -708,6 +715,13 @@ inline cudaError_t launch_fwd_ka(const FwdParams& p, const FwdConfig& c, int G, 
         e = cudaFuncSetAttribute(ctr_fwd_kernel<kFwdNB, 2, INTERP, EPI, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
         if (e != cudaSuccess) return e;
         ctr_fwd_kernel<kFwdNB, 2, INTERP, EPI, 4><<<grid, block, c.smem, st>>>(p);
+        launch_counter()++;
+        return cudaGetLastError();
+    }
+    if (c.depth == 2 && c.KA == 4) {
+        e = cudaFuncSetAttribute(ctr_fwd_kernel<kFwdNB, 4, INTERP, EPI, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+        if (e != cudaSuccess) return e;
+        ctr_fwd_kernel<kFwdNB, 4, INTERP, EPI, 2><<<grid, block, c.smem, st>>>(p);
         launch_counter()++;
         return cudaGetLastError();
     }

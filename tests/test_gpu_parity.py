@@ -295,6 +295,27 @@ def test_dataset_helpers_on_the_projector(cp, orc, tmp_path):
     assert datasets.reconstruction_size(cp.num_proj_pix(128, 128)) == (128, 128)
 
 
+def test_toy_mcmc_likelihood_differentiates_through_the_projector(cp, orc):
+    """Third caller (ctvae/toy_mcmc_v2_functions.py:30-64): a 2x2 image, pad=False, dim=2, Poisson
+    likelihood of the masked projection, differentiated by HMC -- here by autograd, checked against
+    the analytic gradient A^T (d ll / d proj) built from the oracle's matrix."""
+    theta = np.array([0, np.pi / 2])
+    mask = np.array([1.0, 0.0], np.float32)
+    pnm = 1e3
+    O = torch.tensor([[0.1, 0.2], [0.3, 0.4]], device="cuda", requires_grad=True)
+    M = torch.tensor([[0.41, 0.59], [0.0, 0.0]], device="cuda")
+    proj = cp.project_tf_fast(O, theta, pad=False, dim=2, integrate_vae=False)[..., 0]       # [A, P]
+    rate = proj * torch.from_numpy(mask).cuda()[:, None] * pnm
+    ll = torch.distributions.Poisson(rate[0]).log_prob(M[0] * pnm).sum()                      # only the unmasked angle
+    ll.backward()
+    A = orc.build_matrix(theta, 2, 2, False, 0).toarray()                                      # [(A*P) x 4]
+    p = A @ O.detach().cpu().numpy().reshape(-1)
+    dll_dproj = np.zeros(4)
+    dll_dproj[:2] = (M[0].cpu().numpy() * pnm / (p[:2] * pnm) - 1.0) * pnm
+    want = (A.T @ dll_dproj).reshape(2, 2)
+    np.testing.assert_allclose(O.grad.cpu().numpy(), want, rtol=1e-4)
+
+
 def test_golden_fixtures(cp):
     import os
 

@@ -55,6 +55,12 @@ SYMBOLS = {
     "ctr_fbp_plan_destroy": (_c_int, [_c_void_p]),
     "ctr_fbp_workspace_bytes": (_c_size_t, [_c_void_p, _c_int]),
     "ctr_fbp": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_size_t, _c_void_p]),
+    "ctr_hostpipe_create": (_c_int, [_c_void_p, _c_int, ctypes.POINTER(_c_void_p)]),
+    "ctr_hostpipe_destroy": (_c_int, [_c_void_p]),
+    "ctr_hostpipe_forward": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int]),
+    "ctr_hostpipe_adjoint": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int]),
+    "ctr_hostpipe_wait": (_c_int, [_c_void_p]),
+    "ctr_hostpipe_done": (_c_int, [_c_void_p]),
     "ctr_radon_forward_dl": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_void_p]),
     "ctr_radon_adjoint_dl": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p]),
     "ctr_fbp_dl": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
@@ -233,8 +239,7 @@ class _PlanCache:
         with self.lock:
             self.items[key] = plan
             while len(self.items) > self.capacity:
-                _, old = self.items.popitem(last=False)
-                old.close()
+                self.items.popitem(last=False)   # freed by Plan.__del__ once no call or host pipe still holds it
         return plan
 
     def clear(self):
@@ -262,5 +267,7 @@ def get_fbp_plan(theta64, P: int, x_size: int, y_size: int, filter_1d, device: i
 
 
 def clear_plan_caches() -> None:
+    from . import hostpipe
+    hostpipe.clear_pipes()     # pipes borrow their plan: destroy them first
     _plans.clear()
     _fbp_plans.clear()

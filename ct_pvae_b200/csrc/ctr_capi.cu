@@ -555,6 +555,173 @@ int ctr_fbp(const ctr_fbp_plan* p, const float* sino, int A, float* recon, int B
     return CTR_OK;
 }
 
+// ------------------------------------------------------------------------------------------ host pipeline
+// Host-buffer entry points: the batch is cut into chunks that flow through a ring of device
+// staging slots on three streams (copy-in / kernels / copy-out), so PCIe runs in both
+// directions while the kernels of another chunk execute.  Successive calls on the same pipe
+// append to the same ring: the copy-out of one call overlaps the copy-in of the next.
+struct ctr_hostpipe {
+    static constexpr int kSlots = 6;   // r1 trace: with 3 the next call's copy-in stalls on slots still queued for kernels
+    const ctr_plan* plan = nullptr;
+    int device = 0, chunk = 0;
+    size_t buf_bytes = 0, ws_bytes = 0;
+    cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
+    struct Slot {
+        float* d_in = nullptr; float* d_out = nullptr; void* ws = nullptr;
+        cudaEvent_t in_done = nullptr, comp_done = nullptr, out_done = nullptr;
+    } slot[kSlots];
+    long long seq = 0;     // chunks issued so far
+    std::mutex mu;
+    // developer trace (CTR_HOSTPIPE_TRACE): timestamps of every chunk's stages, printed by ctr_hostpipe_wait
+    struct Trace { int kind, n; cudaEvent_t in0, in1, c0, c1, o0, o1; };
+    std::vector<Trace> trace;
+    cudaEvent_t t0 = nullptr;
+};
+
+static void hostpipe_free(ctr_hostpipe* hp)
+{
+    for (auto& s : hp->slot) {
+        cudaFree(s.d_in); cudaFree(s.d_out); cudaFree(s.ws);
+        if (s.in_done) cudaEventDestroy(s.in_done);
+        if (s.comp_done) cudaEventDestroy(s.comp_done);
+        if (s.out_done) cudaEventDestroy(s.out_done);
+    }
+    if (hp->s_in) cudaStreamDestroy(hp->s_in);
+    if (hp->s_comp) cudaStreamDestroy(hp->s_comp);
+    if (hp->s_out) cudaStreamDestroy(hp->s_out);
+    delete hp;
+}
+
+int ctr_hostpipe_create(const ctr_plan* plan, int chunk, ctr_hostpipe** out)
+{
+    if (!out) return fail(CTR_EINVAL, "ctr_hostpipe_create: out is NULL");
+    *out = nullptr;
+    if (!plan || chunk <= 0) return fail(CTR_EINVAL, "ctr_hostpipe_create: need a plan and chunk > 0");
+    DeviceGuard guard(plan->device);
+    if (!guard.ok) return fail_cuda(guard.err, "cudaSetDevice");
+    ctr_hostpipe* hp = new (std::nothrow) ctr_hostpipe();
+    if (!hp) return fail(CTR_EINVAL, "ctr_hostpipe_create: out of host memory");
+    hp->plan = plan; hp->device = plan->device; hp->chunk = chunk;
+    const size_t img_b = (size_t)chunk * plan->X * plan->Y * sizeof(float), sino_b = (size_t)chunk * plan->A * plan->W * sizeof(float);
+    hp->buf_bytes = align_up(std::max(img_b, sino_b), 256);
+    hp->ws_bytes = std::max(ctr_forward_workspace_bytes(plan, chunk), ctr_adjoint_workspace_bytes(plan, chunk));
+    cudaError_t e = cudaSuccess;
+    auto ok = [&](cudaError_t r) { if (e == cudaSuccess) e = r; return e == cudaSuccess; };
+    ok(cudaStreamCreateWithFlags(&hp->s_in, cudaStreamNonBlocking));
+    ok(cudaStreamCreateWithFlags(&hp->s_comp, cudaStreamNonBlocking));
+    ok(cudaStreamCreateWithFlags(&hp->s_out, cudaStreamNonBlocking));
+    for (auto& s : hp->slot) {
+        ok(cudaMalloc((void**)&s.d_in, hp->buf_bytes));
+        ok(cudaMalloc((void**)&s.d_out, hp->buf_bytes));
+        ok(cudaMalloc(&s.ws, hp->ws_bytes));
+        ok(cudaEventCreateWithFlags(&s.in_done, cudaEventDisableTiming));
+        ok(cudaEventCreateWithFlags(&s.comp_done, cudaEventDisableTiming));
+        ok(cudaEventCreateWithFlags(&s.out_done, cudaEventDisableTiming));
+    }
+    if (e != cudaSuccess) { hostpipe_free(hp); return fail_cuda(e, "ctr_hostpipe_create"); }
+    *out = hp;
+    return CTR_OK;
+}
+
+int ctr_hostpipe_destroy(ctr_hostpipe* hp)
+{
+    if (!hp) return CTR_OK;
+    DeviceGuard guard(hp->device);
+    cudaStreamSynchronize(hp->s_in); cudaStreamSynchronize(hp->s_comp); cudaStreamSynchronize(hp->s_out);
+    hostpipe_free(hp);
+    return CTR_OK;
+}
+
+// kind 0: forward (in = images [B,X,Y], out = sinograms [B,A,W]); kind 1: adjoint (the mirror)
+static int hostpipe_run(ctr_hostpipe* hp, int kind, const float* in_host, float* out_host, int B, int interp, int mode,
+                        const char* who)
+{
+    if (!hp || !in_host || !out_host) return fail(CTR_EINVAL, std::string(who) + ": NULL pipe or buffer");
+    if (B <= 0) return fail(CTR_EINVAL, std::string(who) + ": B must be positive");
+    const ctr_plan* p = hp->plan;
+    DeviceGuard guard(hp->device);
+    if (!guard.ok) return fail_cuda(guard.err, "cudaSetDevice");
+    std::lock_guard<std::mutex> lk(hp->mu);
+    const size_t img_n = (size_t)p->X * p->Y, sino_n = (size_t)p->A * p->W;
+    const size_t in_n = kind == 0 ? img_n : sino_n, out_n = kind == 0 ? sino_n : img_n;
+    for (int lo = 0; lo < B; lo += hp->chunk) {
+        const int n = std::min(hp->chunk, B - lo);
+        ctr_hostpipe::Slot& s = hp->slot[hp->seq % ctr_hostpipe::kSlots];
+        const bool reused = hp->seq >= ctr_hostpipe::kSlots;
+        if (reused) CTR_CUDA(cudaStreamWaitEvent(hp->s_in, s.comp_done, 0));     // staging input consumed
+        static const bool tracing = getenv("CTR_HOSTPIPE_TRACE") != nullptr;
+        ctr_hostpipe::Trace tr{kind, n, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        if (tracing) {
+            for (cudaEvent_t* ev : {&tr.in0, &tr.in1, &tr.c0, &tr.c1, &tr.o0, &tr.o1}) cudaEventCreate(ev);
+            if (!hp->t0) { cudaEventCreate(&hp->t0); cudaEventRecord(hp->t0, hp->s_in); }
+            cudaEventRecord(tr.in0, hp->s_in);
+        }
+        CTR_CUDA(cudaMemcpyAsync(s.d_in, in_host + (size_t)lo * in_n, (size_t)n * in_n * sizeof(float), cudaMemcpyHostToDevice, hp->s_in));
+        CTR_CUDA(cudaEventRecord(s.in_done, hp->s_in));
+        if (tracing) cudaEventRecord(tr.in1, hp->s_in);
+        CTR_CUDA(cudaStreamWaitEvent(hp->s_comp, s.in_done, 0));
+        if (reused) CTR_CUDA(cudaStreamWaitEvent(hp->s_comp, s.out_done, 0));    // staging output copied out
+        if (tracing) cudaEventRecord(tr.c0, hp->s_comp);
+        const int rc = kind == 0 ? ctr_radon_forward(p, s.d_in, s.d_out, n, interp, s.ws, hp->ws_bytes, hp->s_comp)
+                                 : ctr_radon_adjoint(p, s.d_in, s.d_out, n, interp, mode, s.ws, hp->ws_bytes, hp->s_comp);
+        if (rc != CTR_OK) return rc;
+        CTR_CUDA(cudaEventRecord(s.comp_done, hp->s_comp));
+        if (tracing) cudaEventRecord(tr.c1, hp->s_comp);
+        CTR_CUDA(cudaStreamWaitEvent(hp->s_out, s.comp_done, 0));
+        if (tracing) cudaEventRecord(tr.o0, hp->s_out);
+        CTR_CUDA(cudaMemcpyAsync(out_host + (size_t)lo * out_n, s.d_out, (size_t)n * out_n * sizeof(float), cudaMemcpyDeviceToHost, hp->s_out));
+        CTR_CUDA(cudaEventRecord(s.out_done, hp->s_out));
+        if (tracing) { cudaEventRecord(tr.o1, hp->s_out); hp->trace.push_back(tr); }
+        ++hp->seq;
+    }
+    return CTR_OK;
+}
+
+int ctr_hostpipe_forward(ctr_hostpipe* hp, const float* img_host, float* sino_host, int B, int interp)
+{
+    if (interp != CTR_INTERP_NEAREST && interp != CTR_INTERP_BILINEAR) return fail(CTR_EINVAL, "ctr_hostpipe_forward: bad interp");
+    return hostpipe_run(hp, 0, img_host, sino_host, B, interp, 0, "ctr_hostpipe_forward");
+}
+
+int ctr_hostpipe_adjoint(ctr_hostpipe* hp, const float* dsino_host, float* dimg_host, int B, int interp, int mode)
+{
+    if (interp != CTR_INTERP_NEAREST && interp != CTR_INTERP_BILINEAR) return fail(CTR_EINVAL, "ctr_hostpipe_adjoint: bad interp");
+    if (mode != CTR_ADJOINT_EXACT && mode != CTR_ADJOINT_TF_COMPAT) return fail(CTR_EINVAL, "ctr_hostpipe_adjoint: bad mode");
+    return hostpipe_run(hp, 1, dsino_host, dimg_host, B, interp, mode, "ctr_hostpipe_adjoint");
+}
+
+int ctr_hostpipe_wait(ctr_hostpipe* hp)
+{
+    if (!hp) return fail(CTR_EINVAL, "ctr_hostpipe_wait: pipe is NULL");
+    DeviceGuard guard(hp->device);
+    if (!guard.ok) return fail_cuda(guard.err, "cudaSetDevice");
+    CTR_CUDA(cudaStreamSynchronize(hp->s_out));   // every result of every call issued so far is in host memory
+    if (!hp->trace.empty()) {
+        std::lock_guard<std::mutex> lk(hp->mu);
+        for (auto& t : hp->trace) {
+            float v[6];
+            cudaEvent_t evs[6] = {t.in0, t.in1, t.c0, t.c1, t.o0, t.o1};
+            for (int q = 0; q < 6; ++q) { cudaEventElapsedTime(&v[q], hp->t0, evs[q]); cudaEventDestroy(evs[q]); }
+            fprintf(stderr, "[hostpipe] %s n=%d  in %.3f-%.3f  kernels %.3f-%.3f  out %.3f-%.3f ms\n", t.kind ? "adj" : "fwd", t.n,
+                    v[0], v[1], v[2], v[3], v[4], v[5]);
+        }
+        hp->trace.clear();
+        cudaEventDestroy(hp->t0);
+        hp->t0 = nullptr;
+    }
+    return CTR_OK;
+}
+
+int ctr_hostpipe_done(ctr_hostpipe* hp)
+{
+    if (!hp) return fail(CTR_EINVAL, "ctr_hostpipe_done: pipe is NULL");
+    DeviceGuard guard(hp->device);
+    const cudaError_t e = cudaStreamQuery(hp->s_out);
+    if (e == cudaSuccess) return 1;
+    if (e == cudaErrorNotReady) return 0;
+    return fail_cuda(e, "cudaStreamQuery");
+}
+
 // ------------------------------------------------------------------------------------------ DLPack
 static int dl_check(const DLTensor* t, const char* name, int min_ndim, int max_ndim, int device)
 {

@@ -89,7 +89,7 @@ def pad_phantom(phantom, dim=3, integrate_vae=False):
     return out.numpy() if was_numpy else out
 
 
-def _project_bxy(img_bxy: torch.Tensor, theta, pad: bool, interpolation: str, adjoint: str) -> torch.Tensor:
+def _project_bxy(img_bxy: torch.Tensor, theta, pad: bool, interpolation: str, adjoint: str, async_op: bool = False):
     """[B,X,Y] (any float dtype, any device) -> [B,A,W] float32 on the compute device."""
     if interpolation not in ops.INTERP:
         raise ValueError(f"interpolation must be 'nearest' or 'bilinear', got {interpolation!r}")
@@ -101,14 +101,15 @@ def _project_bxy(img_bxy: torch.Tensor, theta, pad: bool, interpolation: str, ad
     if hostpipe.eligible(img_bxy):
         # host (pinned) batch: overlap copy-in / kernels / copy-out chunk by chunk; result stays on the host
         iid = ops.INTERP[interpolation]
-        return hostpipe.run_chunked(lambda x: ops.radon_forward(x, plan, iid), img_bxy,
-                                    (img_bxy.shape[0], plan.A, plan.W), dev)
+        return hostpipe.forward_host(plan, img_bxy, iid, async_op=async_op)
+    if async_op:
+        raise ValueError("async_op=True needs a pinned, contiguous float32 host batch of >= 32 images")
     x = img_bxy.to(device=dev, dtype=torch.float32, non_blocking=True)
     return ops.project(x, plan, ops.INTERP[interpolation], ops.ADJOINT[adjoint])
 
 
 def project_tf_fast(phantom, theta, pad=False, dim=3, integrate_vae=False, *, interpolation="nearest",
-                    adjoint="exact"):
+                    adjoint="exact", async_op=False):
     """Parallel-beam Radon transform of every image / channel (reference :80-123).
 
     phantom is ``[X,Y,Z]`` (dim=3), ``[X,Y]`` (dim=2) or, with integrate_vae,
@@ -122,9 +123,15 @@ def project_tf_fast(phantom, theta, pad=False, dim=3, integrate_vae=False, *, in
     if integrate_vae:
         if t.dim() != 4 or t.shape[3] != 1:
             raise ValueError("integrate_vae expects [batch, x, y, 1]")
+        if async_op:
+            # pinned host batch: returns (result, handle); the result may be read after handle.wait()
+            sino, handle = _project_bxy(t[..., 0], theta, pad, interpolation, adjoint, async_op=True)
+            return sino.unsqueeze(-1), handle
         sino = _project_bxy(t[..., 0], theta, pad, interpolation, adjoint)      # [B,A,W]
         out = sino.unsqueeze(-1)
     else:
+        if async_op:
+            raise ValueError("async_op=True is only available with integrate_vae=True (batched host input)")
         if dim == 2:
             if t.dim() != 2:
                 raise ValueError("dim=2 expects [x, y]")
@@ -150,7 +157,8 @@ def project_tf_low_mem(phantom, theta, pad=False, *, interpolation="bilinear", a
     return _finish(sino.permute(1, 2, 0), t, was_numpy)
 
 
-def backproject(sinogram, theta, x_size, y_size, pad=False, *, interpolation="nearest", adjoint="exact"):
+def backproject(sinogram, theta, x_size, y_size, pad=False, *, interpolation="nearest", adjoint="exact",
+                async_op=False):
     """Adjoint of ``project_tf_fast(..., integrate_vae=True)`` as a function:
     ``[B,A,P,1]`` (or ``[B,A,P]``) -> ``[B,x_size,y_size,1]`` (or ``[B,x_size,y_size]``).
     This is what autograd calls; exposed for matched iterative solvers and tests."""
@@ -162,9 +170,13 @@ def backproject(sinogram, theta, x_size, y_size, pad=False, *, interpolation="ne
     plan = _lib.get_plan(th, int(x_size), int(y_size), bool(pad), dev.index or 0)
     if hostpipe.eligible(s3):
         iid, mid = ops.INTERP[interpolation], ops.ADJOINT[adjoint]
-        g = hostpipe.run_chunked(lambda y: ops.radon_adjoint(y, plan, iid, mid), s3,
-                                 (s3.shape[0], int(x_size), int(y_size)), dev)
+        if async_op:
+            g, handle = hostpipe.adjoint_host(plan, s3, iid, mid, async_op=True)
+            return (g.unsqueeze(-1) if squeeze else g), handle
+        g = hostpipe.adjoint_host(plan, s3, iid, mid)
         return _finish(g.unsqueeze(-1) if squeeze else g, t, was_numpy)
+    if async_op:
+        raise ValueError("async_op=True needs a pinned, contiguous float32 host batch of >= 32 sinograms")
     y = s3.to(device=dev, dtype=torch.float32)
     g = ops.radon_adjoint(y, plan, ops.INTERP[interpolation], ops.ADJOINT[adjoint])
     return _finish(g.unsqueeze(-1) if squeeze else g, t, was_numpy)

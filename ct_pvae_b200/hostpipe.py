@@ -1,25 +1,24 @@
-"""Chunked host<->device pipeline for calls made with HOST (pinned) buffers.
+"""Host-buffer calls: pinned NumPy / CPU-tensor batches through libctradon's native chunked pipeline.
 
-A drop-in call from a CPU-side caller moves every image to the GPU and every result
-back.  Run back to back those copies cost several times the kernels, so batches are
-cut into chunks and three streams overlap: copy-in of chunk k+1, kernels of chunk k,
-copy-out of chunk k-1 (PCIe is full duplex).  torch provides the streams, events and
-pinned allocations; the arithmetic is still only libctradon's kernels.
+A drop-in call from a CPU-side caller (``main_ct_vae.py:523-524``, ``scripts/images_to_sinograms.py:61-68`` in the
+reference) moves every image to the GPU and every result back.  Run back to back those copies cost several times the
+kernels, so ``ctr_hostpipe_*`` (include/ctradon.h) cuts the batch into chunks that flow through a ring of device
+staging slots on three streams: copy-in of chunk k+1, kernels of chunk k, copy-out of chunk k-1 (PCIe is full duplex).
+The whole pipeline is enqueued by ONE C call; torch only provides the pinned result tensor.
+
+``async_op=True`` returns ``(result, handle)`` like a torch.distributed work handle: several calls issued back to back
+share the ring, so the copy-out of one overlaps the copy-in of the next; ``handle.wait()`` makes the result readable.
 """
 from __future__ import annotations
 
-from typing import Callable, Tuple
+import collections
+import ctypes
+import os
+import threading
 
 import torch
 
-_streams = {}
-
-
-def _side_streams(dev: torch.device):
-    key = (dev.index or 0)
-    if key not in _streams:
-        _streams[key] = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
-    return _streams[key]
+from . import _lib
 
 
 def eligible(x: torch.Tensor, min_batch: int = 32) -> bool:
@@ -27,29 +26,114 @@ def eligible(x: torch.Tensor, min_batch: int = 32) -> bool:
             and x.is_pinned() and x.is_contiguous() and not x.requires_grad)
 
 
-def run_chunked(fn: Callable[[torch.Tensor], torch.Tensor], x_host: torch.Tensor, out_shape: Tuple[int, ...],
-                dev: torch.device, nchunks: int = 4, align: int = 16) -> torch.Tensor:
-    """y[b] = fn(x[b]) chunk by chunk over dim 0; x_host pinned float32, result pinned float32."""
-    B = x_host.shape[0]
-    per = max(align, ((B + nchunks - 1) // nchunks + align - 1) // align * align)
-    s_in, s_out = _side_streams(dev)
-    cur = torch.cuda.current_stream(dev)
+class NativePipe:
+    """ctr_hostpipe: device staging ring + streams for one plan and chunk size."""
+
+    def __init__(self, plan: "_lib.Plan", chunk: int):
+        self.plan, self.chunk = plan, int(chunk)      # the plan must outlive the pipe
+        self.handle = ctypes.c_void_p()
+        _lib.check(_lib.lib().ctr_hostpipe_create(plan.handle, self.chunk, ctypes.byref(self.handle)))
+
+    def forward(self, x_host: torch.Tensor, out_host: torch.Tensor, interp: int) -> None:
+        _lib.check(_lib.lib().ctr_hostpipe_forward(self.handle, x_host.data_ptr(), out_host.data_ptr(), int(x_host.shape[0]), interp))
+
+    def adjoint(self, y_host: torch.Tensor, out_host: torch.Tensor, interp: int, mode: int) -> None:
+        _lib.check(_lib.lib().ctr_hostpipe_adjoint(self.handle, y_host.data_ptr(), out_host.data_ptr(), int(y_host.shape[0]), interp, mode))
+
+    def wait(self) -> None:
+        _lib.check(_lib.lib().ctr_hostpipe_wait(self.handle))
+
+    def done(self) -> bool:
+        rc = _lib.lib().ctr_hostpipe_done(self.handle)
+        if rc < 0:
+            _lib.check(rc)
+        return rc == 1
+
+    def close(self) -> None:
+        if self.handle:
+            _lib.lib().ctr_hostpipe_destroy(self.handle)
+            self.handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class HostResult:
+    """Completion handle of an ``async_op=True`` host-buffer call: the pinned result may be read after ``wait()``."""
+
+    def __init__(self, pipe: NativePipe, keep):
+        self._pipe, self._keep = pipe, keep          # keeps the host buffers alive while copies are in flight
+
+    def wait(self) -> None:
+        if self._pipe is not None:
+            self._pipe.wait()
+            self._pipe = self._keep = None
+
+    def is_completed(self) -> bool:
+        return self._pipe is None or self._pipe.done()
+
+
+_pipes: "collections.OrderedDict" = collections.OrderedDict()
+_pipes_lock = threading.Lock()
+_MAX_PIPES = 4
+
+
+def chunk_for(plan, B: int, kind: str) -> int:
+    """Images per chunk: four chunks per call, but never so little work that a chunk's launches leave most of the
+    148 SMs idle (r1 measurement at 256 x 128^2 x 180: 1.39 ms per step with 64-image chunks, 2.0 ms with 32);
+    whole 16-image pixel records."""
+    env = os.environ.get("CTR_HOST_CHUNK_" + kind.upper()) or os.environ.get("CTR_HOST_CHUNK")
+    if env:
+        return max(1, int(env))
+    work = plan.A * plan.X * plan.Y                      # pixel-angle updates per image
+    by_work = -(-180_000_000 // work)                    # 64 images at 128^2 x 180, 1 at 512^2 x 720
+    per = max(by_work, (B + 3) // 4)
+    return min(max(16, (per + 15) // 16 * 16), (B + 15) // 16 * 16)
+
+
+def get_pipe(plan: "_lib.Plan", chunk: int, kind: str) -> NativePipe:
+    # forward and adjoint calls get separate pipes (own streams and staging): their kernels may then run
+    # concurrently, the partial last wave of one filling SMs the other leaves idle
+    key = (id(plan), chunk, kind if os.environ.get("CTR_HOST_SPLIT_PIPES") else "")
+    with _pipes_lock:
+        pipe = _pipes.get(key)
+        if pipe is not None and pipe.plan is plan:
+            _pipes.move_to_end(key)
+            return pipe
+        pipe = NativePipe(plan, chunk)
+        _pipes[key] = pipe
+        while len(_pipes) > _MAX_PIPES:
+            _, old = _pipes.popitem(last=False)
+            old.wait()
+            old.close()
+        return pipe
+
+
+def clear_pipes() -> None:
+    with _pipes_lock:
+        for pipe in _pipes.values():
+            pipe.close()
+        _pipes.clear()
+
+
+def _run(plan, x_host: torch.Tensor, out_shape, async_op: bool, issue, kind: str):
+    pipe = get_pipe(plan, chunk_for(plan, int(x_host.shape[0]), kind), kind)
     out = torch.empty(out_shape, dtype=torch.float32, pin_memory=True)
-    s_in.wait_stream(cur)
-    for lo in range(0, B, per):
-        hi = min(B, lo + per)
-        with torch.cuda.stream(s_in):
-            xd = x_host[lo:hi].to(dev, non_blocking=True)
-            e_in = torch.cuda.Event()
-            e_in.record(s_in)
-        cur.wait_event(e_in)
-        xd.record_stream(cur)
-        yd = fn(xd)
-        e_c = torch.cuda.Event()
-        e_c.record(cur)
-        s_out.wait_event(e_c)
-        with torch.cuda.stream(s_out):
-            out[lo:hi].copy_(yd, non_blocking=True)
-        yd.record_stream(s_out)
-    s_out.synchronize()
+    issue(pipe, out)
+    if async_op:
+        return out, HostResult(pipe, (x_host, out))
+    pipe.wait()
     return out
+
+
+def forward_host(plan, x_host: torch.Tensor, interp: int, async_op: bool = False):
+    """[B,X,Y] pinned float32 -> [B,A,W] pinned float32 (project_tf_fast on a host batch)."""
+    return _run(plan, x_host, (x_host.shape[0], plan.A, plan.W), async_op, lambda pipe, out: pipe.forward(x_host, out, interp), "fwd")
+
+
+def adjoint_host(plan, y_host: torch.Tensor, interp: int, mode: int, async_op: bool = False):
+    """[B,A,W] pinned float32 -> [B,X,Y] pinned float32."""
+    return _run(plan, y_host, (y_host.shape[0], plan.X, plan.Y), async_op, lambda pipe, out: pipe.adjoint(y_host, out, interp, mode), "adj")

@@ -149,6 +149,25 @@ size_t ctr_fbp_workspace_bytes(const ctr_fbp_plan* plan, int B);
 int ctr_fbp(const ctr_fbp_plan* plan, const float* sino, int A, float* recon, int B, void* workspace,
             size_t workspace_bytes, void* stream);
 
+/* ---- host-buffer pipeline -------------------------------------------------------------------
+ * The reference's callers hand NumPy arrays to project_tf_fast (main_ct_vae.py:523-524,
+ * scripts/images_to_sinograms.py:61-68).  A pipe owns device staging for `chunk` images per
+ * slot (6 slots), its workspace and three streams; a call cuts the host batch into chunks
+ * and overlaps copy-in, kernels and copy-out.  Calls only ENQUEUE and return; results are
+ * valid after ctr_hostpipe_wait.  Host buffers should be page-locked (pinned) -- pageable
+ * memory works but serialises the copies.  Calls on one pipe are serialised by a mutex and
+ * their chunks share the ring, so back-to-back calls overlap each other's copies.
+ * ctr_hostpipe_done: 1 if everything enqueued so far has completed, 0 if not, < 0 on error. */
+typedef struct ctr_hostpipe ctr_hostpipe;
+int ctr_hostpipe_create(const ctr_plan* plan, int chunk, ctr_hostpipe** out);
+int ctr_hostpipe_destroy(ctr_hostpipe* pipe);
+/* img_host [B,X,Y] -> sino_host [B,A,W] */
+int ctr_hostpipe_forward(ctr_hostpipe* pipe, const float* img_host, float* sino_host, int B, int interp);
+/* dsino_host [B,A,W] -> dimg_host [B,X,Y] */
+int ctr_hostpipe_adjoint(ctr_hostpipe* pipe, const float* dsino_host, float* dimg_host, int B, int interp, int mode);
+int ctr_hostpipe_wait(ctr_hostpipe* pipe);
+int ctr_hostpipe_done(ctr_hostpipe* pipe);
+
 /* ---- zero-copy DLPack entry points ---------------------------------------------------------
  * Same operations on borrowed DLTensors (kDLCUDA, float32, compact row-major).
  * img may be [B,X,Y] or [B,X,Y,1]; sino [B,A,W] or [B,A,W,1].  `workspace` is any

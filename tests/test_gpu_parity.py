@@ -247,6 +247,31 @@ def test_pinned_host_batch_goes_through_the_chunked_pipeline(cp, orc):
     assert g.device.type == "cpu" and rel_l2(g.numpy(), orc.adjoint_exact(cot, th, X, X, True, 1)) <= TOL
 
 
+@pytest.mark.parametrize("chunk", [None, "32", "16"])
+def test_async_host_calls_overlap_and_match(cp, orc, chunk, monkeypatch):
+    """async_op=True: two host-buffer calls in flight at once (result + completion handle each); forced small
+    chunks exercise the staging ring's slot reuse and the ragged last chunk."""
+    if chunk:
+        monkeypatch.setenv("CTR_HOST_CHUNK", chunk)
+    rng = np.random.default_rng(18)
+    B, X, A = 120, 24, 9
+    th = _theta(A)
+    img = rng.random((B, X, X), dtype=np.float32)
+    want = orc.forward(img, th, True, 1)
+    cot = rng.random(want.shape, dtype=np.float32)
+    img_h, cot_h = torch.from_numpy(img).unsqueeze(-1).pin_memory(), torch.from_numpy(cot).pin_memory()
+    for _ in range(3):
+        s, hs = cp.project_tf_fast(img_h, th, pad=True, dim=2, integrate_vae=True, interpolation="bilinear", async_op=True)
+        g, hg = cp.backproject(cot_h, th, X, X, pad=True, interpolation="bilinear", async_op=True)
+        hs.wait()
+        hg.wait()
+        assert hs.is_completed() and hg.is_completed()
+        assert s.is_pinned() and rel_l2(s[..., 0].numpy(), want) <= TOL
+        assert rel_l2(g.numpy(), orc.adjoint_exact(cot, th, X, X, True, 1)) <= TOL
+    with pytest.raises(ValueError):
+        cp.project_tf_fast(torch.from_numpy(img[:4]).unsqueeze(-1), th, pad=True, dim=2, integrate_vae=True, async_op=True)
+
+
 @pytest.mark.parametrize("interp", INTERPS)
 @pytest.mark.parametrize("gather", [False, True])
 def test_fused_loglik_matches_oracle(cp, orc, interp, gather):

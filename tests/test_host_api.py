@@ -105,3 +105,20 @@ def test_host_pipeline_eligibility():
     assert not hostpipe.eligible(torch.zeros(40, 8, 8, dtype=torch.float64))
     assert not hostpipe.eligible(torch.zeros(4, 8, 8))    # small batches are not worth chunking
     assert not hostpipe.eligible(torch.zeros(40, 8, 8, requires_grad=True))
+
+
+def test_host_chunk_sizes(monkeypatch):
+    """Chunks of the native host pipeline: four per call, whole 16-image records, enough work per launch."""
+    import types
+
+    from ct_pvae_b200 import hostpipe
+    monkeypatch.delenv("CTR_HOST_CHUNK", raising=False)
+    monkeypatch.delenv("CTR_HOST_CHUNK_FWD", raising=False)
+    c2 = types.SimpleNamespace(A=180, X=128, Y=128)
+    c4 = types.SimpleNamespace(A=720, X=512, Y=512)
+    assert hostpipe.chunk_for(c2, 256, "fwd") == 64
+    assert hostpipe.chunk_for(c2, 1024, "adj") == 256
+    assert hostpipe.chunk_for(c4, 64, "fwd") == 16
+    assert hostpipe.chunk_for(c2, 40, "fwd") == 48          # one chunk: the batch is too small to split
+    monkeypatch.setenv("CTR_HOST_CHUNK", "32")
+    assert hostpipe.chunk_for(c2, 256, "fwd") == 32

@@ -43,6 +43,7 @@ SYMBOLS = {
     "ctr_plan_destroy": (_c_int, [_c_void_p]),
     "ctr_plan_info": (_c_int, [_c_void_p, _intp, _intp, _intp, _intp, _intp, _intp, _intp]),
     "ctr_plan_tables": (_c_int, [_c_void_p, _f32p, _f32p]),
+    "ctr_plan_describe": (_c_int, [_c_void_p, _c_int, ctypes.c_char_p, _c_size_t]),
     "ctr_forward_workspace_bytes": (_c_size_t, [_c_void_p, _c_int]),
     "ctr_adjoint_workspace_bytes": (_c_size_t, [_c_void_p, _c_int]),
     "ctr_radon_forward": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_size_t, _c_void_p]),
@@ -168,6 +169,11 @@ class Plan:
         inv = np.empty((self.A, 8), np.float32)
         check(lib().ctr_plan_tables(self.handle, fwd.ctypes.data_as(_f32p), inv.ctypes.data_as(_f32p)))
         return fwd, inv
+
+    def describe(self, B: int) -> str:
+        buf = ctypes.create_string_buffer(512)
+        check(lib().ctr_plan_describe(self.handle, int(B), buf, 512))
+        return buf.value.decode()
 
     def forward_workspace_bytes(self, B: int) -> int:
         return int(lib().ctr_forward_workspace_bytes(self.handle, B))

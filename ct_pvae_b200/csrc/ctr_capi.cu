@@ -89,11 +89,14 @@ struct ctr_plan {
     int n_cls[2] = {0, 0};
     CtrClassGeom geom[2];
     ctr::FwdConfig fc;    // 4 images per pixel record (any detector)
-    ctr::FwdConfig fcd;   // depth-first: 16 images per record, detectors <= 256 bins (R == 0: unavailable)
-    void* d_block = nullptr;   // one device allocation: [t | tinv | rays]
+    ctr::FwdConfig fcd;   // depth-first: 8/16 images per record, column-windowed on wide detectors (R == 0: unavailable)
+    std::vector<CtrChunk> chunks, chunks_d;   // CTA columns of the two shapes
+    void* d_block = nullptr;   // one device allocation: [t | tinv | rays | chunks | chunks_d]
     float* d_t = nullptr;
     float* d_tinv = nullptr;
     CtrRay* d_rays = nullptr;
+    CtrChunk* d_chunks = nullptr;
+    CtrChunk* d_chunks_d = nullptr;
 };
 
 struct ctr_fbp_plan {
@@ -207,7 +210,8 @@ int ctr_plan_create(const double* theta, int A, int X, int Y, int pad, int devic
     ctr_h_make_transforms(theta, A, p->H, p->W, p->t.data());
     ctr_h_invert_transforms(p->t.data(), A, p->tinv.data());
     ctr_h_class_geom(X, Y, p->padx, p->pady, p->geom);
-    ctr_h_build_rays(p->t.data(), A, p->rays, p->n_cls[0]);
+    std::vector<int> seg;
+    ctr_h_build_rays(p->t.data(), A, p->rays, p->n_cls[0], &seg);
     p->n_cls[1] = A - p->n_cls[0];
 
     DeviceGuard guard(device);
@@ -218,12 +222,36 @@ int ctr_plan_create(const double* theta, int A, int X, int Y, int pad, int devic
     p->fc = ctr::fwd_config(p->W, p->geom, smem_optin - 2048);
     p->fcd = ctr::fwd_config_depth(p->W, p->geom, smem_optin - 2048);
     if (p->fc.R < 1) { delete p; return fail(CTR_EUNSUPPORTED, "ctr_plan_create: image rows too wide for the shared-memory strips"); }
-    // one allocation + one upload for the three tables (plans are created per angle minibatch in training)
+    // CTA columns: chunks of consecutive table entries, strip height and (wide detectors) column windows
+    size_t strip_bytes = 0;
+    ctr_h_build_chunks(p->rays, seg, p->geom, p->fc.angles_per_cta(), p->W, p->fc.JW, p->fc.jchunks, ctr::kFwdNB * 4,
+                       p->fc.stages, 0, false, p->fc.R, 1, p->fc.R, p->chunks, strip_bytes);
+    if (p->fcd.windowed) {
+        const int NA = p->fcd.angles_per_cta(), fixed = ctr::FwdConfig::fixed_bytes(NA);
+        const size_t budget = (size_t)(smem_optin - 2048 - fixed);
+        int rmax = 16;
+        if (const char* e = getenv("CTR_FWD_R")) { int v = atoi(e); if (v >= 2 && v <= 31) rmax = v; }
+        if (ctr_h_build_chunks(p->rays, seg, p->geom, NA, p->W, p->fcd.JW, p->fcd.jchunks, ctr::kFwdNB * p->fcd.depth * 4,
+                               p->fcd.stages, budget, true, 0, 4, rmax, p->chunks_d, strip_bytes)) {
+            p->fcd.R = 1;   // available; the strip height is per chunk
+            p->fcd.smem = (size_t)fixed + (size_t)p->fcd.stages * strip_bytes;
+        } else {
+            p->fcd.R = 0;   // some CTA's rays are too far apart for a window that fits: whole-row shape only
+            p->chunks_d.clear();
+        }
+    } else if (p->fcd.R >= 1) {
+        ctr_h_build_chunks(p->rays, seg, p->geom, p->fcd.angles_per_cta(), p->W, p->fcd.JW, p->fcd.jchunks,
+                           ctr::kFwdNB * p->fcd.depth * 4, p->fcd.stages, 0, false, p->fcd.R, 1, p->fcd.R, p->chunks_d, strip_bytes);
+    }
+    // one allocation + one upload for all tables (plans are created per angle minibatch in training)
     const size_t tb = (size_t)A * 8 * sizeof(float), rb = (size_t)A * sizeof(CtrRay);
-    std::vector<unsigned char> host(2 * tb + rb);
+    const size_t cb = p->chunks.size() * sizeof(CtrChunk), cdb = p->chunks_d.size() * sizeof(CtrChunk);
+    std::vector<unsigned char> host(2 * tb + rb + cb + cdb);
     std::memcpy(host.data(), p->t.data(), tb);
     std::memcpy(host.data() + tb, p->tinv.data(), tb);
     std::memcpy(host.data() + 2 * tb, p->rays.data(), rb);
+    std::memcpy(host.data() + 2 * tb + rb, p->chunks.data(), cb);
+    if (cdb) std::memcpy(host.data() + 2 * tb + rb + cb, p->chunks_d.data(), cdb);
     if ((e = cudaMalloc(&p->d_block, host.size())) != cudaSuccess ||
         (e = cudaMemcpy(p->d_block, host.data(), host.size(), cudaMemcpyHostToDevice)) != cudaSuccess) {
         int rc = fail_cuda(e, "ctr_plan_create: table upload");
@@ -234,6 +262,8 @@ int ctr_plan_create(const double* theta, int A, int X, int Y, int pad, int devic
     p->d_t = (float*)p->d_block;
     p->d_tinv = (float*)((char*)p->d_block + tb);
     p->d_rays = (CtrRay*)((char*)p->d_block + 2 * tb);
+    p->d_chunks = (CtrChunk*)((char*)p->d_block + 2 * tb + rb);
+    p->d_chunks_d = (CtrChunk*)((char*)p->d_block + 2 * tb + rb + cb);
     *out = p;
     return CTR_OK;
 }
@@ -284,6 +314,23 @@ static size_t pack_bytes(const ctr_plan* p, int B)
     return align_up(G * std::max(px0, px1) * rec * sizeof(float), 256);
 }
 
+// human-readable description of the forward shape a batch of B would run (tests, bench, tuning)
+int ctr_plan_describe(const ctr_plan* p, int B, char* buf, size_t n)
+{
+    if (!p || !buf || n == 0 || B <= 0) return fail(CTR_EINVAL, "ctr_plan_describe: bad argument");
+    const ctr::FwdConfig& fc = fwd_cfg_for(p, B);
+    const std::vector<CtrChunk>& ch = (&fc == &p->fcd) ? p->chunks_d : p->chunks;
+    int rlo = 1 << 30, rhi = 0, wlo = 1 << 30, whi = 0, nwin = 0;
+    for (const CtrChunk& c : ch) {
+        rlo = std::min(rlo, c.R); rhi = std::max(rhi, c.R);
+        if (c.wc > 0) { wlo = std::min(wlo, c.wc); whi = std::max(whi, c.wc); ++nwin; }
+    }
+    snprintf(buf, n, "images_per_record=%d windowed=%d window_chunks=%d/%d JW=%d jchunks=%d NS=%d KA=%d stages=%d R=%d..%d wc=%d..%d smem=%zu",
+             ctr::kFwdNB * fc.depth, fc.windowed, nwin, (int)ch.size(), fc.JW, fc.jchunks, fc.NS, fc.KA, fc.stages, rlo, rhi,
+             nwin ? wlo : 0, whi, fc.smem);
+    return CTR_OK;
+}
+
 size_t ctr_forward_workspace_bytes(const ctr_plan* p, int B)
 {
     if (!p || B <= 0) return 0;
@@ -317,8 +364,7 @@ struct LoglikArgs {
 static size_t loglik_partial_bytes(const ctr_plan* p, int B)
 {
     const ctr::FwdConfig& fc = fwd_cfg_for(p, B);
-    const int NA = fc.angles_per_cta();
-    const size_t chunks = (size_t)(p->n_cls[0] + NA - 1) / NA + (size_t)(p->n_cls[1] + NA - 1) / NA;
+    const size_t chunks = (&fc == &p->fcd) ? p->chunks_d.size() : p->chunks.size();
     const size_t rec = (size_t)ctr::kFwdNB * fc.depth;
     const size_t G = ((size_t)B + rec - 1) / rec;
     return align_up(chunks * fc.jchunks * G * rec * sizeof(float), 256);
@@ -353,17 +399,15 @@ static int forward_impl(const ctr_plan* p, const float* img, float* out, int B, 
     fp.pk[0] = pk0; fp.pk[1] = pk1;
     fp.geom[0] = p->geom[0]; fp.geom[1] = p->geom[1];
     fp.rays = p->d_rays;
-    fp.n_cls[0] = p->n_cls[0]; fp.n_cls[1] = p->n_cls[1];
-    const int NA = fc.angles_per_cta();
+    const bool deep = (&fc == &p->fcd);
+    fp.chunks = deep ? p->d_chunks_d : p->d_chunks;
     fp.kbins = fc.kbins;
     fp.jwd = fc.JW * fc.depth;
     fp.ns = fc.NS;
     fp.stages = fc.stages;
     fp.isync = fc.isync;
-    fp.chunks0 = (p->n_cls[0] + NA - 1) / NA;
-    const int chunks = fp.chunks0 + (p->n_cls[1] + NA - 1) / NA;
+    const int chunks = (int)(deep ? p->chunks_d.size() : p->chunks.size());
     fp.H = p->H; fp.W = p->W; fp.A = p->A; fp.B = B;
-    fp.R = fc.R;
     fp.sino = out;
     fp.mask = nullptr; fp.meas = nullptr; fp.amap = nullptr; fp.A_all = p->A; fp.pnm = 1.f; fp.sqrt_reg = 0.f; fp.partial = nullptr;
     cudaError_t e;

@@ -54,6 +54,60 @@ struct CtrClassGeom {
     int Up, Vp;      // packed row length (pixels) and row count, halos included
 };
 
+// One forward CTA's share of the class-sorted ray table: rays [first, first+cnt) of class
+// `cls`.  wc > 0 selects column-windowed strips: instead of whole packed rows the strip
+// buffers hold, for every packed row, the `wc` pixels starting at a per-strip column that
+// follows the CTA's rays across the image (see ctr_win_*).  R = key rows per strip.
+struct CtrChunk {
+    int first, cnt;
+    int cls;
+    int wc;
+    int R;
+    int pad_[3];
+};
+
+// Where the rays of one angle are, as a function of the detector bin j and the strip
+// coordinate v:  u(j, v) = a + b*j + g*v  (eliminate the step index i from CtrRay's two
+// lines; |g| <= 1, |b| in [1, 1.42]).  Real arithmetic, used only to PLACE the window
+// with two pixels of slack -- sample coordinates themselves stay the exact float32 ones.
+struct CtrWinCoef {
+    float a, b, g;
+};
+
+CTR_HD CtrWinCoef ctr_win_coef(const CtrRay& r)
+{
+    CtrWinCoef c;
+    c.g = r.u1 / r.v1;                                  // IEEE division on both sides (no fast-math)
+    c.b = CTR_SUB(r.u0, CTR_MUL(c.g, r.v0));            // explicit roundings: host and device agree bit for bit
+    c.a = CTR_SUB(r.u2, CTR_MUL(c.g, r.v2));
+    return c;
+}
+
+// u-extent of bins [jlo, jhi] x key rows of strip [rbase, rbase+R) (v in [rbase-0.5, rbase+R]
+// covers floor- and round-keyed samples), clipped to the image footprint (ulo, uhi).
+CTR_HD void ctr_win_range(const CtrWinCoef& c, float jlo, float jhi, float vlo, float vhi, float ulo, float uhi,
+                          float& umin, float& umax)
+{
+    const float bj0 = CTR_MUL(c.b, jlo), bj1 = CTR_MUL(c.b, jhi), gv0 = CTR_MUL(c.g, vlo), gv1 = CTR_MUL(c.g, vhi);
+    float lo = CTR_ADD(CTR_ADD(c.a, fminf(bj0, bj1)), fminf(gv0, gv1));
+    float hi = CTR_ADD(CTR_ADD(c.a, fmaxf(bj0, bj1)), fmaxf(gv0, gv1));
+    lo = fminf(fmaxf(lo, ulo), uhi);
+    hi = fminf(fmaxf(hi, ulo), uhi);
+    umin = fminf(umin, lo);
+    umax = fmaxf(umax, hi);
+}
+
+// First packed column of the window: leftmost tap floor(umin) with one pixel of slack,
+// kept inside the packed row.  Columns needed: floor(umin)-1 .. floor(umax)+2.
+CTR_HD int ctr_win_start(float umin, int offu, int Up, int wc)
+{
+    int c = (int)floorf(umin) - 1 - offu;
+    if (c > Up - wc) c = Up - wc;
+    if (c < 0) c = 0;
+    return c;
+}
+CTR_HD int ctr_win_need(float umin, float umax) { return (int)floorf(umax) - (int)floorf(umin) + 4; }
+
 // NB interleaved floats -> registers (128-bit shared-memory loads on the device).
 template <int NB>
 CTR_HD void ctr_ldv(const float* __restrict__ p, float* __restrict__ out)

@@ -7,6 +7,7 @@
 //   tensorflow/python/ops/image_ops.py _image_projective_transform_v3_grad (inverse table)
 // Must be compiled with -ffp-contract=off: the table is float32, evaluated in TF's order.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <vector>
@@ -91,24 +92,103 @@ inline void ctr_h_class_geom(int X, int Y, int padx, int pady, CtrClassGeom g[2]
     g[1].offu = padx - 1; g[1].offv = pady - 1; g[1].Up = ctr_h_row_pixels(X); g[1].Vp = Y + 2;
 }
 
-// Class-sorted ray table: class-0 angles first (n0 of them), then class 1.
-inline void ctr_h_build_rays(const float* t, int A, std::vector<CtrRay>& rays, int& n0)
+// Class-sorted ray table: class-0 angles first (n0 of them), then class 1.  Inside a class the
+// rays are ordered by (side the detector axis runs to, slope of the rays): CTAs take consecutive
+// table entries, and neighbours that look at the image from almost the same direction need
+// almost the same column window (ctr_h_build_chunks).  `seg` receives the start of every run of
+// equal (class, side) plus the end of the table.
+inline void ctr_h_build_rays(const float* t, int A, std::vector<CtrRay>& rays, int& n0, std::vector<int>* seg = nullptr)
 {
     rays.clear();
     rays.reserve(A);
-    for (int pass = 0; pass < 2; ++pass) {
-        for (int a = 0; a < A; ++a) {
-            const float* r = t + 8 * a;
-            // x = t0*j + t1*i + t2 ; y = t3*j + t4*i + t5.  Strip axis = the one that
-            // advances fastest per step i: |t4| >= |t1| -> rows (class 0).
-            const int cls = (std::fabs(r[4]) >= std::fabs(r[1])) ? 0 : 1;
-            if (cls != pass) continue;
-            CtrRay q;
-            if (cls == 0) { q.u0 = r[0]; q.u1 = r[1]; q.u2 = r[2]; q.v0 = r[3]; q.v1 = r[4]; q.v2 = r[5]; }
-            else          { q.u0 = r[3]; q.u1 = r[4]; q.u2 = r[5]; q.v0 = r[0]; q.v1 = r[1]; q.v2 = r[2]; }
-            q.angle = a; q.cls = cls;
-            rays.push_back(q);
-        }
-        if (pass == 0) n0 = (int)rays.size();
+    for (int a = 0; a < A; ++a) {
+        const float* r = t + 8 * a;
+        // x = t0*j + t1*i + t2 ; y = t3*j + t4*i + t5.  Strip axis = the one that
+        // advances fastest per step i: |t4| >= |t1| -> rows (class 0).
+        const int cls = (std::fabs(r[4]) >= std::fabs(r[1])) ? 0 : 1;
+        CtrRay q;
+        if (cls == 0) { q.u0 = r[0]; q.u1 = r[1]; q.u2 = r[2]; q.v0 = r[3]; q.v1 = r[4]; q.v2 = r[5]; }
+        else          { q.u0 = r[3]; q.u1 = r[4]; q.u2 = r[5]; q.v0 = r[0]; q.v1 = r[1]; q.v2 = r[2]; }
+        q.angle = a; q.cls = cls;
+        rays.push_back(q);
     }
+    auto side = [](const CtrRay& q) { return ctr_win_coef(q).b < 0.f ? 1 : 0; };
+    std::stable_sort(rays.begin(), rays.end(), [&](const CtrRay& x, const CtrRay& y) {
+        if (x.cls != y.cls) return x.cls < y.cls;
+        const int sx = side(x), sy = side(y);
+        if (sx != sy) return sx < sy;
+        return ctr_win_coef(x).g < ctr_win_coef(y).g;
+    });
+    n0 = 0;
+    for (const CtrRay& q : rays) n0 += (q.cls == 0);
+    if (seg) {
+        seg->clear();
+        for (int k = 0; k < (int)rays.size(); ++k)
+            if (k == 0 || rays[k].cls != rays[k - 1].cls || side(rays[k]) != side(rays[k - 1])) seg->push_back(k);
+        seg->push_back((int)rays.size());
+    }
+}
+
+// Column window (pixels) that the CTA serving rays [first, first+cnt) x detector chunks of JW bins
+// needs when its strips hold R key rows: the maximum over detector chunks and strips of what the
+// device will ask for (same ctr_win_* routines, same float32 arithmetic).
+inline int ctr_h_window_pixels(const CtrRay* rays, int cnt, const CtrClassGeom& g, int W, int JW, int jchunks, int R)
+{
+    int need = 0;
+    const int K = (g.Vp + R - 1) / R;
+    std::vector<CtrWinCoef> co(cnt);
+    for (int q = 0; q < cnt; ++q) co[q] = ctr_win_coef(rays[q]);
+    for (int z = 0; z < jchunks; ++z) {
+        const float jlo = (float)(z * JW), jhi = (float)std::min(W - 1, z * JW + JW - 1);
+        for (int k = 0; k < K; ++k) {
+            const float vlo = (float)(k * R + g.offv) - 0.5f, vhi = (float)(k * R + g.offv + R);
+            float umin = 3.0e38f, umax = -3.0e38f;
+            for (int q = 0; q < cnt; ++q) ctr_win_range(co[q], jlo, jhi, vlo, vhi, g.ulo, g.uhi, umin, umax);
+            need = std::max(need, ctr_win_need(umin, umax));
+        }
+    }
+    return need;
+}
+
+// Cut the ray table into CTA-sized chunks of <= NA rays that never straddle a segment.
+//   windowed == false: whole packed rows, R key rows per strip for everybody.
+//   windowed == true : per chunk, the tallest strip (R <= Rmax) whose `stages` buffers of
+//                      (R+1) x window pixels fit `strip_budget` bytes; false if some chunk cannot
+//                      get R >= Rmin (the caller then keeps the whole-row configuration).
+// max_strip_bytes receives the largest single strip buffer of any chunk.
+inline bool ctr_h_build_chunks(const std::vector<CtrRay>& rays, const std::vector<int>& seg, const CtrClassGeom geom[2],
+                               int NA, int W, int JW, int jchunks, int rec_bytes, int stages, size_t strip_budget,
+                               bool windowed, int R, int Rmin, int Rmax, std::vector<CtrChunk>& out, size_t& max_strip_bytes)
+{
+    out.clear();
+    max_strip_bytes = 0;
+    for (size_t s = 0; s + 1 < seg.size(); ++s)
+        for (int first = seg[s]; first < seg[s + 1]; first += NA) {
+            CtrChunk c{};
+            c.first = first;
+            c.cnt = std::min(NA, seg[s + 1] - first);
+            c.cls = rays[first].cls;
+            const CtrClassGeom& g = geom[c.cls];
+            if (!windowed) {
+                c.wc = 0;
+                c.R = R;
+                max_strip_bytes = std::max(max_strip_bytes, (size_t)(R + 1) * g.Up * rec_bytes);
+            } else {
+                bool fit = false;
+                for (int r = std::min(Rmax, g.Vp); r >= Rmin && !fit; --r) {
+                    int wc = (ctr_h_window_pixels(&rays[first], c.cnt, g, W, JW, jchunks, r) + 1) / 2 * 2;
+                    if (wc >= g.Up) wc = g.Up;            // the window is the whole row
+                    const size_t bytes = (size_t)(r + 1) * wc * rec_bytes;
+                    if ((size_t)stages * bytes <= strip_budget) {
+                        c.wc = (wc == g.Up) ? 0 : wc;
+                        c.R = r;
+                        max_strip_bytes = std::max(max_strip_bytes, bytes);
+                        fit = true;
+                    }
+                }
+                if (!fit) return false;
+            }
+            out.push_back(c);
+        }
+    return true;
 }

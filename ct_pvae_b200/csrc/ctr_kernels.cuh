@@ -202,10 +202,8 @@ struct FwdParams {
     const float* pk[2];     // packed images per class  [G][Vp][Up][NB*DEPTH]
     CtrClassGeom geom[2];
     const CtrRay* rays;     // class-sorted ray table [A]
-    int n_cls[2];           // angles per class
-    int chunks0;            // CTAs (along grid.x) that serve class 0
+    const CtrChunk* chunks; // [gridDim.x] rays, class, strip height and column window of every CTA column
     int H, W, A, B;
-    int R;                  // key rows per strip (strip holds R+1 packed rows)
     int kbins;              // 1: a thread's KA rays are KA detector bins (JW apart) of ONE angle; 0: KA angles of one bin
     int jwd, ns;            // consumer threads per angle slot (JW bins x DEPTH groups) and angle slots; block = jwd*ns + 32
     int stages;             // strip buffers in the shared-memory ring (2..4)
@@ -249,14 +247,15 @@ __global__ void __launch_bounds__(kFwdMaxThreads, 1) ctr_fwd_kernel(const FwdPar
     CtrRay* rays_s = reinterpret_cast<CtrRay*>(smem_raw + 128);              // NA rays
     const int rays_bytes = round_up(NA * (int)sizeof(CtrRay), 128);
 
-    const int cls = (int)blockIdx.x >= p.chunks0;
-    const int lchunk = cls ? (int)blockIdx.x - p.chunks0 : (int)blockIdx.x;
-    const int first = (cls ? p.n_cls[0] : 0) + lchunk * NA;
-    const int cnt = min(NA, (cls ? p.n_cls[1] : p.n_cls[0]) - lchunk * NA);
+    const CtrChunk ch = p.chunks[blockIdx.x];
+    const int cls = ch.cls, first = ch.first, cnt = ch.cnt;
     const int g = blockIdx.y;
     const CtrClassGeom geom = cls ? p.geom[1] : p.geom[0];  // static indices: stays in registers
-    const int R = p.R;
-    const int strip_floats = (R + 1) * geom.Up * REC;
+    const int R = ch.R;
+    // column-windowed strips (ch.wc > 0): a strip row holds ch.wc pixels starting at column cst[b]
+    const int Us = ch.wc > 0 ? ch.wc : geom.Up;              // row stride of the strip buffers (pixels)
+    const int strip_floats = (R + 1) * Us * REC;
+    int* cst = reinterpret_cast<int*>(smem_raw + 64);                      // [S] window start of the strip in buffer b
     float* buf0 = reinterpret_cast<float*>(smem_raw + 128 + rays_bytes);   // S strip buffers, strip_floats apart
     const int K = (geom.Vp + R - 1) / R;
     const float* pkg = (cls ? p.pk[1] : p.pk[0]) + (size_t)g * geom.Vp * geom.Up * REC;
@@ -275,13 +274,43 @@ __global__ void __launch_bounds__(kFwdMaxThreads, 1) ctr_fwd_kernel(const FwdPar
     // strip k-S.  No CTA-wide barrier in the loop: a warp that finishes a strip early moves on to the
     // next (already resident) one, so the ragged ends of the strips overlap instead of idling the SM.
     if (producer) {
-        if ((tid & 31) == 0) {
-            for (int k = 0, b = 0, use = 0; k < K; ++k) {      // b = k % S, use = k / S
-                if (use > 0) mbar_wait(&empty[b], (uint32_t)((use - 1) & 1));
+        const int lane = tid & 31;
+        if (ch.wc == 0) {
+            if (lane == 0) {
+                for (int k = 0, b = 0, use = 0; k < K; ++k) {      // b = k % S, use = k / S
+                    if (use > 0) mbar_wait(&empty[b], (uint32_t)((use - 1) & 1));
+                    const int rows = min(R + 1, geom.Vp - k * R);
+                    const uint32_t bytes = (uint32_t)rows * geom.Up * REC * 4u;
+                    mbar_arrive_expect_tx(&full[b], bytes);
+                    bulk_g2s(buf0 + (size_t)b * strip_floats, pkg + (size_t)k * R * geom.Up * REC, bytes, &full[b]);
+                    if (++b == S) { b = 0; ++use; }
+                }
+            }
+        } else {
+            // windowed: the whole warp takes part, lane r copies packed row r of the strip (R + 1 <= 32).
+            // The window start follows the CTA's rays: lane q < cnt holds the line family of ray q.
+            const float jlo = (float)(blockIdx.z * JW), jhi = (float)min(p.W - 1, (int)blockIdx.z * JW + JW - 1);
+            CtrWinCoef co{0.f, 0.f, 0.f};
+            if (lane < cnt) co = ctr_win_coef(rays_s[lane]);
+            const uint32_t row_bytes = (uint32_t)Us * REC * 4u;
+            for (int k = 0, b = 0, use = 0; k < K; ++k) {
+                float umin = 3.0e38f, umax = -3.0e38f;
+                if (lane < cnt)
+                    ctr_win_range(co, jlo, jhi, (float)(k * R + geom.offv) - 0.5f, (float)(k * R + geom.offv + R), geom.ulo,
+                                  geom.uhi, umin, umax);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) umin = fminf(umin, __shfl_xor_sync(0xffffffffu, umin, o));
+                const int c0 = ctr_win_start(umin, geom.offu, geom.Up, Us);
                 const int rows = min(R + 1, geom.Vp - k * R);
-                const uint32_t bytes = (uint32_t)rows * geom.Up * REC * 4u;
-                mbar_arrive_expect_tx(&full[b], bytes);
-                bulk_g2s(buf0 + (size_t)b * strip_floats, pkg + (size_t)k * R * geom.Up * REC, bytes, &full[b]);
+                if (lane == 0) {
+                    if (use > 0) mbar_wait(&empty[b], (uint32_t)((use - 1) & 1));
+                    cst[b] = c0;
+                    mbar_arrive_expect_tx(&full[b], (uint32_t)rows * row_bytes);   // release: publishes cst[b]
+                }
+                __syncwarp();
+                if (lane < rows)
+                    bulk_g2s(buf0 + (size_t)b * strip_floats + (size_t)lane * Us * REC,
+                             pkg + ((size_t)(k * R + lane) * geom.Up + c0) * REC, row_bytes, &full[b]);
                 if (++b == S) { b = 0; ++use; }
             }
         }
@@ -312,6 +341,7 @@ __global__ void __launch_bounds__(kFwdMaxThreads, 1) ctr_fwd_kernel(const FwdPar
             const float* strip = buf0 + (size_t)b * strip_floats + gsub * NB;
             const float vend = (float)((k + 1) * R + geom.offv);
             const int rbase = k * R + geom.offv;
+            const int offu = geom.offu + (ch.wc > 0 ? cst[b] : 0);   // first packed column held by this strip
 #pragma unroll
             for (int q = 0; q < KA; ++q) {
                 const bool isync = (DEPTH == 1) && p.isync && !kb;    // warp-uniform
@@ -325,8 +355,8 @@ __global__ void __launch_bounds__(kFwdMaxThreads, 1) ctr_fwd_kernel(const FwdPar
                     s.fi = ri[q];
                     s.n = rn[q];
                     s.dfi = (r.v1 >= 0.f) ? 1.f : -1.f;
-                    if (isync) ctr_march_isync<NB, INTERP, REC>(strip, geom.Up, vend, rbase, geom.offu, r, s, acc[q]);
-                    else ctr_march<NB, INTERP, REC>(strip, geom.Up, vend, rbase, geom.offu, r, s, acc[q]);
+                    if (isync) ctr_march_isync<NB, INTERP, REC>(strip, Us, vend, rbase, offu, r, s, acc[q]);
+                    else ctr_march<NB, INTERP, REC>(strip, Us, vend, rbase, offu, r, s, acc[q]);
                     ri[q] = s.fi;
                     rn[q] = s.n;
                 }
@@ -587,7 +617,9 @@ __global__ void __launch_bounds__(256) ctr_fbp_filter_kernel(const float* __rest
 // ------------------------------------------------------------------------------------------ launchers
 struct FwdConfig {
     int JW, NS, KA, R, jchunks, depth, kbins, stages, isync;
+    int windowed;   // 1: column-windowed strips, per-chunk R and window (R and smem are filled in by ctr_plan_create)
     size_t smem;
+    static constexpr int fixed_bytes(int NA) { return 128 + (NA * (int)sizeof(CtrRay) + 127) / 128 * 128; }
     int angles_per_cta() const { return kbins ? NS : NS * KA; }
 };
 
@@ -683,12 +715,30 @@ inline FwdConfig fwd_config_depth(int W, const CtrClassGeom geom[2], int smem_bu
     } else {
         c.JW = round_up(W, 32 / c.depth);
         if (c.JW * c.depth > kFwdMaxConsumers) {
-            // experiment (CTR_FWD_WIDE_DEPTH): 8-image records on a wide detector, split in chunks of 368
-            // bins that each stream the full-width strips, four angles per thread to pay for the re-reads
-            if (c.depth != 2 || getenv("CTR_FWD_WIDE_DEPTH") == nullptr) return c;
-            c.JW = kFwdMaxConsumers / 2;
-            c.jchunks = (W + c.JW - 1) / c.JW;
-            c.KA = 4;
+            if (c.depth == 2 && getenv("CTR_FWD_WIDE_DEPTH") != nullptr) {
+                // experiment: 8-image records on a wide detector, split in chunks of 368 bins that each
+                // stream the full-width strips, four angles per thread to pay for the re-reads
+                c.JW = kFwdMaxConsumers / 2;
+                c.jchunks = (W + c.JW - 1) / c.JW;
+                c.KA = 4;
+            } else {
+                // wide detector: 16-image records with COLUMN-WINDOWED strips.  The detector is cut into chunks
+                // of JW bins, NS angle slots share a CTA (neighbouring angles need nearly the same window), and
+                // every strip holds only the columns those rays cross.  R, the windows and the shared-memory
+                // size depend on the angles: ctr_plan_create fills them in (ctr_h_build_chunks).
+                if (getenv("CTR_FWD_NOWINDOW") != nullptr) return c;
+                c.depth = 4;
+                c.NS = 2;
+                if (const char* e = getenv("CTR_FWD_WIN_NS")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) c.NS = v; }
+                c.KA = 2;
+                c.JW = kFwdMaxConsumers / (c.depth * c.NS) / 8 * 8;
+                if (const char* e = getenv("CTR_FWD_WIN_JW")) { int v = atoi(e); if (v >= 8 && v % 8 == 0 && v * c.depth * c.NS <= kFwdMaxConsumers) c.JW = v; }
+                c.jchunks = (W + c.JW - 1) / c.JW;
+                c.JW = round_up((W + c.jchunks - 1) / c.jchunks, c.NS >= 4 ? 2 : 8 / c.NS);   // even out the detector chunks (whole warps per CTA)
+                c.stages = fwd_stages();
+                c.windowed = 1;
+                return c;   // R == 0 until the plan has sized the windows
+            }
         }
     }
     const int fixed = 128 + round_up(c.NS * c.KA * (int)sizeof(CtrRay), 128);

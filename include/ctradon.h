@@ -100,6 +100,9 @@ int ctr_plan_info(const ctr_plan* plan, int* A, int* X, int* Y, int* H, int* W, 
 /* copies the plan's [A,8] tables to host buffers (either may be NULL) */
 int ctr_plan_tables(const ctr_plan* plan, float* fwd_a8, float* inv_a8);
 
+/* one line describing the forward kernel shape a batch of B images would use (diagnostics) */
+int ctr_plan_describe(const ctr_plan* plan, int B, char* buf, size_t n);
+
 size_t ctr_forward_workspace_bytes(const ctr_plan* plan, int B);
 size_t ctr_adjoint_workspace_bytes(const ctr_plan* plan, int B);
 

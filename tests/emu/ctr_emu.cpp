@@ -95,6 +95,82 @@ void forward_impl(const float* img, int B, int X, int Y, int H, int W, int padx,
     }
 }
 
+// Column-windowed strips (ctr_fwd_kernel with CtrChunk::wc > 0): CTA = chunk of <= NA neighbouring rays x
+// detector chunk of JW bins; per strip the producer warp places a window of wc columns from the CTA's line
+// families.  Everything outside the window is NaN here, so a sample that falls outside poisons its ray sum.
+// Returns the number of chunks that really got a window (wc > 0), or -1 if the shape does not fit `budget`.
+template <int INTERP, int DEPTH>
+int forward_window_impl(const float* img, int B, int X, int Y, int H, int W, int padx, int pady, const float* t, int A,
+                        int JW, int NA, int Rmax, int budget, float* sino)
+{
+    constexpr int REC = NB * DEPTH;
+    CtrClassGeom geom[2];
+    ctr_h_class_geom(X, Y, padx, pady, geom);
+    std::vector<float> pk[2];
+    pack_images<DEPTH>(img, B, X, Y, geom, pk[0], pk[1]);
+    std::vector<CtrRay> rays;
+    std::vector<int> seg;
+    int n0 = 0;
+    ctr_h_build_rays(t, A, rays, n0, &seg);
+    const int jchunks = (W + JW - 1) / JW;
+    std::vector<CtrChunk> chunks;
+    size_t strip_bytes = 0;
+    if (!ctr_h_build_chunks(rays, seg, geom, NA, W, JW, jchunks, REC * 4, 2, (size_t)budget, true, 0, 2, Rmax, chunks, strip_bytes))
+        return -1;
+    int windowed = 0, covered = 0;
+    const int G = (B + REC - 1) / REC;
+    for (const CtrChunk& ch : chunks) {
+        windowed += ch.wc > 0;
+        covered += ch.cnt;
+        const CtrClassGeom& cg = geom[ch.cls];
+        const int R = ch.R, Us = ch.wc > 0 ? ch.wc : cg.Up, K = (cg.Vp + R - 1) / R;
+        for (int z = 0; z < jchunks; ++z)
+            for (int g = 0; g < G; ++g) {
+                const float* pkg = pk[ch.cls].data() + (size_t)g * cg.Vp * cg.Up * REC;
+                // consumer state of every (ray, bin, group) thread of the CTA
+                const int nb = std::min(JW, W - z * JW);
+                std::vector<CtrRayState> st((size_t)ch.cnt * nb);
+                std::vector<float> acc((size_t)ch.cnt * nb * REC, 0.f);
+                for (int q = 0; q < ch.cnt; ++q)
+                    for (int jj = 0; jj < nb; ++jj) ctr_ray_begin(rays[ch.first + q], cg, z * JW + jj, H, st[(size_t)q * nb + jj]);
+                for (int k = 0; k < K; ++k) {
+                    // producer warp
+                    int c0 = 0;
+                    if (ch.wc > 0) {
+                        const float jlo = (float)(z * JW), jhi = (float)std::min(W - 1, z * JW + JW - 1);
+                        float umin = 3.0e38f, umax = -3.0e38f;
+                        for (int q = 0; q < ch.cnt; ++q)
+                            ctr_win_range(ctr_win_coef(rays[ch.first + q]), jlo, jhi, (float)(k * R + cg.offv) - 0.5f,
+                                          (float)(k * R + cg.offv + R), cg.ulo, cg.uhi, umin, umax);
+                        c0 = ctr_win_start(umin, cg.offu, cg.Up, Us);
+                    }
+                    const int rows = std::min(R + 1, cg.Vp - k * R);
+                    std::vector<float> strip((size_t)(R + 1) * Us * REC, std::nanf(""));
+                    for (int rr = 0; rr < rows; ++rr)
+                        std::memcpy(strip.data() + (size_t)rr * Us * REC, pkg + ((size_t)(k * R + rr) * cg.Up + c0) * REC,
+                                    sizeof(float) * Us * REC);
+                    // consumers
+                    for (int q = 0; q < ch.cnt; ++q)
+                        for (int jj = 0; jj < nb; ++jj)
+                            for (int gsub = 0; gsub < DEPTH; ++gsub) {
+                                CtrRayState s = st[(size_t)q * nb + jj];   // the DEPTH lanes of a ray march identically
+                                ctr_march<NB, INTERP, REC>(strip.data() + gsub * NB, Us, (float)((k + 1) * R + cg.offv),
+                                                           k * R + cg.offv, cg.offu + c0, rays[ch.first + q], s,
+                                                           &acc[((size_t)q * nb + jj) * REC + gsub * NB]);
+                                if (gsub == DEPTH - 1) st[(size_t)q * nb + jj] = s;
+                            }
+                }
+                for (int q = 0; q < ch.cnt; ++q)
+                    for (int jj = 0; jj < nb; ++jj)
+                        for (int n = 0; n < REC; ++n) {
+                            const int b = g * REC + n;
+                            if (b < B) sino[((size_t)b * A + rays[ch.first + q].angle) * W + z * JW + jj] = acc[((size_t)q * nb + jj) * REC + n];
+                        }
+            }
+    }
+    return covered == A ? windowed : -2;
+}
+
 // ctr_march_isync replayed for one quarter-warp: 8 adjacent rays of one angle take the same
 // step index per trip (mirrors the device loop in ctr_kernels.cuh; shuffles become array ops).
 template <int INTERP>
@@ -245,6 +321,14 @@ void emu_forward_depth(const float* img, int B, int X, int Y, int H, int W, int 
 {
     if (interp == CTR_NEAREST) forward_impl<CTR_NEAREST, 4>(img, B, X, Y, H, W, padx, pady, t, A, R, sino);
     else forward_impl<CTR_BILINEAR, 4>(img, B, X, Y, H, W, padx, pady, t, A, R, sino);
+}
+
+// column-windowed depth-first strips (16-image records)
+int emu_forward_window(const float* img, int B, int X, int Y, int H, int W, int padx, int pady, const float* t, int A,
+                       int interp, int JW, int NA, int Rmax, int budget, float* sino)
+{
+    if (interp == CTR_NEAREST) return forward_window_impl<CTR_NEAREST, 4>(img, B, X, Y, H, W, padx, pady, t, A, JW, NA, Rmax, budget, sino);
+    return forward_window_impl<CTR_BILINEAR, 4>(img, B, X, Y, H, W, padx, pady, t, A, JW, NA, Rmax, budget, sino);
 }
 
 // mode 0: exact (table = forward transforms); mode 1: tf-compat (table = inverted transforms)

@@ -104,3 +104,53 @@ def test_emulated_kernels_property(emu, orc, B, X, Y, pad, R, th, seed):
             emu.emu_adjoint(P(y), B, X, Y, H, W, padx, pady, P(table), A, interp, mode, 32, 8, 40, P(g))
             gw = fn(y, th, X, Y, pad, interp)
             assert np.abs(g - gw).max() <= 2e-5 * max(1.0, np.abs(gw).max())
+
+
+# ---- column-windowed strips (wide detectors, 16-image records) ----
+WIN_CASES = [
+    # B, X, Y, A, pad, JW, NA, Rmax, budget bytes (2 strip buffers), theta kind
+    (3, 64, 64, 24, True, 24, 2, 8, 60000, "even"),
+    (2, 64, 64, 24, True, 16, 4, 6, 40000, "even"),
+    (2, 48, 80, 20, True, 32, 2, 8, 80000, "even"),
+    (2, 80, 48, 20, False, 24, 2, 5, 50000, "even"),
+    (2, 64, 64, 11, True, 24, 2, 8, 80000, "random"),       # far-apart angles in one CTA: wide or whole-row windows
+    (17, 40, 40, 16, True, 16, 4, 7, 30000, "even"),        # two 16-image records, second one ragged
+]
+
+
+@pytest.mark.parametrize("B,X,Y,A,pad,JW,NA,Rmax,budget,kind", WIN_CASES)
+def test_emulated_windowed_forward_matches_oracle(emu, orc, B, X, Y, A, pad, JW, NA, Rmax, budget, kind):
+    rng = np.random.default_rng(A * 131 + X)
+    th = np.linspace(0, np.pi, A, endpoint=False) if kind == "even" else rng.uniform(-4, 4, A)
+    img = rng.random((B, X, Y), dtype=np.float32)
+    H, W, padx, pady = orc.frame_of(X, Y, pad)
+    t = orc.make_transforms(th, H, W)
+    emu.emu_forward_window.restype = ctypes.c_int
+    for interp in (0, 1):
+        s = np.full((B, A, W), np.nan, np.float32)
+        nwin = emu.emu_forward_window(P(img), B, X, Y, H, W, padx, pady, P(t), A, interp, JW, NA, Rmax, budget, P(s))
+        assert nwin >= 0, "shape did not fit the budget / rays not covered"
+        if kind == "even":
+            assert nwin > 0, "no chunk was actually windowed: the case tests nothing"
+        assert not np.isnan(s).any(), "a sample fell outside its strip window"
+        assert rel_l2(s, orc.forward(img, th, pad, interp)) <= 1e-6
+
+
+@settings(max_examples=25, deadline=None)
+@given(X=st.integers(8, 72), Y=st.integers(8, 72), pad=st.booleans(), JW=st.sampled_from([8, 16, 24, 40]),
+       NA=st.sampled_from([1, 2, 4]), Rmax=st.integers(2, 12), seed=st.integers(0, 10_000),
+       th=st.lists(st.floats(-7.0, 7.0, allow_nan=False), min_size=1, max_size=8))
+def test_emulated_windowed_forward_property(emu, orc, X, Y, pad, JW, NA, Rmax, seed, th):
+    rng = np.random.default_rng(seed)
+    th = np.asarray(th, np.float64)
+    A = th.size
+    img = rng.random((2, X, Y), dtype=np.float32)
+    H, W, padx, pady = orc.frame_of(X, Y, pad)
+    t = orc.make_transforms(th, H, W)
+    emu.emu_forward_window.restype = ctypes.c_int
+    for interp in (0, 1):
+        s = np.full((2, A, W), np.nan, np.float32)
+        nwin = emu.emu_forward_window(P(img), 2, X, Y, H, W, padx, pady, P(t), A, interp, JW, NA, Rmax, 1 << 20, P(s))
+        assert nwin >= 0
+        assert not np.isnan(s).any()
+        assert rel_l2(s, orc.forward(img, th, pad, interp)) <= 1e-6

@@ -90,6 +90,24 @@ def test_large_and_rectangular_frames(cp, orc, B, X, Y, A, pad):
         assert rel_l2(g.cpu().numpy(), orc.adjoint_exact(y, th, X, Y, pad, IID[interp])) <= TOL
 
 
+@pytest.mark.parametrize("B,X,Y,A,pad,kind", [(16, 300, 300, 24, True, "even"), (20, 200, 420, 10, False, "random"),
+                                              (33, 260, 260, 16, True, "even"), (12, 512, 512, 6, True, "random")])
+def test_windowed_forward_matches_oracle(cp, orc, B, X, Y, A, pad, kind):
+    """Wide detector + batch >= 12: 16-image records with column-windowed strips (per-CTA windows that follow
+    the rays).  Far-apart random angles force wide / whole-row windows or the 4-image fallback."""
+    from ct_pvae_b200 import _lib
+    rng = np.random.default_rng(70 + B)
+    th = _theta(A) if kind == "even" else rng.uniform(-4, 4, A)
+    img = rng.random((B, X, Y), dtype=np.float32)
+    desc = _lib.get_plan(np.asarray(th, np.float64), X, Y, pad, 0).describe(B)
+    if kind == "even":
+        assert "images_per_record=16 windowed=1" in desc and "window_chunks=0/" not in desc, desc
+    for interp in INTERPS:
+        got = cp.project_tf_fast(torch.from_numpy(img).cuda().unsqueeze(-1), th, pad=pad, dim=2, integrate_vae=True,
+                                 interpolation=interp)[..., 0]
+        assert rel_l2(got.cpu().numpy(), orc.forward(img, th, pad, IID[interp])) <= TOL, desc
+
+
 @pytest.mark.parametrize("seed", range(8))
 def test_randomised_shapes(cp, orc, seed):
     """Random batch / image / angle-set shapes (ragged against every internal group size)."""
@@ -168,7 +186,7 @@ def test_autograd_is_the_adjoint(cp, orc, interp):
 
 
 @pytest.mark.parametrize("interp", INTERPS)
-@pytest.mark.parametrize("B,X,A", [(256, 128, 180), (8, 512, 720)])
+@pytest.mark.parametrize("B,X,A", [(256, 128, 180), (8, 512, 720), (16, 512, 720)])
 def test_full_size_properties(cp, B, X, A, interp):
     """BASELINE.json sizes (C2: 256x128^2x180, C4 slice: 512^2x720): size-independent checks."""
     g = torch.Generator(device="cuda").manual_seed(5)

@@ -88,15 +88,18 @@ struct ctr_plan {
     std::vector<CtrRay> rays;
     int n_cls[2] = {0, 0};
     CtrClassGeom geom[2];
-    ctr::FwdConfig fc;    // 4 images per pixel record (any detector)
-    ctr::FwdConfig fcd;   // depth-first: 8/16 images per record, column-windowed on wide detectors (R == 0: unavailable)
-    std::vector<CtrChunk> chunks, chunks_d;   // CTA columns of the two shapes
-    void* d_block = nullptr;   // one device allocation: [t | tinv | rays | chunks | chunks_d]
+    // forward kernel shapes: [0] 4 images per pixel record (any detector, any batch), [1] depth-first 8/16-image
+    // records, [2] 32-image records with 8 images per lane; [1] and [2] are column-windowed on wide detectors
+    // (fc.R == 0: shape unavailable for this geometry)
+    struct Shape {
+        ctr::FwdConfig fc;
+        std::vector<CtrChunk> chunks;   // CTA columns
+        CtrChunk* d_chunks = nullptr;
+    } shape[3];
+    void* d_block = nullptr;   // one device allocation: [t | tinv | rays | chunk tables]
     float* d_t = nullptr;
     float* d_tinv = nullptr;
     CtrRay* d_rays = nullptr;
-    CtrChunk* d_chunks = nullptr;
-    CtrChunk* d_chunks_d = nullptr;
 };
 
 struct ctr_fbp_plan {
@@ -219,39 +222,43 @@ int ctr_plan_create(const double* theta, int A, int X, int Y, int pad, int devic
     int smem_optin = 0;
     cudaError_t e = cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if (e != cudaSuccess) { int rc = fail_cuda(e, "cudaDeviceGetAttribute"); delete p; return rc; }
-    p->fc = ctr::fwd_config(p->W, p->geom, smem_optin - 2048);
-    p->fcd = ctr::fwd_config_depth(p->W, p->geom, smem_optin - 2048);
-    if (p->fc.R < 1) { delete p; return fail(CTR_EUNSUPPORTED, "ctr_plan_create: image rows too wide for the shared-memory strips"); }
+    p->shape[0].fc = ctr::fwd_config(p->W, p->geom, smem_optin - 2048);
+    p->shape[1].fc = ctr::fwd_config_depth(p->W, p->geom, smem_optin - 2048, false);
+    p->shape[2].fc = ctr::fwd_use_rec32() ? ctr::fwd_config_depth(p->W, p->geom, smem_optin - 2048, true) : ctr::FwdConfig{};
+    if (p->shape[0].fc.R < 1) { delete p; return fail(CTR_EUNSUPPORTED, "ctr_plan_create: image rows too wide for the shared-memory strips"); }
     // CTA columns: chunks of consecutive table entries, strip height and (wide detectors) column windows
-    size_t strip_bytes = 0;
-    ctr_h_build_chunks(p->rays, seg, p->geom, p->fc.angles_per_cta(), p->W, p->fc.JW, p->fc.jchunks, ctr::kFwdNB * 4,
-                       p->fc.stages, 0, false, p->fc.R, 1, p->fc.R, p->chunks, strip_bytes);
-    if (p->fcd.windowed) {
-        const int NA = p->fcd.angles_per_cta(), fixed = ctr::FwdConfig::fixed_bytes(NA);
-        const size_t budget = (size_t)(smem_optin - 2048 - fixed);
-        int rmax = 16;
-        if (const char* e = getenv("CTR_FWD_R")) { int v = atoi(e); if (v >= 2 && v <= 31) rmax = v; }
-        if (ctr_h_build_chunks(p->rays, seg, p->geom, NA, p->W, p->fcd.JW, p->fcd.jchunks, ctr::kFwdNB * p->fcd.depth * 4,
-                               p->fcd.stages, budget, true, 0, 4, rmax, p->chunks_d, strip_bytes)) {
-            p->fcd.R = 1;   // available; the strip height is per chunk
-            p->fcd.smem = (size_t)fixed + (size_t)p->fcd.stages * strip_bytes;
-        } else {
-            p->fcd.R = 0;   // some CTA's rays are too far apart for a window that fits: whole-row shape only
-            p->chunks_d.clear();
+    for (auto& sh : p->shape) {
+        ctr::FwdConfig& fc = sh.fc;
+        size_t strip_bytes = 0;
+        const int NA = fc.angles_per_cta(), rec_bytes = ctr::kFwdNB * fc.depth * 4;
+        if (fc.windowed) {
+            const int fixed = ctr::FwdConfig::fixed_bytes(NA);
+            const size_t budget = (size_t)(smem_optin - 2048 - fixed);
+            int rmax = 16;
+            if (const char* e = getenv("CTR_FWD_R")) { int v = atoi(e); if (v >= 2 && v <= 31) rmax = v; }
+            if (ctr_h_build_chunks(p->rays, seg, p->geom, NA, p->W, fc.JW, fc.jchunks, rec_bytes, fc.stages, budget, true, 0, 4,
+                                   rmax, sh.chunks, strip_bytes)) {
+                fc.R = 1;   // available; the strip height is per chunk
+                fc.smem = (size_t)fixed + (size_t)fc.stages * strip_bytes;
+            } else {
+                fc.R = 0;   // some CTA's rays are too far apart for a window that fits
+                sh.chunks.clear();
+            }
+        } else if (fc.R >= 1) {
+            ctr_h_build_chunks(p->rays, seg, p->geom, NA, p->W, fc.JW, fc.jchunks, rec_bytes, fc.stages, 0, false, fc.R, 1, fc.R,
+                               sh.chunks, strip_bytes);
         }
-    } else if (p->fcd.R >= 1) {
-        ctr_h_build_chunks(p->rays, seg, p->geom, p->fcd.angles_per_cta(), p->W, p->fcd.JW, p->fcd.jchunks,
-                           ctr::kFwdNB * p->fcd.depth * 4, p->fcd.stages, 0, false, p->fcd.R, 1, p->fcd.R, p->chunks_d, strip_bytes);
     }
     // one allocation + one upload for all tables (plans are created per angle minibatch in training)
     const size_t tb = (size_t)A * 8 * sizeof(float), rb = (size_t)A * sizeof(CtrRay);
-    const size_t cb = p->chunks.size() * sizeof(CtrChunk), cdb = p->chunks_d.size() * sizeof(CtrChunk);
-    std::vector<unsigned char> host(2 * tb + rb + cb + cdb);
+    size_t cb[3], ctot = 0;
+    for (int k = 0; k < 3; ++k) { cb[k] = p->shape[k].chunks.size() * sizeof(CtrChunk); ctot += cb[k]; }
+    std::vector<unsigned char> host(2 * tb + rb + ctot);
     std::memcpy(host.data(), p->t.data(), tb);
     std::memcpy(host.data() + tb, p->tinv.data(), tb);
     std::memcpy(host.data() + 2 * tb, p->rays.data(), rb);
-    std::memcpy(host.data() + 2 * tb + rb, p->chunks.data(), cb);
-    if (cdb) std::memcpy(host.data() + 2 * tb + rb + cb, p->chunks_d.data(), cdb);
+    for (size_t k = 0, off = 2 * tb + rb; k < 3; off += cb[k], ++k)
+        if (cb[k]) std::memcpy(host.data() + off, p->shape[k].chunks.data(), cb[k]);
     if ((e = cudaMalloc(&p->d_block, host.size())) != cudaSuccess ||
         (e = cudaMemcpy(p->d_block, host.data(), host.size(), cudaMemcpyHostToDevice)) != cudaSuccess) {
         int rc = fail_cuda(e, "ctr_plan_create: table upload");
@@ -262,8 +269,7 @@ int ctr_plan_create(const double* theta, int A, int X, int Y, int pad, int devic
     p->d_t = (float*)p->d_block;
     p->d_tinv = (float*)((char*)p->d_block + tb);
     p->d_rays = (CtrRay*)((char*)p->d_block + 2 * tb);
-    p->d_chunks = (CtrChunk*)((char*)p->d_block + 2 * tb + rb);
-    p->d_chunks_d = (CtrChunk*)((char*)p->d_block + 2 * tb + rb + cb);
+    for (size_t k = 0, off = 2 * tb + rb; k < 3; off += cb[k], ++k) p->shape[k].d_chunks = (CtrChunk*)((char*)p->d_block + off);
     *out = p;
     return CTR_OK;
 }
@@ -298,13 +304,18 @@ int ctr_plan_tables(const ctr_plan* p, float* fwd, float* inv)
     return CTR_OK;
 }
 
-// which forward shape serves a batch of B: depth-first when the detector allows it and the
-// batch fills at least most of a 16-image record
-static const ctr::FwdConfig& fwd_cfg_for(const ctr_plan* p, int B)
+// which forward shape serves a batch of B: the deepest pixel record the batch fills reasonably
+// (32 images from 17 up, 8/16 from 3 lanes' worth up), else the 4-image records
+static const ctr_plan::Shape& shape_for(const ctr_plan* p, int B)
 {
     static const bool no_depth = getenv("CTR_FWD_NODEPTH") != nullptr;   // developer switch for A/B timing
-    return (!no_depth && p->fcd.R >= 1 && B >= 3 * p->fcd.depth) ? p->fcd : p->fc;
+    if (!no_depth) {
+        if (p->shape[2].fc.R >= 1 && B > 16) return p->shape[2];
+        if (p->shape[1].fc.R >= 1 && B >= 3 * p->shape[1].fc.depth) return p->shape[1];
+    }
+    return p->shape[0];
 }
+static const ctr::FwdConfig& fwd_cfg_for(const ctr_plan* p, int B) { return shape_for(p, B).fc; }
 
 static size_t pack_bytes(const ctr_plan* p, int B)
 {
@@ -319,7 +330,7 @@ int ctr_plan_describe(const ctr_plan* p, int B, char* buf, size_t n)
 {
     if (!p || !buf || n == 0 || B <= 0) return fail(CTR_EINVAL, "ctr_plan_describe: bad argument");
     const ctr::FwdConfig& fc = fwd_cfg_for(p, B);
-    const std::vector<CtrChunk>& ch = (&fc == &p->fcd) ? p->chunks_d : p->chunks;
+    const std::vector<CtrChunk>& ch = shape_for(p, B).chunks;
     int rlo = 1 << 30, rhi = 0, wlo = 1 << 30, whi = 0, nwin = 0;
     for (const CtrChunk& c : ch) {
         rlo = std::min(rlo, c.R); rhi = std::max(rhi, c.R);
@@ -364,7 +375,7 @@ struct LoglikArgs {
 static size_t loglik_partial_bytes(const ctr_plan* p, int B)
 {
     const ctr::FwdConfig& fc = fwd_cfg_for(p, B);
-    const size_t chunks = (&fc == &p->fcd) ? p->chunks_d.size() : p->chunks.size();
+    const size_t chunks = shape_for(p, B).chunks.size();
     const size_t rec = (size_t)ctr::kFwdNB * fc.depth;
     const size_t G = ((size_t)B + rec - 1) / rec;
     return align_up(chunks * fc.jchunks * G * rec * sizeof(float), 256);
@@ -399,14 +410,13 @@ static int forward_impl(const ctr_plan* p, const float* img, float* out, int B, 
     fp.pk[0] = pk0; fp.pk[1] = pk1;
     fp.geom[0] = p->geom[0]; fp.geom[1] = p->geom[1];
     fp.rays = p->d_rays;
-    const bool deep = (&fc == &p->fcd);
-    fp.chunks = deep ? p->d_chunks_d : p->d_chunks;
+    fp.chunks = shape_for(p, B).d_chunks;
     fp.kbins = fc.kbins;
-    fp.jwd = fc.JW * fc.depth;
+    fp.jwd = fc.JW * fc.lanes;
     fp.ns = fc.NS;
     fp.stages = fc.stages;
     fp.isync = fc.isync;
-    const int chunks = (int)(deep ? p->chunks_d.size() : p->chunks.size());
+    const int chunks = (int)shape_for(p, B).chunks.size();
     fp.H = p->H; fp.W = p->W; fp.A = p->A; fp.B = B;
     fp.sino = out;
     fp.mask = nullptr; fp.meas = nullptr; fp.amap = nullptr; fp.A_all = p->A; fp.pnm = 1.f; fp.sqrt_reg = 0.f; fp.partial = nullptr;

@@ -124,6 +124,17 @@ CTR_HD void ctr_ldv(const float* __restrict__ p, float* __restrict__ out)
 #endif
 }
 
+// Eight images of one lane out of a 32-image (128-byte) pixel record, as two 16-byte loads in an order
+// that depends on the ray's parity (swz = 0 or 4 floats): in the same instruction the four lanes of an
+// even ray read chunks 0,2,4,6 of their record and those of an odd ray chunks 1,3,5,7, so the eight
+// lanes of a quarter-warp always hit eight different bank groups -- conflict-free wherever the two
+// rays' pixels are.  out[0..3] holds images (swz..swz+3) of the lane's block, out[4..7] the other half.
+CTR_HD void ctr_ldv8_swz(const float* __restrict__ p, int swz, float* __restrict__ out)
+{
+    ctr_ldv<4>(p + swz, out);
+    ctr_ldv<4>(p + (swz ^ 4), out + 4);
+}
+
 // Sinogram windows are staged as NB/4 planes of [bin][4 images] (pstride floats apart):
 // with 16-byte bins, lanes that read consecutive bins hit consecutive bank groups.
 template <int NB>
@@ -277,20 +288,27 @@ CTR_HD void ctr_sample(const CtrRay& r, float pu, float pv, float fi, int Up, in
     o.off = (kvi - rbase) * Up + (kui - offu);
 }
 
+template <int NB>
+CTR_HD void ctr_ld_rec(const float* __restrict__ p, int swz, float* __restrict__ out)
+{
+    if (NB == 8) ctr_ldv8_swz(p, swz, out);
+    else ctr_ldv<NB>(p, out);
+}
+
 template <int NB, int INTERP, int REC>
-CTR_HD void ctr_gather(const float* __restrict__ strip, int Up, const CtrSample<INTERP>& o, float* __restrict__ acc)
+CTR_HD void ctr_gather(const float* __restrict__ strip, int Up, const CtrSample<INTERP>& o, float* __restrict__ acc, int swz = 0)
 {
     const float* p0 = strip + o.off * REC;
     if (INTERP == CTR_NEAREST) {
         float a[NB];
-        ctr_ldv<NB>(p0, a);
+        ctr_ld_rec<NB>(p0, swz, a);
 #pragma unroll
         for (int q = 0; q < NB; ++q) acc[q] += a[q];
     } else {
         const float* p1 = p0 + Up * REC;
         float a00[NB], a01[NB], a10[NB], a11[NB];
-        ctr_ldv<NB>(p0, a00); ctr_ldv<NB>(p0 + REC, a01);
-        ctr_ldv<NB>(p1, a10); ctr_ldv<NB>(p1 + REC, a11);
+        ctr_ld_rec<NB>(p0, swz, a00); ctr_ld_rec<NB>(p0 + REC, swz, a01);
+        ctr_ld_rec<NB>(p1, swz, a10); ctr_ld_rec<NB>(p1 + REC, swz, a11);
 #pragma unroll
         for (int q = 0; q < NB; ++q)
             acc[q] = fmaf(o.w11, a11[q], fmaf(o.w10, a10[q], fmaf(o.w01, a01[q], fmaf(o.w00, a00[q], acc[q]))));
@@ -303,13 +321,13 @@ CTR_HD void ctr_gather(const float* __restrict__ strip, int Up, const CtrSample<
 // the shared-memory and issue pipes, not by latency.)
 template <int NB, int INTERP, int REC = NB>
 CTR_HD void ctr_march(const float* __restrict__ strip, int Up, float vend, int rbase, int offu,
-                      const CtrRay& r, CtrRayState& s, float* __restrict__ acc)
+                      const CtrRay& r, CtrRayState& s, float* __restrict__ acc, int swz = 0)
 {
     while (s.n > 0) {
         CtrSample<INTERP> a;
         ctr_sample<INTERP>(r, s.pu, s.pv, s.fi, Up, rbase, offu, a);
         if (a.kvf >= vend) break;
-        ctr_gather<NB, INTERP, REC>(strip, Up, a, acc);
+        ctr_gather<NB, INTERP, REC>(strip, Up, a, acc, swz);
         s.fi += s.dfi;
         --s.n;
     }

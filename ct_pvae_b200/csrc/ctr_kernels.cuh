@@ -237,6 +237,9 @@ __global__ void __launch_bounds__(kFwdMaxThreads, 1) ctr_fwd_kernel(const FwdPar
     const bool producer = tid >= nconsumers;                 // last warp: drives the TMA strip pipeline
     const int ty = producer ? 0 : tid / JWD;
     const int tx = (tid - ty * JWD) / DEPTH, gsub = (tid - ty * JWD) % DEPTH;
+    // 8 images per lane (32-image records): the two 16-byte halves of a lane's block are read in an order
+    // that alternates with the ray's parity, which makes every quarter-warp load conflict-free (ctr_ldv8_swz)
+    const int swz = (NB == 8) ? (tx & 1) * 4 : 0;
     // kbins: thread (tx,ty) owns bins tx, tx+JW, .. of angle slot ty (opt-in experiment, see fwd_use_kbins)
     const bool kb = p.kbins != 0;
     const int NA = kb ? NS : NS * KA;
@@ -356,7 +359,7 @@ __global__ void __launch_bounds__(kFwdMaxThreads, 1) ctr_fwd_kernel(const FwdPar
                     s.n = rn[q];
                     s.dfi = (r.v1 >= 0.f) ? 1.f : -1.f;
                     if (isync) ctr_march_isync<NB, INTERP, REC>(strip, Us, vend, rbase, offu, r, s, acc[q]);
-                    else ctr_march<NB, INTERP, REC>(strip, Us, vend, rbase, offu, r, s, acc[q]);
+                    else ctr_march<NB, INTERP, REC>(strip, Us, vend, rbase, offu, r, s, acc[q], swz);
                     ri[q] = s.fi;
                     rn[q] = s.n;
                 }
@@ -377,7 +380,7 @@ __global__ void __launch_bounds__(kFwdMaxThreads, 1) ctr_fwd_kernel(const FwdPar
                 const int ao = (EPI && p.amap) ? p.amap[a] : a;
 #pragma unroll
                 for (int n = 0; n < NB; ++n) {
-                    const int b = (g * DEPTH + gsub) * NB + n;
+                    const int b = (g * DEPTH + gsub) * NB + (n ^ swz);   // register n holds image n ^ swz of the lane's block
                     if (b < p.B) {
                         float outv = acc[q][n];
                         if (EPI) {
@@ -392,6 +395,10 @@ __global__ void __launch_bounds__(kFwdMaxThreads, 1) ctr_fwd_kernel(const FwdPar
             }
         }
         if (EPI) {
+            if (NB == 8 && swz) {   // back to image order before lanes of different parity are combined
+#pragma unroll
+                for (int n = 0; n < 4; ++n) { const float t = lsum[n]; lsum[n] = lsum[n + 4]; lsum[n + 4] = t; }
+            }
             // warp-level part of the deterministic log-likelihood reduction (lanes of equal gsub)
 #pragma unroll
             for (int n = 0; n < NB; ++n) {
@@ -617,6 +624,7 @@ __global__ void __launch_bounds__(256) ctr_fbp_filter_kernel(const float* __rest
 // ------------------------------------------------------------------------------------------ launchers
 struct FwdConfig {
     int JW, NS, KA, R, jchunks, depth, kbins, stages, isync;
+    int lanes;      // lanes per ray (each owns 4 * depth / lanes images of the pixel record)
     int windowed;   // 1: column-windowed strips, per-chunk R and window (R and smem are filled in by ctr_plan_create)
     size_t smem;
     static constexpr int fixed_bytes(int NA) { return 128 + (NA * (int)sizeof(CtrRay) + 127) / 128 * 128; }
@@ -640,12 +648,13 @@ inline bool fwd_use_kbins()
 
 // Shape the forward CTA: JW detector bins x NS angle slots x KA angles per slot, and the
 // largest strip height R whose double buffer fits the shared-memory budget.
-inline FwdConfig fwd_config_depth(int W, const CtrClassGeom geom[2], int smem_budget);
+inline FwdConfig fwd_config_depth(int W, const CtrClassGeom geom[2], int smem_budget, bool rec32);
 
 inline FwdConfig fwd_config(int W, const CtrClassGeom geom[2], int smem_budget)
 {
     FwdConfig c{};
     c.depth = 1;
+    c.lanes = 1;
     c.kbins = fwd_use_kbins() ? 1 : 0;
     // r1 measurement: the i-synchronous march loses (C4 slice 3.95 vs 2.50 ms, nearest 3.81 vs 1.49):
     // the sit-out trips and the vote per trip cost more issue slots than the conflicts they remove.
@@ -692,47 +701,59 @@ inline FwdConfig fwd_config(int W, const CtrClassGeom geom[2], int smem_budget)
 // (16 images, two angles per thread) for detectors of <= 184 bins, DEPTH = 2 (8 images) up to 368 bins; DEPTH = 8 (32 images, conflict-free, four angles per
 // thread, detector split into chunks of <= 128 bins) is selectable for experiments.
 constexpr int kFwdDepth = 4;
-inline FwdConfig fwd_config_depth(int W, const CtrClassGeom geom[2], int smem_budget)
+// 32-image records, 8 images per lane with parity-swizzled loads (conflict-free quarter-warps): default
+// where four lanes per ray fit; CTR_FWD_REC32=0 keeps the 16-image records (4 images per lane)
+inline bool fwd_use_rec32()
+{
+    const char* e = getenv("CTR_FWD_REC32");
+    return e ? atoi(e) != 0 : true;
+}
+
+inline FwdConfig fwd_config_depth(int W, const CtrClassGeom geom[2], int smem_budget, bool rec32)
 {
     FwdConfig c{};
-    // 16 images per record while 4 lanes per bin fit the CTA (P <= 184), else 8 images (P <= 368)
-    c.depth = (round_up(W, 8) * kFwdDepth <= kFwdMaxConsumers) ? kFwdDepth : 2;
+    // four lanes per ray while they fit the CTA (P <= 184), else two (P <= 368)
+    c.lanes = (round_up(W, 8) * kFwdDepth <= kFwdMaxConsumers) ? kFwdDepth : 2;
     c.stages = 2;
-    if (const char* e = getenv("CTR_FWD_DEPTH")) { int v = atoi(e); if (v == 2 || v == 4 || v == 8) c.depth = v; }
+    if (const char* e = getenv("CTR_FWD_DEPTH")) { int v = atoi(e); if (v == 2 || v == 4) c.lanes = v; }
+    c.depth = c.lanes;                                   // 4 images per lane ...
+    if (rec32) {                                         // ... or 8 (32-image records), four lanes per ray only
+        if (c.lanes != 4 && round_up(W, 8) * c.lanes <= kFwdMaxConsumers) return c;   // R = 0: mid-size detectors keep 8-image records
+        c.lanes = 4;
+        c.depth = 8;
+    }
     c.kbins = (fwd_use_kbins() && c.depth == 4) ? 1 : 0;
     c.NS = 1;
-    c.KA = (c.depth == 8) ? 4 : 2;
+    c.KA = 2;
     c.R = 0;
     c.smem = 0;
     c.jchunks = 1;
-    if (c.depth == 8) {
-        c.JW = round_up(W, 8);
-        if (c.JW > 96) { c.jchunks = (W + 95) / 96; c.JW = round_up((W + c.jchunks - 1) / c.jchunks, 8); }
-    } else if (c.kbins) {
+    if (c.kbins) {
         c.JW = round_up((W + 1) / 2, 8);      // bins tx and tx + JW of one angle per thread, two angle slots
         c.NS = 2;
-        if (c.JW * c.depth * c.NS > kFwdMaxConsumers) return c;   // R = 0: not available for this detector width
+        if (c.JW * c.lanes * c.NS > kFwdMaxConsumers) return c;   // R = 0: not available for this detector width
     } else {
-        c.JW = round_up(W, 32 / c.depth);
-        if (c.JW * c.depth > kFwdMaxConsumers) {
-            if (c.depth == 2 && getenv("CTR_FWD_WIDE_DEPTH") != nullptr) {
+        c.JW = round_up(W, 32 / c.lanes);
+        if (c.JW * c.lanes > kFwdMaxConsumers) {
+            if (c.lanes == 2 && getenv("CTR_FWD_WIDE_DEPTH") != nullptr) {
                 // experiment: 8-image records on a wide detector, split in chunks of 368 bins that each
                 // stream the full-width strips, four angles per thread to pay for the re-reads
                 c.JW = kFwdMaxConsumers / 2;
                 c.jchunks = (W + c.JW - 1) / c.JW;
                 c.KA = 4;
             } else {
-                // wide detector: 16-image records with COLUMN-WINDOWED strips.  The detector is cut into chunks
+                // wide detector: 16/32-image records with COLUMN-WINDOWED strips.  The detector is cut into chunks
                 // of JW bins, NS angle slots share a CTA (neighbouring angles need nearly the same window), and
                 // every strip holds only the columns those rays cross.  R, the windows and the shared-memory
                 // size depend on the angles: ctr_plan_create fills them in (ctr_h_build_chunks).
                 if (getenv("CTR_FWD_NOWINDOW") != nullptr) return c;
-                c.depth = 4;
+                c.lanes = 4;
+                c.depth = rec32 ? 8 : 4;
                 c.NS = 2;
                 if (const char* e = getenv("CTR_FWD_WIN_NS")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) c.NS = v; }
                 c.KA = 2;
-                c.JW = kFwdMaxConsumers / (c.depth * c.NS) / 8 * 8;
-                if (const char* e = getenv("CTR_FWD_WIN_JW")) { int v = atoi(e); if (v >= 8 && v % 8 == 0 && v * c.depth * c.NS <= kFwdMaxConsumers) c.JW = v; }
+                c.JW = kFwdMaxConsumers / (c.lanes * c.NS) / 8 * 8;
+                if (const char* e = getenv("CTR_FWD_WIN_JW")) { int v = atoi(e); if (v >= 8 && v % 8 == 0 && v * c.lanes * c.NS <= kFwdMaxConsumers) c.JW = v; }
                 c.jchunks = (W + c.JW - 1) / c.JW;
                 c.JW = round_up((W + c.jchunks - 1) / c.jchunks, c.NS >= 4 ? 2 : 8 / c.NS);   // even out the detector chunks (whole warps per CTA)
                 c.stages = fwd_stages();
@@ -759,36 +780,23 @@ inline FwdConfig fwd_config_depth(int W, const CtrClassGeom geom[2], int smem_bu
 template <int INTERP, int EPI>
 inline cudaError_t launch_fwd_ka(const FwdParams& p, const FwdConfig& c, int G, int chunks, cudaStream_t st)
 {
-    dim3 grid(chunks, G, c.jchunks), block(c.JW * c.depth * c.NS + 32);   // + the producer warp
+    dim3 grid(chunks, G, c.jchunks), block(c.JW * c.lanes * c.NS + 32);   // + the producer warp
     cudaError_t e;
-    if (c.depth == 4) {   // G counts super-groups of kFwdNB * depth images here
-        e = cudaFuncSetAttribute(ctr_fwd_kernel<kFwdNB, 2, INTERP, EPI, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
-        if (e != cudaSuccess) return e;
-        ctr_fwd_kernel<kFwdNB, 2, INTERP, EPI, 4><<<grid, block, c.smem, st>>>(p);
-        launch_counter()++;
-        return cudaGetLastError();
+#define CTR_FWD_DEEP(NBL_, KA_, LANES_)                                                                                            \
+    {                                                                                                                              \
+        e = cudaFuncSetAttribute(ctr_fwd_kernel<NBL_, KA_, INTERP, EPI, LANES_>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                 (int)c.smem);                                                                                     \
+        if (e != cudaSuccess) return e;                                                                                            \
+        ctr_fwd_kernel<NBL_, KA_, INTERP, EPI, LANES_><<<grid, block, c.smem, st>>>(p);                                            \
+        launch_counter()++;                                                                                                        \
+        return cudaGetLastError();                                                                                                 \
     }
-    if (c.depth == 2 && c.KA == 4) {
-        e = cudaFuncSetAttribute(ctr_fwd_kernel<kFwdNB, 4, INTERP, EPI, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
-        if (e != cudaSuccess) return e;
-        ctr_fwd_kernel<kFwdNB, 4, INTERP, EPI, 2><<<grid, block, c.smem, st>>>(p);
-        launch_counter()++;
-        return cudaGetLastError();
-    }
-    if (c.depth == 2) {
-        e = cudaFuncSetAttribute(ctr_fwd_kernel<kFwdNB, 2, INTERP, EPI, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
-        if (e != cudaSuccess) return e;
-        ctr_fwd_kernel<kFwdNB, 2, INTERP, EPI, 2><<<grid, block, c.smem, st>>>(p);
-        launch_counter()++;
-        return cudaGetLastError();
-    }
-    if (c.depth == 8) {
-        e = cudaFuncSetAttribute(ctr_fwd_kernel<kFwdNB, 4, INTERP, EPI, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
-        if (e != cudaSuccess) return e;
-        ctr_fwd_kernel<kFwdNB, 4, INTERP, EPI, 8><<<grid, block, c.smem, st>>>(p);
-        launch_counter()++;
-        return cudaGetLastError();
-    }
+    // G counts super-groups of kFwdNB * depth images here
+    if (c.lanes == 4 && c.depth == 8) CTR_FWD_DEEP(8, 2, 4)         // 32-image records, 8 images per lane
+    if (c.lanes == 4) CTR_FWD_DEEP(kFwdNB, 2, 4)                    // 16-image records
+    if (c.lanes == 2 && c.KA == 4) CTR_FWD_DEEP(kFwdNB, 4, 2)
+    if (c.lanes == 2) CTR_FWD_DEEP(kFwdNB, 2, 2)
+#undef CTR_FWD_DEEP
 #define CTR_FWD_CASE(KA_)                                                                                                  \
     case KA_:                                                                                                              \
         e = cudaFuncSetAttribute(ctr_fwd_kernel<kFwdNB, KA_, INTERP, EPI, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, \

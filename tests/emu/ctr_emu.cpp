@@ -54,15 +54,16 @@ void pack_sino(const float* y, int B, int A, int W, std::vector<float>& spk)
             }
 }
 
-template <int INTERP, int DEPTH>
+// DEPTH = lanes per ray, NBL = images per lane (4, or 8 with the parity-swizzled loads of 32-image records)
+template <int INTERP, int DEPTH, int NBL = NB>
 void forward_impl(const float* img, int B, int X, int Y, int H, int W, int padx, int pady,
                   const float* t, int A, int R, float* sino)
 {
-    constexpr int REC = NB * DEPTH;
+    constexpr int REC = NBL * DEPTH;
     CtrClassGeom geom[2];
     ctr_h_class_geom(X, Y, padx, pady, geom);
     std::vector<float> pk[2];
-    pack_images<DEPTH>(img, B, X, Y, geom, pk[0], pk[1]);
+    pack_images<REC / NB>(img, B, X, Y, geom, pk[0], pk[1]);
     std::vector<CtrRay> rays;
     int n0 = 0;
     ctr_h_build_rays(t, A, rays, n0);
@@ -77,17 +78,18 @@ void forward_impl(const float* img, int B, int X, int Y, int H, int W, int padx,
               for (int gsub = 0; gsub < DEPTH; ++gsub) {   // the DEPTH lanes that share ray j
                 CtrRayState s;
                 ctr_ray_begin(r, cg, j, H, s);
-                float acc[NB] = {0, 0, 0, 0};
+                float acc[NBL] = {};
+                const int swz = (NBL == 8) ? (j & 1) * 4 : 0;
                 for (int k = 0; k < K; ++k) {
                     // the strip buffer the TMA bulk copy would have filled: rows [kR, kR+R+1)
                     const int rows = std::min(R + 1, cg.Vp - k * R);
                     std::vector<float> strip((size_t)(R + 1) * cg.Up * REC, -1e30f);  // poison what is not loaded
                     std::memcpy(strip.data(), pkg + (size_t)k * R * cg.Up * REC, sizeof(float) * rows * cg.Up * REC);
-                    ctr_march<NB, INTERP, REC>(strip.data() + gsub * NB, cg.Up, (float)((k + 1) * R + cg.offv),
-                                               k * R + cg.offv, cg.offu, r, s, acc);
+                    ctr_march<NBL, INTERP, REC>(strip.data() + gsub * NBL, cg.Up, (float)((k + 1) * R + cg.offv),
+                                                k * R + cg.offv, cg.offu, r, s, acc, swz);
                 }
-                for (int n = 0; n < NB; ++n) {
-                    const int b = (g * DEPTH + gsub) * NB + n;
+                for (int n = 0; n < NBL; ++n) {
+                    const int b = (g * DEPTH + gsub) * NBL + (n ^ swz);
                     if (b < B) sino[((size_t)b * A + r.angle) * W + j] = acc[n];
                 }
             }
@@ -99,15 +101,15 @@ void forward_impl(const float* img, int B, int X, int Y, int H, int W, int padx,
 // detector chunk of JW bins; per strip the producer warp places a window of wc columns from the CTA's line
 // families.  Everything outside the window is NaN here, so a sample that falls outside poisons its ray sum.
 // Returns the number of chunks that really got a window (wc > 0), or -1 if the shape does not fit `budget`.
-template <int INTERP, int DEPTH>
+template <int INTERP, int DEPTH, int NBL = NB>
 int forward_window_impl(const float* img, int B, int X, int Y, int H, int W, int padx, int pady, const float* t, int A,
                         int JW, int NA, int Rmax, int budget, float* sino)
 {
-    constexpr int REC = NB * DEPTH;
+    constexpr int REC = NBL * DEPTH;
     CtrClassGeom geom[2];
     ctr_h_class_geom(X, Y, padx, pady, geom);
     std::vector<float> pk[2];
-    pack_images<DEPTH>(img, B, X, Y, geom, pk[0], pk[1]);
+    pack_images<REC / NB>(img, B, X, Y, geom, pk[0], pk[1]);
     std::vector<CtrRay> rays;
     std::vector<int> seg;
     int n0 = 0;
@@ -154,16 +156,18 @@ int forward_window_impl(const float* img, int B, int X, int Y, int H, int W, int
                         for (int jj = 0; jj < nb; ++jj)
                             for (int gsub = 0; gsub < DEPTH; ++gsub) {
                                 CtrRayState s = st[(size_t)q * nb + jj];   // the DEPTH lanes of a ray march identically
-                                ctr_march<NB, INTERP, REC>(strip.data() + gsub * NB, Us, (float)((k + 1) * R + cg.offv),
-                                                           k * R + cg.offv, cg.offu + c0, rays[ch.first + q], s,
-                                                           &acc[((size_t)q * nb + jj) * REC + gsub * NB]);
+                                ctr_march<NBL, INTERP, REC>(strip.data() + gsub * NBL, Us, (float)((k + 1) * R + cg.offv),
+                                                            k * R + cg.offv, cg.offu + c0, rays[ch.first + q], s,
+                                                            &acc[((size_t)q * nb + jj) * REC + gsub * NBL],
+                                                            (NBL == 8) ? (jj & 1) * 4 : 0);
                                 if (gsub == DEPTH - 1) st[(size_t)q * nb + jj] = s;
                             }
                 }
                 for (int q = 0; q < ch.cnt; ++q)
                     for (int jj = 0; jj < nb; ++jj)
                         for (int n = 0; n < REC; ++n) {
-                            const int b = g * REC + n;
+                            // register n of lane n / NBL holds image n ^ swz of that lane's block
+                            const int b = g * REC + (n ^ ((NBL == 8) ? (jj & 1) * 4 : 0));
                             if (b < B) sino[((size_t)b * A + rays[ch.first + q].angle) * W + z * JW + jj] = acc[((size_t)q * nb + jj) * REC + n];
                         }
             }
@@ -321,6 +325,20 @@ void emu_forward_depth(const float* img, int B, int X, int Y, int H, int W, int 
 {
     if (interp == CTR_NEAREST) forward_impl<CTR_NEAREST, 4>(img, B, X, Y, H, W, padx, pady, t, A, R, sino);
     else forward_impl<CTR_BILINEAR, 4>(img, B, X, Y, H, W, padx, pady, t, A, R, sino);
+}
+
+// 32-image records, 8 images per lane with parity-swizzled loads (ctr_fwd_kernel<8, 2, ., ., 4>)
+void emu_forward_rec32(const float* img, int B, int X, int Y, int H, int W, int padx, int pady, const float* t, int A,
+                       int interp, int R, float* sino)
+{
+    if (interp == CTR_NEAREST) forward_impl<CTR_NEAREST, 4, 8>(img, B, X, Y, H, W, padx, pady, t, A, R, sino);
+    else forward_impl<CTR_BILINEAR, 4, 8>(img, B, X, Y, H, W, padx, pady, t, A, R, sino);
+}
+int emu_forward_window32(const float* img, int B, int X, int Y, int H, int W, int padx, int pady, const float* t, int A,
+                         int interp, int JW, int NA, int Rmax, int budget, float* sino)
+{
+    if (interp == CTR_NEAREST) return forward_window_impl<CTR_NEAREST, 4, 8>(img, B, X, Y, H, W, padx, pady, t, A, JW, NA, Rmax, budget, sino);
+    return forward_window_impl<CTR_BILINEAR, 4, 8>(img, B, X, Y, H, W, padx, pady, t, A, JW, NA, Rmax, budget, sino);
 }
 
 // column-windowed depth-first strips (16-image records)

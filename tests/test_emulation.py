@@ -48,6 +48,9 @@ def test_emulated_kernels_match_oracle(emu, orc, B, X, Y, A, pad, R, TW, TH, win
         assert rel_l2(s, orc.forward(img, th, pad, interp)) <= 1e-6
         sd = np.full((B, A, W), np.nan, np.float32)       # depth-first records (16 images per record)
         emu.emu_forward_depth(P(img), B, X, Y, H, W, padx, pady, P(t), A, interp, R, P(sd))
+        s32 = np.full_like(sd, np.nan)
+        emu.emu_forward_rec32(P(img), B, X, Y, H, W, padx, pady, P(t), A, interp, R, P(s32))
+        assert np.array_equal(s32, sd), "32-image records (swizzled 8-image lanes) differ from 16-image records"
         np.testing.assert_array_equal(sd, s)
         si = np.full((B, A, W), np.nan, np.float32)       # i-synchronous quarter-warps: same samples, same order per ray
         emu.emu_forward_isync(P(img), B, X, Y, H, W, padx, pady, P(t), A, interp, R, P(si))
@@ -95,6 +98,9 @@ def test_emulated_kernels_property(emu, orc, B, X, Y, pad, R, th, seed):
         assert np.abs(s - want).max() <= 2e-5 * max(1.0, np.abs(want).max())
         sd = np.full((B, A, W), np.nan, np.float32)
         emu.emu_forward_depth(P(img), B, X, Y, H, W, padx, pady, P(t), A, interp, R, P(sd))
+        s32 = np.full_like(sd, np.nan)
+        emu.emu_forward_rec32(P(img), B, X, Y, H, W, padx, pady, P(t), A, interp, R, P(s32))
+        assert np.array_equal(s32, sd), "32-image records (swizzled 8-image lanes) differ from 16-image records"
         np.testing.assert_array_equal(sd, s)
         si = np.full((B, A, W), np.nan, np.float32)
         emu.emu_forward_isync(P(img), B, X, Y, H, W, padx, pady, P(t), A, interp, R, P(si))
@@ -125,15 +131,17 @@ def test_emulated_windowed_forward_matches_oracle(emu, orc, B, X, Y, A, pad, JW,
     img = rng.random((B, X, Y), dtype=np.float32)
     H, W, padx, pady = orc.frame_of(X, Y, pad)
     t = orc.make_transforms(th, H, W)
-    emu.emu_forward_window.restype = ctypes.c_int
+    emu.emu_forward_window.restype = emu.emu_forward_window32.restype = ctypes.c_int
     for interp in (0, 1):
-        s = np.full((B, A, W), np.nan, np.float32)
-        nwin = emu.emu_forward_window(P(img), B, X, Y, H, W, padx, pady, P(t), A, interp, JW, NA, Rmax, budget, P(s))
-        assert nwin >= 0, "shape did not fit the budget / rays not covered"
-        if kind == "even":
-            assert nwin > 0, "no chunk was actually windowed: the case tests nothing"
-        assert not np.isnan(s).any(), "a sample fell outside its strip window"
-        assert rel_l2(s, orc.forward(img, th, pad, interp)) <= 1e-6
+        want = orc.forward(img, th, pad, interp)
+        for fn, bud in ((emu.emu_forward_window, budget), (emu.emu_forward_window32, 2 * budget)):
+            s = np.full((B, A, W), np.nan, np.float32)
+            nwin = fn(P(img), B, X, Y, H, W, padx, pady, P(t), A, interp, JW, NA, Rmax, bud, P(s))
+            assert nwin >= 0, "shape did not fit the budget / rays not covered"
+            if kind == "even":
+                assert nwin > 0, "no chunk was actually windowed: the case tests nothing"
+            assert not np.isnan(s).any(), "a sample fell outside its strip window"
+            assert rel_l2(s, want) <= 1e-6
 
 
 @settings(max_examples=25, deadline=None)

@@ -101,7 +101,8 @@ def test_windowed_forward_matches_oracle(cp, orc, B, X, Y, A, pad, kind):
     img = rng.random((B, X, Y), dtype=np.float32)
     desc = _lib.get_plan(np.asarray(th, np.float64), X, Y, pad, 0).describe(B)
     if kind == "even":
-        assert "images_per_record=16 windowed=1" in desc and "window_chunks=0/" not in desc, desc
+        assert ("images_per_record=32 windowed=1" if B > 16 else "images_per_record=16 windowed=1") in desc, desc
+        assert "window_chunks=0/" not in desc, desc
     for interp in INTERPS:
         got = cp.project_tf_fast(torch.from_numpy(img).cuda().unsqueeze(-1), th, pad=pad, dim=2, integrate_vae=True,
                                  interpolation=interp)[..., 0]

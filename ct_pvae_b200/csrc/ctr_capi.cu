@@ -227,26 +227,30 @@ int ctr_plan_create(const double* theta, int A, int X, int Y, int pad, int devic
     p->shape[2].fc = ctr::fwd_use_rec32() ? ctr::fwd_config_depth(p->W, p->geom, smem_optin - 2048, true) : ctr::FwdConfig{};
     if (p->shape[0].fc.R < 1) { delete p; return fail(CTR_EUNSUPPORTED, "ctr_plan_create: image rows too wide for the shared-memory strips"); }
     // CTA columns: chunks of consecutive table entries, strip height and (wide detectors) column windows
-    for (auto& sh : p->shape) {
+    for (int k = 0; k < 3; ++k) {
+        ctr_plan::Shape& sh = p->shape[k];
         ctr::FwdConfig& fc = sh.fc;
         size_t strip_bytes = 0;
-        const int NA = fc.angles_per_cta(), rec_bytes = ctr::kFwdNB * fc.depth * 4;
         if (fc.windowed) {
-            const int fixed = ctr::FwdConfig::fixed_bytes(NA);
-            const size_t budget = (size_t)(smem_optin - 2048 - fixed);
             int rmax = 16;
             if (const char* e = getenv("CTR_FWD_R")) { int v = atoi(e); if (v >= 2 && v <= 31) rmax = v; }
-            if (ctr_h_build_chunks(p->rays, seg, p->geom, NA, p->W, fc.JW, fc.jchunks, rec_bytes, fc.stages, budget, true, 0, 4,
-                                   rmax, sh.chunks, strip_bytes)) {
-                fc.R = 1;   // available; the strip height is per chunk
-                fc.smem = (size_t)fixed + (size_t)fc.stages * strip_bytes;
-            } else {
-                fc.R = 0;   // some CTA's rays are too far apart for a window that fits
+            // widely spaced angles (sparse-angle minibatches): retry with fewer angle slots per CTA
+            for (int ns = fc.NS; ns >= 1; ns /= 2) {
+                if (ns != fc.NS) fc = ctr::fwd_config_depth(p->W, p->geom, smem_optin - 2048, k == 2, ns);
+                const int NA = fc.angles_per_cta(), fixed = ctr::FwdConfig::fixed_bytes(NA);
+                const size_t budget = (size_t)(smem_optin - 2048 - fixed);
+                if (ctr_h_build_chunks(p->rays, seg, p->geom, NA, p->W, fc.JW, fc.jchunks, ctr::kFwdNB * fc.depth * 4, fc.stages,
+                                       budget, true, 0, 4, rmax, sh.chunks, strip_bytes)) {
+                    fc.R = 1;   // available; the strip height is per chunk
+                    fc.smem = (size_t)fixed + (size_t)fc.stages * strip_bytes;
+                    break;
+                }
+                fc.R = 0;       // some CTA's rays are too far apart for a window that fits
                 sh.chunks.clear();
             }
         } else if (fc.R >= 1) {
-            ctr_h_build_chunks(p->rays, seg, p->geom, NA, p->W, fc.JW, fc.jchunks, rec_bytes, fc.stages, 0, false, fc.R, 1, fc.R,
-                               sh.chunks, strip_bytes);
+            ctr_h_build_chunks(p->rays, seg, p->geom, fc.angles_per_cta(), p->W, fc.JW, fc.jchunks, ctr::kFwdNB * fc.depth * 4,
+                               fc.stages, 0, false, fc.R, 1, fc.R, sh.chunks, strip_bytes);
         }
     }
     // one allocation + one upload for all tables (plans are created per angle minibatch in training)

@@ -648,7 +648,7 @@ inline bool fwd_use_kbins()
 
 // Shape the forward CTA: JW detector bins x NS angle slots x KA angles per slot, and the
 // largest strip height R whose double buffer fits the shared-memory budget.
-inline FwdConfig fwd_config_depth(int W, const CtrClassGeom geom[2], int smem_budget, bool rec32);
+inline FwdConfig fwd_config_depth(int W, const CtrClassGeom geom[2], int smem_budget, bool rec32, int win_ns = 0);
 
 inline FwdConfig fwd_config(int W, const CtrClassGeom geom[2], int smem_budget)
 {
@@ -709,7 +709,9 @@ inline bool fwd_use_rec32()
     return e ? atoi(e) != 0 : true;
 }
 
-inline FwdConfig fwd_config_depth(int W, const CtrClassGeom geom[2], int smem_budget, bool rec32)
+// win_ns > 0 forces the number of angle slots of the column-windowed shape (the plan retries with fewer
+// slots when the angles sharing a CTA are too far apart for a window that fits)
+inline FwdConfig fwd_config_depth(int W, const CtrClassGeom geom[2], int smem_budget, bool rec32, int win_ns)
 {
     FwdConfig c{};
     // four lanes per ray while they fit the CTA (P <= 184), else two (P <= 368)
@@ -749,8 +751,9 @@ inline FwdConfig fwd_config_depth(int W, const CtrClassGeom geom[2], int smem_bu
                 if (getenv("CTR_FWD_NOWINDOW") != nullptr) return c;
                 c.lanes = 4;
                 c.depth = rec32 ? 8 : 4;
-                c.NS = 2;
+                c.NS = rec32 ? 4 : 2;   // r1 sweep at 64 x 512^2 x 720: 6.60 ms (NS 4) vs 6.80 (2) / 6.63 (8) with 32-image records
                 if (const char* e = getenv("CTR_FWD_WIN_NS")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) c.NS = v; }
+                if (win_ns > 0) c.NS = win_ns;
                 c.KA = 2;
                 c.JW = kFwdMaxConsumers / (c.lanes * c.NS) / 8 * 8;
                 if (const char* e = getenv("CTR_FWD_WIN_JW")) { int v = atoi(e); if (v >= 8 && v % 8 == 0 && v * c.lanes * c.NS <= kFwdMaxConsumers) c.JW = v; }

@@ -215,11 +215,13 @@ struct FwdParams {
     const int* amap;        // [A] plan angle -> column of mask/meas (the angles_i gather), or null = identity
     int A_all;
     float pnm, sqrt_reg;    // poisson_noise_multiplier, sqrt_reg
-    float* partial;         // [gridDim.z*gridDim.x][G*NB*DEPTH] per-CTA log-likelihood sums
+    float* partial;         // [jchunks*gridDim.x][G*NB*DEPTH] per-CTA log-likelihood sums
 };
 
 // One CTA = (angle chunk of NS*KA same-class angles) x (image group of NB) x (detector chunk of JW bins).
-// thread (tx, ty): detector bin j = blockIdx.z*JW + tx, angles ty*KA .. ty*KA+KA-1 of the chunk.
+// thread (tx, ty): detector bin j = blockIdx.y*JW + tx, angles ty*KA .. ty*KA+KA-1 of the chunk.
+// grid = (ray chunks, detector chunks, image super-groups): the super-group is the slowest index, so the CTAs in flight
+// at any time read the packs of one or two super-groups and the column windows are re-read from L2, not from HBM.
 // All threads walk the image group's strips in lock step; thread 0 drives the TMA double buffer.
 // DEPTH > 1 is the depth-first variant: DEPTH image groups share one pixel record and the
 // lanes of a quarter-warp are (8/DEPTH rays) x (DEPTH groups), so a quarter-warp's LDS.128
@@ -252,7 +254,7 @@ __global__ void __launch_bounds__(kFwdMaxThreads, 1) ctr_fwd_kernel(const FwdPar
 
     const CtrChunk ch = p.chunks[blockIdx.x];
     const int cls = ch.cls, first = ch.first, cnt = ch.cnt;
-    const int g = blockIdx.y;
+    const int g = blockIdx.z, jz = blockIdx.y;
     const CtrClassGeom geom = cls ? p.geom[1] : p.geom[0];  // static indices: stays in registers
     const int R = ch.R;
     // column-windowed strips (ch.wc > 0): a strip row holds ch.wc pixels starting at column cst[b]
@@ -292,7 +294,7 @@ __global__ void __launch_bounds__(kFwdMaxThreads, 1) ctr_fwd_kernel(const FwdPar
         } else {
             // windowed: the whole warp takes part, lane r copies packed row r of the strip (R + 1 <= 32).
             // The window start follows the CTA's rays: lane q < cnt holds the line family of ray q.
-            const float jlo = (float)(blockIdx.z * JW), jhi = (float)min(p.W - 1, (int)blockIdx.z * JW + JW - 1);
+            const float jlo = (float)(jz * JW), jhi = (float)min(p.W - 1, jz * JW + JW - 1);
             CtrWinCoef co{0.f, 0.f, 0.f};
             if (lane < cnt) co = ctr_win_coef(rays_s[lane]);
             const uint32_t row_bytes = (uint32_t)Us * REC * 4u;
@@ -319,7 +321,7 @@ __global__ void __launch_bounds__(kFwdMaxThreads, 1) ctr_fwd_kernel(const FwdPar
         }
     } else {
         // ---- consumers.  per-ray state: next step and steps left (coefficients are re-read per strip)
-        const int jb = kb ? blockIdx.z * (JW * KA) + tx : blockIdx.z * JW + tx;
+        const int jb = kb ? jz * (JW * KA) + tx : jz * JW + tx;
         const int jstep = kb ? JW : 0, lbase = kb ? ty : ty * KA, lstep = kb ? 0 : 1;
         float ri[KA];
         int rn[KA];
@@ -422,8 +424,8 @@ __global__ void __launch_bounds__(kFwdMaxThreads, 1) ctr_fwd_kernel(const FwdPar
             if (tid < REC) {   // tid = gsub * NB + n
                 float v = 0.f;
                 for (int w = 0; w < nwarps; ++w) v += red[w * REC + tid];
-                const size_t cta = (size_t)blockIdx.z * gridDim.x + blockIdx.x;
-                p.partial[cta * ((size_t)gridDim.y * REC) + (size_t)g * REC + tid] = v;
+                const size_t cta = (size_t)jz * gridDim.x + blockIdx.x;
+                p.partial[cta * ((size_t)gridDim.z * REC) + (size_t)g * REC + tid] = v;
             }
         }
     }
@@ -783,7 +785,7 @@ inline FwdConfig fwd_config_depth(int W, const CtrClassGeom geom[2], int smem_bu
 template <int INTERP, int EPI>
 inline cudaError_t launch_fwd_ka(const FwdParams& p, const FwdConfig& c, int G, int chunks, cudaStream_t st)
 {
-    dim3 grid(chunks, G, c.jchunks), block(c.JW * c.lanes * c.NS + 32);   // + the producer warp
+    dim3 grid(chunks, c.jchunks, G), block(c.JW * c.lanes * c.NS + 32);   // + the producer warp
     cudaError_t e;
 #define CTR_FWD_DEEP(NBL_, KA_, LANES_)                                                                                            \
     {                                                                                                                              \

@@ -268,9 +268,15 @@ def run_ours(args, wl):
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    json_fd = None
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
-            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: one JSON line only
+            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL writes its version banner to file descriptor 1 when the first communicator comes up (seen in the
+        # angle-sharded run): point fd 1 at stderr for the whole run and keep the real stdout for the ONE JSON line
+        sys.stdout.flush()
+        json_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
 
     B, X, A = wl["B"], wl["X"], wl["A"]
@@ -451,7 +457,11 @@ def run_ours(args, wl):
                 line["cpu_baseline"] = cpu_baseline(wl)
             except Exception as exc:  # the checker library is optional for the GPU numbers
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": f"failed: {exc}"}
-        print(json.dumps(line), flush=True)
+        if json_fd is None:
+            print(json.dumps(line), flush=True)
+        else:
+            sys.stdout.flush()
+            os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

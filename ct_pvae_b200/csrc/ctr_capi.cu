@@ -96,6 +96,7 @@ struct ctr_plan {
         std::vector<CtrChunk> chunks;   // CTA columns
         CtrChunk* d_chunks = nullptr;
     } shape[3];
+    int sm_count = 148;
     void* d_block = nullptr;   // one device allocation: [t | tinv | rays | chunk tables]
     float* d_t = nullptr;
     float* d_tinv = nullptr;
@@ -222,6 +223,7 @@ int ctr_plan_create(const double* theta, int A, int X, int Y, int pad, int devic
     int smem_optin = 0;
     cudaError_t e = cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if (e != cudaSuccess) { int rc = fail_cuda(e, "cudaDeviceGetAttribute"); delete p; return rc; }
+    if (cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || p->sm_count <= 0) p->sm_count = 148;
     p->shape[0].fc = ctr::fwd_config(p->W, p->geom, smem_optin - 2048);
     p->shape[1].fc = ctr::fwd_config_depth(p->W, p->geom, smem_optin - 2048, false);
     p->shape[2].fc = ctr::fwd_use_rec32() ? ctr::fwd_config_depth(p->W, p->geom, smem_optin - 2048, true) : ctr::FwdConfig{};
@@ -313,10 +315,23 @@ int ctr_plan_tables(const ctr_plan* p, float* fwd, float* inv)
 static const ctr_plan::Shape& shape_for(const ctr_plan* p, int B)
 {
     static const bool no_depth = getenv("CTR_FWD_NODEPTH") != nullptr;   // developer switch for A/B timing
-    if (!no_depth) {
-        if (p->shape[2].fc.R >= 1 && B > 16) return p->shape[2];
-        if (p->shape[1].fc.R >= 1 && B >= 3 * p->shape[1].fc.depth) return p->shape[1];
+    if (no_depth) return p->shape[0];
+    const ctr_plan::Shape& s16 = p->shape[1];
+    const ctr_plan::Shape& s32 = p->shape[2];
+    const bool ok16 = s16.fc.R >= 1 && B >= 3 * s16.fc.depth, ok32 = s32.fc.R >= 1 && B > 16;
+    if (ok16 && ok32 && s16.fc.lanes == 4 && !s16.fc.windowed) {
+        // Both run one CTA per SM; a 32-image CTA does twice the work of a 16-image one in 1.84x the time
+        // (r1: 93 vs 51 us per wave at 128^2 x 180).  Small batches (the chunks of the host pipeline) leave the last
+        // wave mostly empty, so count waves: 64 images -> 182 CTAs = 2 waves (32) vs 364 CTAs = 3 waves (16).
+        auto waves = [&](const ctr_plan::Shape& sh) {
+            const long long rec = ctr::kFwdNB * sh.fc.depth, G = (B + rec - 1) / rec;
+            const long long ctas = G * (long long)sh.chunks.size() * sh.fc.jchunks;
+            return (double)((ctas + p->sm_count - 1) / p->sm_count);
+        };
+        return (waves(s32) * 1.84 <= waves(s16)) ? s32 : s16;
     }
+    if (ok32) return s32;
+    if (ok16) return s16;
     return p->shape[0];
 }
 static const ctr::FwdConfig& fwd_cfg_for(const ctr_plan* p, int B) { return shape_for(p, B).fc; }

@@ -4,7 +4,10 @@ import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ct_pvae_b200 import _lib, ops
 import ct_pvae_b200 as cp
-for (B, X, A) in ((256, 128, 180), (64, 512, 720)):
+shapes = ((256, 128, 180), (64, 512, 720))
+if os.environ.get("TIME_ADJ_SHAPES"):
+    shapes = [tuple(int(v) for v in s.split("x")) for s in os.environ["TIME_ADJ_SHAPES"].split(",")]
+for (B, X, A) in shapes:
     th = np.linspace(0, np.pi, A, endpoint=False)
     plan = _lib.get_plan(th, X, X, True, 0)
     y = torch.rand((B, A, plan.W), device="cuda")

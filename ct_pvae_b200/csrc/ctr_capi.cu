@@ -319,7 +319,7 @@ static const ctr_plan::Shape& shape_for(const ctr_plan* p, int B)
     const ctr_plan::Shape& s16 = p->shape[1];
     const ctr_plan::Shape& s32 = p->shape[2];
     const bool ok16 = s16.fc.R >= 1 && B >= 3 * s16.fc.depth, ok32 = s32.fc.R >= 1 && B > 16;
-    if (ok16 && ok32 && s16.fc.lanes == 4 && !s16.fc.windowed) {
+    if (ok16 && ok32 && s16.fc.lanes == 4 && !s16.fc.windowed && !s32.fc.windowed) {
         // Both run one CTA per SM; a 32-image CTA does twice the work of a 16-image one in 1.84x the time
         // (r1: 93 vs 51 us per wave at 128^2 x 180).  Small batches (the chunks of the host pipeline) leave the last
         // wave mostly empty, so count waves: 64 images -> 182 CTAs = 2 waves (32) vs 364 CTAs = 3 waves (16).
@@ -435,6 +435,7 @@ static int forward_impl(const ctr_plan* p, const float* img, float* out, int B, 
     fp.ns = fc.NS;
     fp.stages = fc.stages;
     fp.isync = fc.isync;
+
     const int chunks = (int)shape_for(p, B).chunks.size();
     fp.H = p->H; fp.W = p->W; fp.A = p->A; fp.B = B;
     fp.sino = out;
@@ -503,7 +504,7 @@ int ctr_radon_adjoint_scaled(const ctr_plan* p, const float* dsino, float* dimg,
     DeviceGuard guard(p->device);
     if (!guard.ok) return fail_cuda(guard.err, "cudaSetDevice");
     cudaStream_t st = (cudaStream_t)stream;
-    const int NBb = ctr::bp_nb_for_batch(B, mode == CTR_ADJOINT_EXACT ? CTR_ADJ_EXACT : CTR_ADJ_TF);
+    const int NBb = ctr::bp_nb_for_batch(B, mode == CTR_ADJOINT_EXACT ? CTR_ADJ_EXACT : CTR_ADJ_TF, p->X, p->Y);
     const int G = (B + NBb - 1) / NBb;
     float* spk = (float*)ws;
     {
@@ -594,7 +595,7 @@ int ctr_fbp(const ctr_fbp_plan* p, const float* sino, int A, float* recon, int B
     DeviceGuard guard(p->device);
     if (!guard.ok) return fail_cuda(guard.err, "cudaSetDevice");
     cudaStream_t st = (cudaStream_t)stream;
-    const int NBb = ctr::bp_nb_for_batch(B, CTR_ADJ_FBP);
+    const int NBb = ctr::bp_nb_for_batch(B, CTR_ADJ_FBP, p->x_size, p->y_size);
     const int G = (B + NBb - 1) / NBb;
     float* spk = (float*)ws;
     {

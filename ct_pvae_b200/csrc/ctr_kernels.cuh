@@ -227,8 +227,12 @@ struct FwdParams {
 // lanes of a quarter-warp are (8/DEPTH rays) x (DEPTH groups), so a quarter-warp's LDS.128
 // touches 8/DEPTH records of DEPTH*16 contiguous bytes -- shared-memory bank conflicts drop
 // from ~1.7x (8 rays spaced 1/cos(theta) > 1 chunks apart) to ~1.2x at DEPTH = 4.
-template <int NB, int KA, int INTERP, int EPI, int DEPTH>
-__global__ void __launch_bounds__(kFwdMaxThreads, 1) ctr_fwd_kernel(const FwdParams p)
+// The vertical-reuse march keeps two register sets of records alive across loop trips: its CTAs are capped at
+// 640 threads so that ptxas may use 96 registers instead of 80 (no spills; 704 threads still get 80: registers
+// are granted per warp in blocks that make 88 x 22 warps overflow the file).
+constexpr int kFwdReuseThreads = 640;
+template <int NB, int KA, int INTERP, int EPI, int DEPTH, int REUSE = 0>
+__global__ void __launch_bounds__(REUSE ? kFwdReuseThreads : kFwdMaxThreads, 1) ctr_fwd_kernel(const FwdParams p)
 {
     constexpr int REC = NB * DEPTH;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -361,6 +365,7 @@ __global__ void __launch_bounds__(kFwdMaxThreads, 1) ctr_fwd_kernel(const FwdPar
                     s.n = rn[q];
                     s.dfi = (r.v1 >= 0.f) ? 1.f : -1.f;
                     if (isync) ctr_march_isync<NB, INTERP, REC>(strip, Us, vend, rbase, offu, r, s, acc[q]);
+                    else if (REUSE && NB == 8 && INTERP == CTR_BILINEAR) ctr_march_reuse<NB, REC>(strip, Us, vend, rbase, offu, r, s, acc[q], swz);
                     else ctr_march<NB, INTERP, REC>(strip, Us, vend, rbase, offu, r, s, acc[q], swz);
                     ri[q] = s.fi;
                     rn[q] = s.n;
@@ -627,6 +632,7 @@ __global__ void __launch_bounds__(256) ctr_fbp_filter_kernel(const float* __rest
 struct FwdConfig {
     int JW, NS, KA, R, jchunks, depth, kbins, stages, isync;
     int lanes;      // lanes per ray (each owns 4 * depth / lanes images of the pixel record)
+    int reuse;      // 1: bilinear march keeps the previous bottom row in registers (ctr_march_reuse; 8-image lanes)
     int windowed;   // 1: column-windowed strips, per-chunk R and window (R and smem are filled in by ctr_plan_create)
     size_t smem;
     static constexpr int fixed_bytes(int NA) { return 128 + (NA * (int)sizeof(CtrRay) + 127) / 128 * 128; }
@@ -738,7 +744,8 @@ inline FwdConfig fwd_config_depth(int W, const CtrClassGeom geom[2], int smem_bu
         if (c.JW * c.lanes * c.NS > kFwdMaxConsumers) return c;   // R = 0: not available for this detector width
     } else {
         c.JW = round_up(W, 32 / c.lanes);
-        if (c.JW * c.lanes > kFwdMaxConsumers) {
+        // CTR_FWD_FORCE_WINDOW: experiment, column-windowed shape also where whole rows fit (narrow detectors)
+        if (c.JW * c.lanes > kFwdMaxConsumers || (rec32 && getenv("CTR_FWD_FORCE_WINDOW") != nullptr)) {
             if (c.lanes == 2 && getenv("CTR_FWD_WIDE_DEPTH") != nullptr) {
                 // experiment: 8-image records on a wide detector, split in chunks of 368 bins that each
                 // stream the full-width strips, four angles per thread to pay for the re-reads
@@ -757,8 +764,12 @@ inline FwdConfig fwd_config_depth(int W, const CtrClassGeom geom[2], int smem_bu
                 if (const char* e = getenv("CTR_FWD_WIN_NS")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) c.NS = v; }
                 if (win_ns > 0) c.NS = win_ns;
                 c.KA = 2;
-                c.JW = kFwdMaxConsumers / (c.lanes * c.NS) / 8 * 8;
-                if (const char* e = getenv("CTR_FWD_WIN_JW")) { int v = atoi(e); if (v >= 8 && v % 8 == 0 && v * c.lanes * c.NS <= kFwdMaxConsumers) c.JW = v; }
+                // r1: the vertical-reuse march pays with the tall strips of the windowed shape (C4 6.57 -> 6.24 ms),
+                // not with the 5-row strips of whole-row 32-image records (C2 0.521 -> 0.532 ms)
+                c.reuse = (rec32 && getenv("CTR_FWD_NOREUSE") == nullptr) ? 1 : 0;
+                const int maxc = c.reuse ? kFwdReuseThreads - 32 : kFwdMaxConsumers;
+                { const int q = c.NS >= 4 ? 2 : 8 / c.NS; c.JW = maxc / (c.lanes * c.NS) / q * q; }   // whole warps per CTA
+                if (const char* e = getenv("CTR_FWD_WIN_JW")) { int v = atoi(e); if (v >= 8 && v % 8 == 0 && v * c.lanes * c.NS <= maxc) c.JW = v; }
                 c.jchunks = (W + c.JW - 1) / c.JW;
                 c.JW = round_up((W + c.jchunks - 1) / c.jchunks, c.NS >= 4 ? 2 : 8 / c.NS);   // even out the detector chunks (whole warps per CTA)
                 c.stages = fwd_stages();
@@ -767,6 +778,7 @@ inline FwdConfig fwd_config_depth(int W, const CtrClassGeom geom[2], int smem_bu
             }
         }
     }
+    c.reuse = (c.depth == 8 && getenv("CTR_FWD_REUSE") != nullptr) ? 1 : 0;   // opt-in experiment for whole-row strips
     const int fixed = 128 + round_up(c.NS * c.KA * (int)sizeof(CtrRay), 128);
     const int Upmax = geom[0].Up > geom[1].Up ? geom[0].Up : geom[1].Up;
     const int Vpmax = geom[0].Vp > geom[1].Vp ? geom[0].Vp : geom[1].Vp;
@@ -787,16 +799,17 @@ inline cudaError_t launch_fwd_ka(const FwdParams& p, const FwdConfig& c, int G, 
 {
     dim3 grid(chunks, c.jchunks, G), block(c.JW * c.lanes * c.NS + 32);   // + the producer warp
     cudaError_t e;
-#define CTR_FWD_DEEP(NBL_, KA_, LANES_)                                                                                            \
+#define CTR_FWD_DEEP(NBL_, KA_, LANES_, ...)                                                                                       \
     {                                                                                                                              \
-        e = cudaFuncSetAttribute(ctr_fwd_kernel<NBL_, KA_, INTERP, EPI, LANES_>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
-                                 (int)c.smem);                                                                                     \
+        e = cudaFuncSetAttribute(ctr_fwd_kernel<NBL_, KA_, INTERP, EPI, LANES_, ##__VA_ARGS__>,                                    \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);                                        \
         if (e != cudaSuccess) return e;                                                                                            \
-        ctr_fwd_kernel<NBL_, KA_, INTERP, EPI, LANES_><<<grid, block, c.smem, st>>>(p);                                            \
+        ctr_fwd_kernel<NBL_, KA_, INTERP, EPI, LANES_, ##__VA_ARGS__><<<grid, block, c.smem, st>>>(p);                             \
         launch_counter()++;                                                                                                        \
         return cudaGetLastError();                                                                                                 \
     }
     // G counts super-groups of kFwdNB * depth images here
+    if (c.lanes == 4 && c.depth == 8 && c.reuse && INTERP == CTR_BILINEAR) CTR_FWD_DEEP(8, 2, 4, 1)   // + vertical reuse
     if (c.lanes == 4 && c.depth == 8) CTR_FWD_DEEP(8, 2, 4)         // 32-image records, 8 images per lane
     if (c.lanes == 4) CTR_FWD_DEEP(kFwdNB, 2, 4)                    // 16-image records
     if (c.lanes == 2 && c.KA == 4) CTR_FWD_DEEP(kFwdNB, 4, 2)
@@ -830,12 +843,20 @@ inline size_t bp_smem_bytes(int win, int NB, int AB)
 // 32x8-pixel tiles), tiny ones 8 on 32x16 tiles (fewer idle accumulator lanes).
 // (r1: 32 images pay off only for the geometry-heavy exact adjoint -- C4 5.63 -> 4.64 ms;
 // the 2-tap TF-compat and FBP gathers lose occupancy and stay at 16.)
-inline int bp_nb_for_batch(int B, int mode)
+// X, Y: when the 32-image shape would not even give every SM one CTA (small images x small batch, e.g. the
+// 32..64-image chunks of the host pipeline at 128^2) the 16-image shape has twice the CTAs: 0.105 vs 0.141 ms
+// at 32 x 128^2 x 180.  Pass X = 0 for "size for the worst case" (workspace queries).
+inline int bp_nb_for_batch(int B, int mode, int X = 0, int Y = 0)
 {
     static const int forced = getenv("CTR_BP_NB") ? atoi(getenv("CTR_BP_NB")) : 0;   // developer override
     if (forced == 8 || forced == 16 || forced == 32) return forced;
     if (B <= 8) return 8;
-    return (mode == CTR_ADJ_EXACT && B >= 24) ? 32 : 16;
+    if (mode != CTR_ADJ_EXACT || B < 24) return 16;
+    if (X > 0 && Y > 0) {
+        const long long ctas32 = (long long)((Y + kBpTW - 1) / kBpTW) * ((X + 7) / 8) * ((B + 31) / 32);
+        if (ctas32 < 148) return 16;
+    }
+    return 32;
 }
 
 template <int NB, int TH, int MINB, int MODE, int INTERP>
@@ -856,7 +877,7 @@ inline cudaError_t launch_bp_cfg(BpParams p, cudaStream_t st)
 template <int MODE, int INTERP>
 inline cudaError_t launch_bp(const BpParams& p, cudaStream_t st)
 {
-    const int nb = bp_nb_for_batch(p.B, MODE);
+    const int nb = bp_nb_for_batch(p.B, MODE, p.X, p.Y);
     if (nb == 32) {
         static const bool small_tiles = getenv("CTR_BP_TH4") != nullptr;   // developer switch
         if (small_tiles) return launch_bp_cfg<32, 4, 4, MODE, INTERP>(p, st);

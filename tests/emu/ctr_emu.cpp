@@ -85,8 +85,12 @@ void forward_impl(const float* img, int B, int X, int Y, int H, int W, int padx,
                     const int rows = std::min(R + 1, cg.Vp - k * R);
                     std::vector<float> strip((size_t)(R + 1) * cg.Up * REC, -1e30f);  // poison what is not loaded
                     std::memcpy(strip.data(), pkg + (size_t)k * R * cg.Up * REC, sizeof(float) * rows * cg.Up * REC);
-                    ctr_march<NBL, INTERP, REC>(strip.data() + gsub * NBL, cg.Up, (float)((k + 1) * R + cg.offv),
-                                                k * R + cg.offv, cg.offu, r, s, acc, swz);
+                    if (NBL == 8 && INTERP == CTR_BILINEAR)   // the kernel's default march for 8-image lanes
+                        ctr_march_reuse<NBL, REC>(strip.data() + gsub * NBL, cg.Up, (float)((k + 1) * R + cg.offv),
+                                                  k * R + cg.offv, cg.offu, r, s, acc, swz);
+                    else
+                        ctr_march<NBL, INTERP, REC>(strip.data() + gsub * NBL, cg.Up, (float)((k + 1) * R + cg.offv),
+                                                    k * R + cg.offv, cg.offu, r, s, acc, swz);
                 }
                 for (int n = 0; n < NBL; ++n) {
                     const int b = (g * DEPTH + gsub) * NBL + (n ^ swz);
@@ -156,10 +160,15 @@ int forward_window_impl(const float* img, int B, int X, int Y, int H, int W, int
                         for (int jj = 0; jj < nb; ++jj)
                             for (int gsub = 0; gsub < DEPTH; ++gsub) {
                                 CtrRayState s = st[(size_t)q * nb + jj];   // the DEPTH lanes of a ray march identically
-                                ctr_march<NBL, INTERP, REC>(strip.data() + gsub * NBL, Us, (float)((k + 1) * R + cg.offv),
-                                                            k * R + cg.offv, cg.offu + c0, rays[ch.first + q], s,
-                                                            &acc[((size_t)q * nb + jj) * REC + gsub * NBL],
-                                                            (NBL == 8) ? (jj & 1) * 4 : 0);
+                                if (NBL == 8 && INTERP == CTR_BILINEAR)
+                                    ctr_march_reuse<NBL, REC>(strip.data() + gsub * NBL, Us, (float)((k + 1) * R + cg.offv),
+                                                              k * R + cg.offv, cg.offu + c0, rays[ch.first + q], s,
+                                                              &acc[((size_t)q * nb + jj) * REC + gsub * NBL], (jj & 1) * 4);
+                                else
+                                    ctr_march<NBL, INTERP, REC>(strip.data() + gsub * NBL, Us, (float)((k + 1) * R + cg.offv),
+                                                                k * R + cg.offv, cg.offu + c0, rays[ch.first + q], s,
+                                                                &acc[((size_t)q * nb + jj) * REC + gsub * NBL],
+                                                                (NBL == 8) ? (jj & 1) * 4 : 0);
                                 if (gsub == DEPTH - 1) st[(size_t)q * nb + jj] = s;
                             }
                 }

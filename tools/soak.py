@@ -10,10 +10,13 @@ n = int(os.environ.get("SOAK_ITERS", "300"))
 t0 = time.time()
 worst = 0.0
 for it in range(n):
-    B, X, Y, A = int(rng.integers(1, 70)), int(rng.integers(2, 220)), int(rng.integers(2, 220)), int(rng.integers(1, 48))
+    big = it % 4 == 3       # every fourth case: wide detector (column-windowed 16/32-image shapes)
+    hi = 420 if big else 220
+    B, X, Y, A = int(rng.integers(1, 70)), int(rng.integers(2, hi)), int(rng.integers(2, hi)), int(rng.integers(1, 48))
     pad = bool(rng.integers(0, 2))
     interp = ("nearest", "bilinear")[int(rng.integers(0, 2))]
-    th = rng.uniform(-4, 4, A)
+    # random angles (sparse: wide windows / fallbacks) or an evenly spaced fan with a random offset (real windows)
+    th = rng.uniform(-4, 4, A) if it % 2 else np.linspace(0, np.pi, A, endpoint=False) + rng.uniform(-1, 1)
     img = torch.rand((B, X, Y, 1), device="cuda")
     s1 = cp.project_tf_fast(img, th, pad=pad, dim=2, integrate_vae=True, interpolation=interp)
     s2 = cp.project_tf_fast(img, th, pad=pad, dim=2, integrate_vae=True, interpolation=interp)

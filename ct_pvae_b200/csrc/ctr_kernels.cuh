@@ -1,7 +1,7 @@
 // ctr_kernels.cuh -- sm_100a kernels of the Radon path and their launchers.
 //
 //   K0  ctr_pack_image_kernel   [B,X,Y] -> batch-interleaved, halo-padded packs (row-major + transposed),
-//                               4 or 16 images per pixel record
+//                               4, 8, 16 or 32 images per pixel record
 //   K0' ctr_pack_sino_kernel    [B,A,W] -> [G,A,NB/4,W+2,4] sinogram planes with zero halo bins
 //   K1  ctr_fwd_kernel          ray-driven forward projector (project_tf_fast / project_tf_low_mem,
 //                               /root/reference/ctvae/forward_functions.py:80-123, :49-78), optionally with
@@ -15,10 +15,13 @@
 // shared memory by the TMA engine with 1-D bulk copies (cp.async.bulk, SASS UBLKCP)
 // completing on mbarriers.  K1 runs a producer warp / consumer warps ring (full + empty
 // mbarriers per strip buffer, no CTA-wide barrier in the loop); K2/K3b double-buffer
-// batches of 8 angles.  The packs exist so that every staged block is ONE contiguous,
-// 16-byte aligned range in HBM and so that one 128-bit shared-memory load serves 4
-// images: the per-sample geometry (coordinates, floor, weights, address) is computed
-// once per 4 (K1) or 16-32 (K2) images.
+// batches of 8 angles.  The packs exist so that every staged block is a contiguous,
+// 16-byte aligned range in HBM (whole packed rows, or -- wide detectors -- the column
+// window of every row that the CTA's rays cross) and so that one 128-bit shared-memory
+// load serves 4 images: the per-sample geometry (coordinates, floor, weights, address)
+// is computed once per 4 or 8 (K1) or 16-32 (K2) images.  K1's big-batch shape reads
+// 32-image records with parity-swizzled 8-image lanes (conflict-free quarter-warps) and,
+// with tall windowed strips, keeps the previous sample's bottom row in registers.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

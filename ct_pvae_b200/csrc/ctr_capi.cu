@@ -637,7 +637,7 @@ int ctr_fbp(const ctr_fbp_plan* p, const float* sino, int A, float* recon, int B
 struct ctr_hostpipe {
     static constexpr int kSlots = 6;   // r1 trace: with 3 the next call's copy-in stalls on slots still queued for kernels
     const ctr_plan* plan = nullptr;
-    int device = 0, chunk = 0;
+    int device = 0, chunk = 0, adj_mult = 1;
     size_t buf_bytes = 0, ws_bytes = 0;
     cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
     struct Slot {
@@ -676,9 +676,14 @@ int ctr_hostpipe_create(const ctr_plan* plan, int chunk, ctr_hostpipe** out)
     ctr_hostpipe* hp = new (std::nothrow) ctr_hostpipe();
     if (!hp) return fail(CTR_EINVAL, "ctr_hostpipe_create: out of host memory");
     hp->plan = plan; hp->device = plan->device; hp->chunk = chunk;
-    const size_t img_b = (size_t)chunk * plan->X * plan->Y * sizeof(float), sino_b = (size_t)chunk * plan->A * plan->W * sizeof(float);
+    // experiment (CTR_HOST_ADJ_MULT): adjoint chunks of mult x chunk images (its kernels need bigger batches to fill the SMs)
+    hp->adj_mult = 1;
+    if (const char* e = getenv("CTR_HOST_ADJ_MULT")) { int v = atoi(e); if (v >= 1 && v <= 8) hp->adj_mult = v; }
+    const int cap = chunk * hp->adj_mult;
+    const size_t img_b = (size_t)cap * plan->X * plan->Y * sizeof(float), sino_b = (size_t)cap * plan->A * plan->W * sizeof(float);
     hp->buf_bytes = align_up(std::max(img_b, sino_b), 256);
-    hp->ws_bytes = std::max(ctr_forward_workspace_bytes(plan, chunk), ctr_adjoint_workspace_bytes(plan, chunk));
+    hp->ws_bytes = std::max(std::max(ctr_forward_workspace_bytes(plan, chunk), ctr_adjoint_workspace_bytes(plan, chunk)),
+                            std::max(ctr_forward_workspace_bytes(plan, cap), ctr_adjoint_workspace_bytes(plan, cap)));
     cudaError_t e = cudaSuccess;
     auto ok = [&](cudaError_t r) { if (e == cudaSuccess) e = r; return e == cudaSuccess; };
     ok(cudaStreamCreateWithFlags(&hp->s_in, cudaStreamNonBlocking));
@@ -718,8 +723,9 @@ static int hostpipe_run(ctr_hostpipe* hp, int kind, const float* in_host, float*
     std::lock_guard<std::mutex> lk(hp->mu);
     const size_t img_n = (size_t)p->X * p->Y, sino_n = (size_t)p->A * p->W;
     const size_t in_n = kind == 0 ? img_n : sino_n, out_n = kind == 0 ? sino_n : img_n;
-    for (int lo = 0; lo < B; lo += hp->chunk) {
-        const int n = std::min(hp->chunk, B - lo);
+    const int step = kind == 1 ? hp->chunk * hp->adj_mult : hp->chunk;
+    for (int lo = 0; lo < B; lo += step) {
+        const int n = std::min(step, B - lo);
         ctr_hostpipe::Slot& s = hp->slot[hp->seq % ctr_hostpipe::kSlots];
         const bool reused = hp->seq >= ctr_hostpipe::kSlots;
         if (reused) CTR_CUDA(cudaStreamWaitEvent(hp->s_in, s.comp_done, 0));     // staging input consumed

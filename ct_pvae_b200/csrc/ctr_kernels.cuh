@@ -108,16 +108,25 @@ __global__ void __launch_bounds__(256) ctr_pack_image_kernel(const float* __rest
     const int rec = NB * depth;
     const int pr0 = blockIdx.y * 32, pc0 = blockIdx.x * 32;
     const int tx = threadIdx.x, ty = threadIdx.y;
+    // all NB x 4 loads of a thread are issued before the first one is consumed (the kernel is latency-bound:
+    // r1 ncu, 18 long-scoreboard stalls per issue with the loads interleaved with the shared-memory stores)
+    float v[NB][4];
+    const int c = pc0 + tx - 1;
+    const bool cok = c >= 0 && c < Y;
 #pragma unroll
     for (int n = 0; n < NB; ++n) {
         const int b = g * NB + n;
-        for (int rr = ty; rr < 32; rr += 8) {
-            const int r = pr0 + rr - 1, c = pc0 + tx - 1;
-            float v = 0.f;
-            if (b < B && r >= 0 && r < X && c >= 0 && c < Y) v = __ldg(img + ((size_t)b * X + r) * Y + c);
-            tile[n][rr][tx] = v;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int r = pr0 + ty + 8 * k - 1;
+            const bool ok = cok && b < B && r >= 0 && r < X;
+            v[n][k] = ok ? __ldg(img + ((size_t)(ok ? b : 0) * X + (ok ? r : 0)) * Y + (ok ? c : 0)) : 0.f;
         }
     }
+#pragma unroll
+    for (int n = 0; n < NB; ++n)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tile[n][ty + 8 * k][tx] = v[n][k];
     __syncthreads();
     if (pk0) {
         for (int rr = ty; rr < 32; rr += 8) {

@@ -74,6 +74,15 @@ def test_errors_return_codes_not_aborts(L):
     assert L.ctr_radon_forward(None, None, None, 1, 0, None, 0, None) == -1
     assert L.ctr_plan_destroy(None) == 0
     assert L.ctr_profile_read(99, None, None) == -1
+    # host pipeline and diagnostics: NULL handles are errors, never crashes
+    hp = ctypes.c_void_p()
+    assert L.ctr_hostpipe_create(None, 64, ctypes.byref(hp)) == -1 and not hp.value
+    assert L.ctr_hostpipe_forward(None, None, None, 4, 1) == -1
+    assert L.ctr_hostpipe_adjoint(None, None, None, 4, 1, 0) == -1
+    assert L.ctr_hostpipe_wait(None) == -1 and L.ctr_hostpipe_done(None) == -1
+    assert L.ctr_hostpipe_destroy(None) == 0
+    buf = ctypes.create_string_buffer(64)
+    assert L.ctr_plan_describe(None, 4, buf, 64) == -1
 
 
 def test_no_gpu_means_loud_failure(L):

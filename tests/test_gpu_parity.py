@@ -292,11 +292,12 @@ def test_async_host_calls_overlap_and_match(cp, orc, chunk, monkeypatch):
 
 
 @pytest.mark.parametrize("interp", INTERPS)
-@pytest.mark.parametrize("gather", [False, True])
-def test_fused_loglik_matches_oracle(cp, orc, interp, gather):
+@pytest.mark.parametrize("gather,X", [(False, 32), (True, 32), (False, 150)])
+def test_fused_loglik_matches_oracle(cp, orc, interp, gather, X):
     """projector + mask + Normal log-prob + reduction in one pass, and its gradient."""
     rng = np.random.default_rng(9)
-    B, X, A_all = (18 if gather else 6), 32, 20     # 18: depth-first forward, 6: 4-image records
+    # 18 images: 32-image records (X = 150: P = 216, column-windowed strips + reuse march); 6: 4-image records
+    B, A_all = (18 if (gather or X > 100) else 6), 20
     th = _theta(A_all)
     angles_i = rng.permutation(A_all)[:7] if gather else None
     pnm, sreg = 1e4, float(np.finfo(np.float32).eps)

@@ -173,3 +173,31 @@ def test_edge_cases(orc):
     assert one.shape == (1, 4, orc.num_proj_pix(1, 1)) and np.all(np.abs(one.sum(axis=2) - 1) < 0.1) and one[0, 0, 1] == 1
     img = np.random.default_rng(6).random((1, 9, 9), dtype=np.float32)
     np.testing.assert_allclose(orc.forward(img, [0.4], True, 1), orc.forward(img, [0.4 + 2 * np.pi], True, 1), atol=2e-5)
+
+
+@pytest.mark.parametrize("mode,order,tol", [(1, 1, 2e-6), (0, 0, 2e-3)])
+def test_forward_matches_scipy_affine_transform(orc, mode, order, tol):
+    """Independent public implementation of the same operator: scipy.ndimage.affine_transform with the
+    tfa transform as (matrix, offset), zero fill, order 1 (bilinear) / 0 (nearest), then the row sum of
+    forward_functions.py:114.  float64 coordinates there, float32 here: bilinear agrees to rounding; nearest
+    may flip a sample that sits within ~1e-6 of a rounding boundary (none does for this seed: 3e-8)."""
+    import scipy.ndimage as ndi
+
+    rng = np.random.default_rng(3)
+    X, Y, A = 40, 33, 9
+    img = rng.random((2, X, Y), dtype=np.float32)
+    th = np.linspace(0, np.pi, A, endpoint=False) + 0.1
+    H, W, padx, pady = orc.frame_of(X, Y, True)
+    t = orc.make_transforms(th, H, W).astype(np.float64)
+    want = orc.forward(img, th, True, mode)
+    got = np.zeros(want.shape)
+    for b in range(img.shape[0]):
+        padded = np.zeros((H, W))
+        padded[padx:padx + X, pady:pady + Y] = img[b]
+        for a in range(A):
+            c, ms, xo, s, c2, yo = t[a, :6]
+            # output (row, col) -> input (row, col): y_in = s*x + c*y + y_off ; x_in = c*x - s*y + x_off
+            rot = ndi.affine_transform(padded, np.array([[c2, s], [ms, c]]), offset=np.array([yo, xo]), order=order,
+                                       mode="constant", cval=0.0, output_shape=(H, W))
+            got[b, a] = rot.sum(axis=0)
+    assert np.linalg.norm(got - want) / np.linalg.norm(want) <= tol

@@ -201,3 +201,28 @@ def test_forward_matches_scipy_affine_transform(orc, mode, order, tol):
                                        mode="constant", cval=0.0, output_shape=(H, W))
             got[b, a] = rot.sum(axis=0)
     assert np.linalg.norm(got - want) / np.linalg.norm(want) <= tol
+
+
+@pytest.mark.parametrize("mode,order,tol", [(1, 1, 2e-6), (0, 0, 2e-3)])
+def test_tf_gradient_matches_scipy_affine_transform(orc, mode, order, tol):
+    """TensorFlow's registered gradient of the projector graph, restated independently: the cotangent of the
+    row sum is the sinogram row broadcast over the rows of the frame; ImageProjectiveTransformV3's gradient
+    resamples it with the inverted transforms (same interpolation, zero fill); pad's gradient is the crop."""
+    import scipy.ndimage as ndi
+
+    rng = np.random.default_rng(4)
+    X, Y, A = 40, 33, 9
+    th = np.linspace(0, np.pi, A, endpoint=False) + 0.1
+    H, W, padx, pady = orc.frame_of(X, Y, True)
+    y = rng.random((2, A, W), dtype=np.float32)
+    ti = orc.invert_transforms(orc.make_transforms(th, H, W)).astype(np.float64)
+    want = orc.adjoint_tf(y, th, X, Y, True, mode)
+    got = np.zeros((2, H, W))
+    for b in range(2):
+        for a in range(A):
+            g = np.broadcast_to(y[b, a][None, :].astype(np.float64), (H, W))
+            c, ms, xo, s, c2, yo = ti[a, :6]
+            got[b] += ndi.affine_transform(g, np.array([[c2, s], [ms, c]]), offset=np.array([yo, xo]), order=order,
+                                           mode="constant", cval=0.0, output_shape=(H, W))
+    got = got[:, padx:padx + X, pady:pady + Y]
+    assert np.linalg.norm(got - want) / np.linalg.norm(want) <= tol

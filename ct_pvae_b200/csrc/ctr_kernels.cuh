@@ -895,6 +895,8 @@ inline cudaError_t launch_bp(const BpParams& p, cudaStream_t st)
         if (small_tiles) return launch_bp_cfg<32, 4, 4, MODE, INTERP>(p, st);
         static const bool occ3 = getenv("CTR_BP_OCC3") != nullptr;          // developer switch: 3 CTAs/SM (85 regs)
         if (occ3) return launch_bp_cfg<32, 8, 3, MODE, INTERP>(p, st);
+        // (r1: 32 x 5 / 32 x 6 pixel tiles with three CTAs per SM -- finer tiles against the 1.73-wave grid of
+        // C2 -- measured 0.371 / 0.376 vs 0.374 ms at C2 and 5.12 / 4.90 vs 4.65 ms at C4: not kept)
         return launch_bp_cfg<32, 8, 2, MODE, INTERP>(p, st);
     }
     if (nb == 16) return launch_bp_cfg<16, 8, 3, MODE, INTERP>(p, st);

@@ -304,8 +304,14 @@ def run_ours(args, wl):
         parts, works = [], []
         for lo in range(0, B, half):
             g = ops.radon_adjoint(cot[lo:lo + half], plan, iid, mid)
-            works.append(dist.all_reduce(g, async_op=True))
-            parts.append(g)
+            if args.angle_collective == "reduce_scatter" and g.shape[0] % world == 0:
+                # result stays batch-sharded: rank r ends up with the summed images [r*n/world, (r+1)*n/world) of this half
+                out = torch.empty((g.shape[0] // world,) + tuple(g.shape[1:]), dtype=g.dtype, device=g.device)
+                works.append(dist.reduce_scatter_tensor(out, g, async_op=True))
+                parts.append((out, g))      # keep the input alive until the collective has run
+            else:
+                works.append(dist.all_reduce(g, async_op=True))
+                parts.append(g)
         for w in works:
             w.wait()
         return s, parts
@@ -440,7 +446,7 @@ def run_ours(args, wl):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if angle_mode else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic foam (unit disk, random circular pores), random cotangents",
             "config": {"workload": wl["name"], "interpolation": INTERP, "adjoint": "exact", "B_per_gpu": B, "X": X, "Y": X,
-                       "A": A, "P": P, "sharding": "angle" if angle_mode else "batch",
+                       "A": A, "P": P, "sharding": ("angle/" + args.angle_collective) if angle_mode else "batch",
                        "l2": "flushed (256 MiB memset) between timed steps"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
@@ -475,6 +481,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--shard", default="batch", choices=["batch", "angle"])
+    ap.add_argument("--angle-collective", default="all_reduce", choices=["all_reduce", "reduce_scatter"],
+                    help="angle-sharded mode: how the partial back-projections are summed")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-side-legs", action="store_true")
     ap.add_argument("--no-train-leg", action="store_true")

@@ -55,7 +55,7 @@ void pack_sino(const float* y, int B, int A, int W, std::vector<float>& spk)
 }
 
 // DEPTH = lanes per ray, NBL = images per lane (4, or 8 with the parity-swizzled loads of 32-image records)
-template <int INTERP, int DEPTH, int NBL = NB>
+template <int INTERP, int DEPTH, int NBL = NB, bool REUSE = true>
 void forward_impl(const float* img, int B, int X, int Y, int H, int W, int padx, int pady,
                   const float* t, int A, int R, float* sino)
 {
@@ -85,7 +85,7 @@ void forward_impl(const float* img, int B, int X, int Y, int H, int W, int padx,
                     const int rows = std::min(R + 1, cg.Vp - k * R);
                     std::vector<float> strip((size_t)(R + 1) * cg.Up * REC, -1e30f);  // poison what is not loaded
                     std::memcpy(strip.data(), pkg + (size_t)k * R * cg.Up * REC, sizeof(float) * rows * cg.Up * REC);
-                    if (NBL == 8 && INTERP == CTR_BILINEAR)   // the kernel's default march for 8-image lanes
+                    if (REUSE && NBL == 8 && INTERP == CTR_BILINEAR)   // the windowed shape's march for 8-image lanes
                         ctr_march_reuse<NBL, REC>(strip.data() + gsub * NBL, cg.Up, (float)((k + 1) * R + cg.offv),
                                                   k * R + cg.offv, cg.offu, r, s, acc, swz);
                     else
@@ -342,6 +342,13 @@ void emu_forward_rec32(const float* img, int B, int X, int Y, int H, int W, int 
 {
     if (interp == CTR_NEAREST) forward_impl<CTR_NEAREST, 4, 8>(img, B, X, Y, H, W, padx, pady, t, A, R, sino);
     else forward_impl<CTR_BILINEAR, 4, 8>(img, B, X, Y, H, W, padx, pady, t, A, R, sino);
+}
+// same records, plain march (the whole-row 32-image shape of narrow detectors)
+void emu_forward_rec32_plain(const float* img, int B, int X, int Y, int H, int W, int padx, int pady, const float* t, int A,
+                             int interp, int R, float* sino)
+{
+    if (interp == CTR_NEAREST) forward_impl<CTR_NEAREST, 4, 8, false>(img, B, X, Y, H, W, padx, pady, t, A, R, sino);
+    else forward_impl<CTR_BILINEAR, 4, 8, false>(img, B, X, Y, H, W, padx, pady, t, A, R, sino);
 }
 int emu_forward_window32(const float* img, int B, int X, int Y, int H, int W, int padx, int pady, const float* t, int A,
                          int interp, int JW, int NA, int Rmax, int budget, float* sino)

@@ -50,7 +50,10 @@ def test_emulated_kernels_match_oracle(emu, orc, B, X, Y, A, pad, R, TW, TH, win
         emu.emu_forward_depth(P(img), B, X, Y, H, W, padx, pady, P(t), A, interp, R, P(sd))
         s32 = np.full_like(sd, np.nan)
         emu.emu_forward_rec32(P(img), B, X, Y, H, W, padx, pady, P(t), A, interp, R, P(s32))
-        assert np.array_equal(s32, sd), "32-image records (swizzled 8-image lanes) differ from 16-image records"
+        assert np.array_equal(s32, sd), "32-image records (swizzled 8-image lanes, reuse march) differ from 16-image records"
+        s32p = np.full_like(sd, np.nan)
+        emu.emu_forward_rec32_plain(P(img), B, X, Y, H, W, padx, pady, P(t), A, interp, R, P(s32p))
+        assert np.array_equal(s32p, sd), "32-image records (plain march) differ from 16-image records"
         np.testing.assert_array_equal(sd, s)
         si = np.full((B, A, W), np.nan, np.float32)       # i-synchronous quarter-warps: same samples, same order per ray
         emu.emu_forward_isync(P(img), B, X, Y, H, W, padx, pady, P(t), A, interp, R, P(si))
@@ -100,7 +103,10 @@ def test_emulated_kernels_property(emu, orc, B, X, Y, pad, R, th, seed):
         emu.emu_forward_depth(P(img), B, X, Y, H, W, padx, pady, P(t), A, interp, R, P(sd))
         s32 = np.full_like(sd, np.nan)
         emu.emu_forward_rec32(P(img), B, X, Y, H, W, padx, pady, P(t), A, interp, R, P(s32))
-        assert np.array_equal(s32, sd), "32-image records (swizzled 8-image lanes) differ from 16-image records"
+        assert np.array_equal(s32, sd), "32-image records (swizzled 8-image lanes, reuse march) differ from 16-image records"
+        s32p = np.full_like(sd, np.nan)
+        emu.emu_forward_rec32_plain(P(img), B, X, Y, H, W, padx, pady, P(t), A, interp, R, P(s32p))
+        assert np.array_equal(s32p, sd), "32-image records (plain march) differ from 16-image records"
         np.testing.assert_array_equal(sd, s)
         si = np.full((B, A, W), np.nan, np.float32)
         emu.emu_forward_isync(P(img), B, X, Y, H, W, padx, pady, P(t), A, interp, R, P(si))

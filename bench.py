@@ -189,6 +189,9 @@ def run_reference(args, wl):
         return
     from oracle import radon_oracle as orc
 
+    # all host threads the box has (torchrun pins OMP_NUM_THREADS=1 per rank; the other ranks do no work here)
+    avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    orc.lib().orc_set_num_threads(int(avail))
     cores = int(orc.lib().orc_max_threads())
     # size the per-step sample so warmup+steps stay within a few minutes
     cpu_reference_pass(wl["B"], wl["X"], wl["A"], 1)        # first touch: library load, page-in

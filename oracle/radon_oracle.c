@@ -38,6 +38,17 @@
 
 int orc_version(void) { return 1; }
 
+/* torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm of bench.py (rank 0 alone) asks for
+ * all host cores again. */
+void orc_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int orc_max_threads(void)
 {
 #ifdef _OPENMP

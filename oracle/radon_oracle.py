@@ -54,6 +54,8 @@ def lib():
         L.orc_num_proj_pix.argtypes = [i, i]
         L.orc_num_proj_pix.restype = i
         L.orc_max_threads.restype = i
+        L.orc_set_num_threads.argtypes = [i]
+        L.orc_set_num_threads.restype = None
         L.orc_make_transforms.argtypes = [_f64p, i, i, i, _f32p]
         L.orc_invert_transforms.argtypes = [_f32p, i, _f32p]
         for name in ("orc_forward", "orc_forward_dataflow", "orc_adjoint_exact", "orc_adjoint_tf"):

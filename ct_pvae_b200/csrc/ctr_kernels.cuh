@@ -790,7 +790,7 @@ inline FwdConfig fwd_config_depth(int W, const CtrClassGeom geom[2], int smem_bu
             }
         }
     }
-    c.reuse = (c.depth == 8 && getenv("CTR_FWD_REUSE") != nullptr) ? 1 : 0;   // opt-in experiment for whole-row strips
+    c.reuse = 0;   // whole-row strips: the reuse march needs 96 registers, i.e. CTAs of <= 640 threads (r1: 0.532 vs 0.521 ms with 80)
     const int fixed = 128 + round_up(c.NS * c.KA * (int)sizeof(CtrRay), 128);
     const int Upmax = geom[0].Up > geom[1].Up ? geom[0].Up : geom[1].Up;
     const int Vpmax = geom[0].Vp > geom[1].Vp ? geom[0].Vp : geom[1].Vp;

@@ -482,12 +482,13 @@ __host__ __device__ constexpr int bp_ab(int TH, int NB = 16, int MINB = 2) { ret
 // threads gather from the previous batch.  No atomics anywhere: each thread owns its
 // pixel's NB accumulators, and the per-pixel geometry is shared by the NB images.
 template <int NB, int TH, int MINB, int MODE, int INTERP>
-__global__ void __launch_bounds__(kBpTW * TH, MINB) ctr_bp_kernel(const BpParams p)
+__global__ void __launch_bounds__(kBpTW * (TH + 1), MINB) ctr_bp_kernel(const BpParams p)
 {
     constexpr int TW = kBpTW, AB = bp_ab(TH, NB, MINB), NBP = NB / 4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);            // [2]
-    int* jb = reinterpret_cast<int*>(smem_raw + 16);                   // [2][AB]
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);            // [2] batch landed (AB producer lanes + their TMA bytes)
+    uint64_t* empty = full + 2;                                        // [2] batch consumed (one arrive per consumer warp)
+    int* jb = reinterpret_cast<int*>(smem_raw + 32);                   // [2][AB]
     float* tbl = reinterpret_cast<float*>(smem_raw + 128);             // [2][AB][8]
     double* css = reinterpret_cast<double*>(smem_raw + 128 + 2 * AB * 8 * 4);  // [2][AB][2]
     float* wins = reinterpret_cast<float*>(smem_raw + 128 + 2 * AB * 8 * 4 + 2 * AB * 2 * 8);  // [2][AB][NBP][win][4]
@@ -506,6 +507,8 @@ __global__ void __launch_bounds__(kBpTW * TH, MINB) ctr_bp_kernel(const BpParams
     if (tid == 0) {
         mbar_init(&full[0], AB);
         mbar_init(&full[1], AB);
+        mbar_init(&empty[0], TH);
+        mbar_init(&empty[1], TH);
         fence_barrier_init();
     }
     __syncthreads();
@@ -553,9 +556,17 @@ __global__ void __launch_bounds__(kBpTW * TH, MINB) ctr_bp_kernel(const BpParams
                      p.spk + ((((size_t)g * p.A + a) * NBP + h) * Wp2 + start) * 4, bytes, bar);
     };
 
-    if (tid < AB) {
-        produce(0, tid);
-        if (nbatch > 1) produce(1, tid);
+    // ---- producer warp (threadIdx.y == TH): lane k < AB owns angle k of every batch.  A batch buffer is
+    // refilled as soon as every consumer warp has released it -- no CTA-wide barrier in the angle loop (r1 ncu:
+    // one warp in four sat at the __syncthreads of the previous version).
+    if (ty == TH) {
+        if (tx < AB) {
+            for (int nb = 0; nb < nbatch; ++nb) {
+                if (nb >= 2) mbar_wait(&empty[nb & 1], (uint32_t)(((nb >> 1) - 1) & 1));
+                produce(nb, tx);
+            }
+        }
+        return;
     }
 
     float acc[NB];
@@ -582,8 +593,8 @@ __global__ void __launch_bounds__(kBpTW * TH, MINB) ctr_bp_kernel(const BpParams
                 else ctr_adj_tf<NB, INTERP>(t, p.H, p.W, px, py, ywin, pstride, start, acc);
             }
         }
-        __syncthreads();  // batch buffers free again
-        if (tid < AB && nb + 2 < nbatch) produce(nb + 2, tid);
+        __syncwarp();
+        if (tx == 0) mbar_arrive(&empty[s]);       // this warp is done reading the batch buffers
     }
 
     if (r < p.X && c < p.Y) {
@@ -875,7 +886,7 @@ template <int NB, int TH, int MINB, int MODE, int INTERP>
 inline cudaError_t launch_bp_cfg(BpParams p, cudaStream_t st)
 {
     const int G = (p.B + NB - 1) / NB;
-    dim3 grid((p.Y + kBpTW - 1) / kBpTW, (p.X + TH - 1) / TH, G), block(kBpTW, TH);
+    dim3 grid((p.Y + kBpTW - 1) / kBpTW, (p.X + TH - 1) / TH, G), block(kBpTW, TH + 1);   // + the producer warp
     if (p.win > bp_win(TH)) p.win = bp_win(TH);
     const size_t smem = bp_smem_bytes(p.win, NB, bp_ab(TH, NB, MINB));
     cudaError_t e = cudaFuncSetAttribute(ctr_bp_kernel<NB, TH, MINB, MODE, INTERP>,

@@ -13,9 +13,9 @@
 //
 // Data movement: image strips (K1) and sinogram bin windows (K2/K3b) are staged in
 // shared memory by the TMA engine with 1-D bulk copies (cp.async.bulk, SASS UBLKCP)
-// completing on mbarriers.  K1 runs a producer warp / consumer warps ring (full + empty
-// mbarriers per strip buffer, no CTA-wide barrier in the loop); K2/K3b double-buffer
-// batches of 8 angles.  The packs exist so that every staged block is a contiguous,
+// completing on mbarriers.  K1 and K2/K3b run a producer warp / consumer warps ring (full +
+// empty mbarriers per buffer, no CTA-wide barrier in the loop): strips for K1, batches of 8
+// angles for K2/K3b.  The packs exist so that every staged block is a contiguous,
 // 16-byte aligned range in HBM (whole packed rows, or -- wide detectors -- the column
 // window of every row that the CTA's rays cross) and so that one 128-bit shared-memory
 // load serves 4 images: the per-sample geometry (coordinates, floor, weights, address)
@@ -475,12 +475,13 @@ __host__ __device__ constexpr int bp_win(int TH) { return TH <= 8 ? 40 : 44; }
 // angles staged per batch: 4 for the small 32x4 tiles (4 CTAs per SM must fit in shared memory)
 __host__ __device__ constexpr int bp_ab(int TH, int NB = 16, int MINB = 2) { return (TH <= 4 || (NB >= 32 && MINB >= 3)) ? 4 : kBpAB; }
 
-// One CTA = 32 x TH pixel tile x image group of NB.  Angles are processed in batches
-// of AB: lanes 0..AB-1 of warp 0 each own one angle of the batch -- they compute the
-// bin window the tile needs, publish its start + the angle's coefficients to shared
-// memory, and issue the window's TMA bulk copies (one per 4-image plane) -- while all
-// threads gather from the previous batch.  No atomics anywhere: each thread owns its
-// pixel's NB accumulators, and the per-pixel geometry is shared by the NB images.
+// One CTA = 32 x TH pixel tile x image group of NB (TH consumer warps) + one producer warp.
+// Angles are processed in batches of AB: lanes 0..AB-1 of the producer warp each own one
+// angle of the batch -- they compute the bin window the tile needs, publish its start + the
+// angle's coefficients to shared memory, and issue the window's TMA bulk copies (one per
+// 4-image plane) -- while the consumer warps gather from the other batch buffer and release
+// it warp by warp.  No atomics anywhere: each thread owns its pixel's NB accumulators, and
+// the per-pixel geometry is shared by the NB images.
 template <int NB, int TH, int MINB, int MODE, int INTERP>
 __global__ void __launch_bounds__(kBpTW * (TH + 1), MINB) ctr_bp_kernel(const BpParams p)
 {

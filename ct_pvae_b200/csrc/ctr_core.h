@@ -429,10 +429,15 @@ CTR_HD void ctr_adj_exact(const float* t, int H, int W, float px, float py,
             }
             if (i >= 0 && i < H) wsum += w;
         }
-        float yv[NB];
-        ctr_ld_bins<NB>(ywin, pstride, j + 1 - jbase_p, yv);
+        // plane by plane (4 images per 16-byte bin): keeps the live load registers at 4 instead of NB
+        const float* yb = ywin + (size_t)(j + 1 - jbase_p) * 4;
 #pragma unroll
-        for (int q = 0; q < NB; ++q) acc[q] += wsum * yv[q];
+        for (int h = 0; h < NB / 4; ++h) {
+            float y4[4];
+            ctr_ldv<4>(yb + (size_t)h * pstride, y4);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[4 * h + q] += wsum * y4[q];
+        }
     }
 }
 

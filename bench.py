@@ -440,6 +440,9 @@ def run_ours(args, wl):
             "fwd_gray_sums_per_s": (B * A_loc * P / (fwd_ms * 1e-3) / 1e9) if fwd_ms else None,
             "adjoint_gupdates_per_s": (B * A_loc * X * X / (adj_ms * 1e-3) / 1e9) if adj_ms else None,
             # binding on-chip limit of the forward gather: 16 B of shared memory per in-support bilinear sample
+            # same for the exact adjoint: 3 candidate bins x 4 B of shared memory per pixel-angle update and image
+            "adj_smem_roofline": ({"achieved_GBs": 12.0 * B * A_loc * X * X / (adj_ms * 1e-3) / 1e9, "peak_GBs": smem_peak,
+                                   "frac": 12.0 * B * A_loc * X * X / (adj_ms * 1e-3) / 1e9 / smem_peak} if adj_ms else None),
             "fwd_smem_roofline": ({"achieved_GBs": 16.0 * B * A_loc * (X + 1) ** 2 / (fwd_ms * 1e-3) / 1e9,
                                    "peak_GBs": smem_peak, "frac": 16.0 * B * A_loc * (X + 1) ** 2 / (fwd_ms * 1e-3) / 1e9 / smem_peak}
                                   if fwd_ms else None),

@@ -163,16 +163,19 @@ __global__ void __launch_bounds__(128) ctr_pack_sino_kernel(const float* __restr
     const int jp = blockIdx.x * blockDim.x + threadIdx.x;
     if (jp >= W + 2) return;
     const int a = blockIdx.y, g = blockIdx.z, j = jp - 1;
+    // all NB loads are issued before the first store (latency-bound kernel, like the image pack)
+    float v[NB];
+    const bool jok = j >= 0 && j < W;
+#pragma unroll
+    for (int n = 0; n < NB; ++n) {
+        const int b = g * NB + n;
+        const bool ok = jok && b < B;
+        v[n] = ok ? __ldg(y + ((size_t)(ok ? b : 0) * A + a) * W + (ok ? j : 0)) : 0.f;
+    }
 #pragma unroll
     for (int h = 0; h < NB / 4; ++h) {
-        float v[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int b = g * NB + 4 * h + q;
-            v[q] = (b < B && j >= 0 && j < W) ? __ldg(y + ((size_t)b * A + a) * W + j) : 0.f;
-        }
         float* dst = spk + ((((size_t)g * A + a) * (NB / 4) + h) * (W + 2) + jp) * 4;
-        *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(dst) = make_float4(v[4 * h], v[4 * h + 1], v[4 * h + 2], v[4 * h + 3]);
     }
 }
 

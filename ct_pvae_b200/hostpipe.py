@@ -75,6 +75,14 @@ class HostResult:
     def is_completed(self) -> bool:
         return self._pipe is None or self._pipe.done()
 
+    def __del__(self):
+        # a dropped handle must not release the pinned buffers while the copies are still in flight: the
+        # pipe's streams are invisible to torch's pinned-memory allocator
+        try:
+            self.wait()
+        except Exception:
+            pass
+
 
 _pipes: "collections.OrderedDict" = collections.OrderedDict()
 _pipes_lock = threading.Lock()
@@ -122,7 +130,11 @@ def clear_pipes() -> None:
 def _run(plan, x_host: torch.Tensor, out_shape, async_op: bool, issue, kind: str):
     pipe = get_pipe(plan, chunk_for(plan, int(x_host.shape[0]), kind), kind)
     out = torch.empty(out_shape, dtype=torch.float32, pin_memory=True)
-    issue(pipe, out)
+    try:
+        issue(pipe, out)
+    except Exception:
+        pipe.wait()        # chunks already enqueued still reference the host buffers
+        raise
     if async_op:
         return out, HostResult(pipe, (x_host, out))
     pipe.wait()

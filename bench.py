@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
 """bench.py -- Radon forward + adjoint throughput on B200 (BASELINE.json's metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c4] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c2|c5] [--shard batch|angle]
+                  [--impl ours|reference]
 
 A *step* is one pass of the hot path over one batch of synthetic foam images: the
 ray-driven forward projection (bilinear) of B images at A angles, then the exact
@@ -10,13 +11,21 @@ projector forward + backward costs (reference: helper_functions.py:359 inside th
 tape of main_ct_vae.py:471-481).  `value` is ray-sums per second over the whole job:
 B*A*P ray-sums (each projected once and back-projected once) / step time.
 
-N > 1 (torchrun, one rank per GPU): the batch is sharded -- every rank owns its own B
-images (weak scaling, no data-path collective).  `--shard angle` switches to the
-angle-sharded mode of SURVEY 8e (every rank holds all B images and A/N angles; the
-partial back-projections are summed with one NCCL all-reduce).
+Default workload: BASELINE.json configs[3] (C4: 64 x 512^2 x 720 angles, P = 728) -- the
+configuration north_star quotes its target on.  configs[1] (C2: 256 x 128^2 x 180) and
+configs[4] (C5: FBP over 1000 x 128^2 x 180) are measured in the same run and reported
+under `extra`.
+
+N = 1: the whole batch on one GPU.
+N > 1 (torchrun, one rank per GPU), default `--shard angle`: configs[3]'s angle-sharded mode --
+every rank holds all B images and A/N angles; the forward writes disjoint sinogram row
+blocks and the partial back-projections are summed over the ranks INSIDE the timed step
+(strong scaling: the total work is fixed).  The warm-up asserts that the reduced
+back-projection equals a single-rank adjoint of the same cotangent (rel-L2 <= 1e-6).
+`--shard batch`: every rank owns its own B images (weak scaling, no data-path collective).
 
 `--impl reference` times the reference's CPU dataflow (oracle port; TensorFlow itself
-is not installable in this image) on the host cores.
+is not installable in this image) on the host cores, on the same workload.
 """
 from __future__ import annotations
 
@@ -35,10 +44,12 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # BASELINE.json configs[1]: the configuration the metric is quoted on
+    # BASELINE.json configs[1]: the reference's projector/adjoint microbench
     "c2": dict(B=256, X=128, A=180, name="configs[1] projector/adjoint microbench: foam 128x128, 180 angles, batch 256"),
-    # BASELINE.json configs[3]: large-scale operator sweep
+    # BASELINE.json configs[3]: large-scale operator sweep -- the configuration north_star's target is quoted on
     "c4": dict(B=64, X=512, A=720, name="configs[3] operator sweep: 512x512, 720 angles, batch 64"),
+    # BASELINE.json configs[4]: FBP evaluation pass over the full foam dataset (helper_functions.py:477-529)
+    "c5": dict(B=1000, X=128, A=180, name="configs[4] FBP evaluation pass: 1000 foam sinograms 180x184 -> 128x128, ramp filter"),
 }
 METRIC = "Radon fwd+adjoint Gray-sums/s"
 UNIT = "Gray-sums/s"
@@ -53,9 +64,10 @@ def env_int(name, default):
 
 
 def ncu_traffic(workload, kernel):
-    """Per-launch DRAM bytes of `kernel` from the committed ncu capture (profiles/), or None."""
+    """Per-launch DRAM bytes (read + write) of `kernel` from the committed `ncu --set full` capture of this
+    workload (profiles/dram_traffic.json, which names the .ncu-rep summary each figure comes from), or None."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_dram_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "dram_traffic.json")) as f:
             return json.load(f)[workload].get(kernel)
     except Exception:
         return None
@@ -69,6 +81,19 @@ def measured_peaks():
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def measured_smem_peak(sm_mhz):
+    """Shared-memory read bandwidth ceiling in GB/s: bytes per clock per SM measured by tools/micro/ldsbw.cu
+    (profiles/r2_ldsbw.json, conflict-free LDS.128) x 148 SMs x the clock sampled during this run."""
+    per_clk, src = 128.0, "derived (128 B/clk/SM)"
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_ldsbw.json")) as f:
+            per_clk = float(json.load(f)["lds128_bytes_per_clk_per_sm"])
+            src = "measured (tools/micro/ldsbw.cu, profiles/r2_ldsbw.json)"
+    except Exception:
+        pass
+    return 148 * per_clk * sm_mhz * 1e6 / 1e9, src
 
 
 class ClockSampler:
@@ -121,9 +146,9 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------- data
-def synthetic_foam_torch(B, X, device, seed):
+def synthetic_foam_cpu(B, X, seed):
     """Unit disk with random zero-valued circular pores (stand-in for xdesign.Foam,
-    scripts/create_foam_images.py:27-40; xdesign is not installable here)."""
+    scripts/create_foam_images.py:27-40; xdesign is not installable here).  torch CPU tensor [B,X,X]."""
     import torch
 
     g = torch.Generator(device="cpu").manual_seed(seed)
@@ -141,25 +166,45 @@ def synthetic_foam_torch(B, X, device, seed):
         sl = slice(b0, min(B, b0 + 32))
         pore = (((xx - cx[sl]) ** 2 + (yy - cy[sl]) ** 2) <= r[sl] ** 2).float() * keep[sl]
         out[sl] = disk * (1 - pore.amax(dim=1))
-    return out.to(device)
+    return out
+
+
+def synthetic_foam_torch(B, X, device, seed):
+    return synthetic_foam_cpu(B, X, seed).to(device)
 
 
 # ----------------------------------------------------------------------------------------- CPU arm
-def cpu_reference_pass(B, X, A, nb, seed=0):
+def cpu_reference_pass(wl, nb, seed=0):
     """One bounded sample of the reference's CPU dataflow: project_tf_fast's
     pad -> repeat -> rotate -> row-sum graph (bilinear) and TensorFlow's gradient of it,
-    restated in oracle/radon_oracle.c with OpenMP over all host cores.  -> seconds."""
+    restated in oracle/radon_oracle.c with OpenMP over all host cores, on `nb` synthetic foam images of the
+    workload (the same generator as the GPU arm).  -> (seconds, ray-sums)."""
     from oracle import radon_oracle as orc
 
-    rng = np.random.default_rng(seed)
+    X, A = wl["X"], wl["A"]
     theta = np.linspace(0, np.pi, A, endpoint=False)
-    img = rng.random((nb, X, X), dtype=np.float32)
+    img = synthetic_foam_cpu(nb, X, seed).numpy()
     W = orc.frame_of(X, X, True)[1]
-    cot = rng.random((nb, A, W), dtype=np.float32)
+    cot = np.random.default_rng(1 + seed).random((nb, A, W), dtype=np.float32)
     t0 = time.perf_counter()
     orc.forward(img, theta, True, orc.BILINEAR, dataflow=True)
     orc.adjoint_tf(cot, theta, X, X, True, orc.BILINEAR)
     return time.perf_counter() - t0, nb * A * W
+
+
+def cpu_fbp_pass(wl, nb, seed=0):
+    """Bounded sample of the reference's iradon (fbp_tensorflow.py:14-75) in float64 on the host cores:
+    complex FFT row filter + per-angle interpolating back-projection (oracle port).  -> (seconds, updates)."""
+    from oracle import radon_oracle as orc
+
+    X, A = wl["X"], wl["A"]
+    P = orc.frame_of(X, X, True)[1]
+    theta = np.linspace(0, np.pi, A, endpoint=False)
+    sino = np.random.default_rng(2 + seed).random((nb, A, P))
+    filt = orc.get_fourier_filter(P, "ramp")
+    t0 = time.perf_counter()
+    orc.iradon(sino, theta, X, X, filt)
+    return time.perf_counter() - t0, nb * A * X * X
 
 
 def _max_sample(wl, cores):
@@ -168,19 +213,22 @@ def _max_sample(wl, cores):
     return int(max(1, min(wl["B"], 8e9 / (cores * P * P * 4.0))))
 
 
-def cpu_baseline(wl, target_s=10.0):
+def cpu_baseline(wl, target_s=10.0, fbp=False):
     from oracle import radon_oracle as orc
 
     cores = int(orc.lib().orc_max_threads())
-    cap = _max_sample(wl, cores)
+    cap = wl["B"] if fbp else _max_sample(wl, cores)
+    run = cpu_fbp_pass if fbp else cpu_reference_pass
     nb = max(1, min(cap, 2))
-    cpu_reference_pass(wl["B"], wl["X"], wl["A"], 1)        # first touch: library load, page-in
-    t, units = cpu_reference_pass(wl["B"], wl["X"], wl["A"], nb)
+    run(wl, 1)                                               # first touch: library load, page-in
+    t, units = run(wl, nb)
     if t < target_s / 2:
         nb = int(max(1, min(cap, nb * target_s / max(t, 1e-3))))
-        t, units = cpu_reference_pass(wl["B"], wl["X"], wl["A"], nb)
-    return {"value": units / t / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{nb} of {wl['B']} images, all {wl['A']} angles, fwd dataflow + TF-style gradient, {t:.2f} s"}
+        t, units = run(wl, nb)
+    what = ("float64 iradon: FFT row filter + interpolating back-projection" if fbp
+            else "fwd dataflow + TF-style gradient")
+    return {"value": units / t / 1e9, "unit": "G pixel-angle updates/s" if fbp else UNIT, "cores": cores, "kind": "port",
+            "sample": f"{nb} of {wl['B']} images, all {wl['A']} angles, {what}, {t:.2f} s"}
 
 
 def run_reference(args, wl):
@@ -193,29 +241,37 @@ def run_reference(args, wl):
     avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     orc.lib().orc_set_num_threads(int(avail))
     cores = int(orc.lib().orc_max_threads())
+    fbp = args.workload == "c5"
+    run = cpu_fbp_pass if fbp else cpu_reference_pass
     # size the per-step sample so warmup+steps stay within a few minutes
-    cpu_reference_pass(wl["B"], wl["X"], wl["A"], 1)        # first touch: library load, page-in
-    t_probe, _ = cpu_reference_pass(wl["B"], wl["X"], wl["A"], 2)
+    run(wl, 1)                                               # first touch: library load, page-in
+    t_probe, _ = run(wl, 2)
     budget = 120.0 / max(1, args.steps + args.warmup)
-    nb = int(max(1, min(_max_sample(wl, cores), 2 * budget / max(t_probe, 1e-3))))
+    cap = wl["B"] if fbp else _max_sample(wl, cores)
+    nb = int(max(1, min(cap, 2 * budget / max(t_probe, 1e-3))))
     for _ in range(args.warmup):
-        cpu_reference_pass(wl["B"], wl["X"], wl["A"], nb)
+        run(wl, nb)
     tot, units = 0.0, 0
     for _ in range(args.steps):
-        t, u = cpu_reference_pass(wl["B"], wl["X"], wl["A"], nb)
+        t, u = run(wl, nb)
         tot += t
         units += u
     value = units / tot / 1e9
     P = orc.frame_of(wl["X"], wl["X"], True)[1]
     sample = f"{nb} of {wl['B']} images per step, all {wl['A']} angles"
+    unit = "G pixel-angle updates/s" if fbp else UNIT
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": tot / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic (uniform random images)",
-        "config": {"workload": wl["name"], "interpolation": INTERP, "adjoint": "TF gradient", "B": wl["B"],
+        "impl": "reference", "metric": "FBP Gpixel-angle updates/s" if fbp else METRIC, "value": value, "unit": unit,
+        "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": tot / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "strong" if (args.gpus > 1 and args.shard == "angle") else "weak",
+        "vs_baseline": None, "dtype": "f64" if fbp else "f32",
+        "data": "synthetic foam (unit disk, random circular pores), random cotangents",
+        "config": {"workload": wl["name"], "interpolation": INTERP,
+                   "adjoint": "n/a" if fbp else "TF gradient (the reference's autodiff)", "B": wl["B"],
                    "X": wl["X"], "Y": wl["X"], "A": wl["A"], "P": P, "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
@@ -261,222 +317,474 @@ def vae_training_leg(dev, iters=20, warm=3, seed=0, world=1):
 
 
 # ----------------------------------------------------------------------------------------- GPU arm
-def run_ours(args, wl):
-    import torch
-    import torch.distributed as dist
+class Ctx:
+    """Process-wide state of one bench run (device, ranks, the L2 flush buffer)."""
 
-    import ct_pvae_b200 as cp
-    from ct_pvae_b200 import _lib, ops, sharding
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
 
-    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    json_fd = None
-    if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
-            os.environ["NCCL_DEBUG"] = "WARN"
-        # NCCL writes its version banner to file descriptor 1 when the first communicator comes up (seen in the
-        # angle-sharded run): point fd 1 at stderr for the whole run and keep the real stdout for the ONE JSON line
-        sys.stdout.flush()
-        json_fd = os.dup(1)
-        os.dup2(2, 1)
-        dist.init_process_group("nccl", device_id=dev)
+        self.torch, self.dist = torch, dist
+        self.rank, self.world, self.local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        self.json_fd = None
+        if self.world > 1:
+            if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
+                os.environ["NCCL_DEBUG"] = "WARN"
+            # NCCL writes its version banner to file descriptor 1 when the first communicator comes up: point fd 1 at
+            # stderr for the whole run and keep the real stdout for the ONE JSON line
+            sys.stdout.flush()
+            self.json_fd = os.dup(1)
+            os.dup2(2, 1)
+            _pin_rank_to_cores(self.local, self.world)
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=self.dev)  # > 126 MB L2
 
-    B, X, A = wl["B"], wl["X"], wl["A"]
-    theta = np.linspace(0, np.pi, A, endpoint=False)
-    angle_mode = args.shard == "angle" and world > 1
-    if angle_mode:
-        a_lo, a_hi = sharding.shard_range(A, rank, world)
-        theta_local = theta[a_lo:a_hi]
-    else:
-        theta_local = theta
-    plan = _lib.get_plan(theta_local, X, X, True, local)
-    P, A_loc = plan.W, plan.A
-    img = synthetic_foam_torch(B, X, dev, seed=(0 if angle_mode else rank))
-    cot = torch.rand((B, A_loc, P), device=dev, generator=torch.Generator(device=dev).manual_seed(1 + rank))
-    iid, mid = ops.INTERP[INTERP], ops.ADJOINT["exact"]
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    def sync_all(self):
+        self.torch.cuda.synchronize(self.dev)
+        if self.world > 1:
+            self.dist.barrier()
+            self.torch.cuda.synchronize(self.dev)
 
-    def step():
-        s = ops.radon_forward(img, plan, iid)
-        if not angle_mode:
-            return s, ops.radon_adjoint(cot, plan, iid, mid)
-        # angle-sharded: sum the partial back-projections over the angle shards.  The batch is cut in
-        # two so the NCCL all-reduce of one half overlaps the adjoint kernels of the other.
-        half = max(32, (B // 2 + 31) // 32 * 32)
-        parts, works = [], []
-        for lo in range(0, B, half):
-            g = ops.radon_adjoint(cot[lo:lo + half], plan, iid, mid)
-            if args.angle_collective == "reduce_scatter" and g.shape[0] % world == 0:
-                # result stays batch-sharded: rank r ends up with the summed images [r*n/world, (r+1)*n/world) of this half
-                out = torch.empty((g.shape[0] // world,) + tuple(g.shape[1:]), dtype=g.dtype, device=g.device)
-                works.append(dist.reduce_scatter_tensor(out, g, async_op=True))
-                parts.append((out, g))      # keep the input alive until the collective has run
-            else:
-                works.append(dist.all_reduce(g, async_op=True))
-                parts.append(g)
-        for w in works:
-            w.wait()
-        return s, parts
+    def max_over_ranks(self, v: float) -> float:
+        t = self.torch.tensor([v], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
 
-    def sync_all():
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize(dev)
+    def emit(self, line):
+        if self.rank != 0:
+            return
+        if self.json_fd is None:
+            print(json.dumps(line), flush=True)
+        else:
+            sys.stdout.flush()
+            os.write(self.json_fd, (json.dumps(line) + "\n").encode())
 
-    warm = max(args.warmup, 3)   # timing rule: at least 3 warm-up steps
+
+def _pin_rank_to_cores(local, world):
+    """Give every rank its own slice of the host cores (the copy engines' staging threads and the pinned-memory
+    first touch then stay local to it instead of all ranks sharing core 0's neighbourhood)."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = max(1, len(cores) // max(1, world))
+        mine = cores[local * per:(local + 1) * per] or cores
+        os.sched_setaffinity(0, mine)
+    except Exception:
+        pass
+
+
+def timed_steps(ctx, step, steps, warm):
+    """W warm-up steps, then K steps timed with per-step CUDA events on the launching stream, the L2 flushed
+    (256 MiB memset) before each; barrier + synchronize on both sides; MAX over ranks.
+    -> (ms_per_step, per-kernel {name: (total ms, launches)}, launches, clocks)"""
+    from ct_pvae_b200 import _lib
+    torch = ctx.torch
     for _ in range(warm):
         step()
-    sync_all()
-
-    # ---- timed region: K steps, per-step CUDA events, L2 flushed between steps
-    sampler = ClockSampler(local) if rank == 0 else None
+    ctx.sync_all()
+    sampler = ClockSampler(ctx.local) if ctx.rank == 0 else None
     _lib.profile_reset()
     _lib.profile_enable(True)
     launches0 = _lib.launch_count()
     evs = []
-    sync_all()
-    for _ in range(args.steps):
-        flush.zero_()
+    ctx.sync_all()
+    for _ in range(steps):
+        ctx.flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         step()
         e1.record()
         evs.append((e0, e1))
-    sync_all()
+    ctx.sync_all()
     launches = _lib.launch_count() - launches0
     _lib.profile_enable(False)
     total_ms = sum(a.elapsed_time(b) for a, b in evs)
     prof = _lib.profile_read()
     _lib.profile_reset()
     clocks = sampler.stop() if sampler else None
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    ms_per_step = total_ms / args.steps
-    units_per_step = B * A * P * (1 if angle_mode else world)   # whole-job ray-sums per step
-    value = units_per_step / (ms_per_step * 1e-3) / 1e9
+    total_ms = ctx.max_over_ranks(total_ms)
+    return total_ms / steps, prof, launches, clocks, total_ms
 
-    # ---- side legs (reported under "extra", not part of the headline step): the reference's
-    # default nearest mode, TF-compatible gradient, and the FBP evaluation pass on the same batch
-    def best_ms(fn, iters=5):
+
+def best_ms(ctx, fn, iters=5):
+    torch = ctx.torch
+    fn()
+    torch.cuda.synchronize(ctx.dev)
+    ts = []
+    for _ in range(iters):
+        ctx.flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
         fn()
-        torch.cuda.synchronize(dev)
-        ts = []
-        for _ in range(iters):
-            flush.zero_()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            fn()
-            b.record()
-            torch.cuda.synchronize(dev)
-            ts.append(a.elapsed_time(b))
-        return float(np.median(ts))
+        b.record()
+        torch.cuda.synchronize(ctx.dev)
+        ts.append(a.elapsed_time(b))
+    return float(np.median(ts))
 
-    side = {}
-    if rank == 0 and not args.no_side_legs:
-        nid = ops.INTERP["nearest"]
-        side["fwd_nearest_ms"] = best_ms(lambda: ops.radon_forward(img, plan, nid))
-        side["adj_exact_nearest_ms"] = best_ms(lambda: ops.radon_adjoint(cot, plan, nid, mid))
-        side["adj_tf_compat_bilinear_ms"] = best_ms(lambda: ops.radon_adjoint(cot, plan, iid, ops.ADJOINT["tf_compat"]))
-        fplan = _lib.get_fbp_plan(theta_local, P, X, X, cp.get_fourier_filter(P, "ramp"), local)
-        side["fbp_ms"] = best_ms(lambda: ops.fbp(cot, fplan))
-        side["fbp_gupdates_per_s"] = B * A_loc * X * X / (side["fbp_ms"] * 1e-3) / 1e9
-        side["fwd_nearest_gray_sums_per_s"] = B * A_loc * P / (side["fwd_nearest_ms"] * 1e-3) / 1e9
-    if not args.no_side_legs and not args.no_train_leg and (rank == 0 or world > 1):
-        # world > 1: every rank trains on its own batch slice, gradients averaged over NCCL
-        try:
-            leg = vae_training_leg(dev, seed=rank, world=world)
-            if rank == 0:
-                side["vae_train"] = leg
-        except Exception as exc:  # the restated VAE is a caller, never a reason to lose the headline
-            side["vae_train"] = {"error": repr(exc)[:200]}
-    sync_all()
 
-    # ---- e2e: the public API with pinned HOST buffers, copies inside the timed region
-    img_h = img.cpu().unsqueeze(-1).pin_memory()
-    cot_h = cot.cpu().pin_memory()
+def kernel_table(prof, total_ms):
+    return {k: {"ms_per_launch": v[0] / v[1], "launches": v[1], "share_of_step": v[0] / total_ms} for k, v in prof.items()}
+
+
+def batch_record(ctx, wl, steps, warm, seed_rank=True):
+    """Device-timed fwd + exact adjoint of one workload on this rank's own batch (batch-sharded / single GPU)."""
+    import ct_pvae_b200 as cp  # noqa: F401
+    from ct_pvae_b200 import _lib, ops
+    torch = ctx.torch
+    B, X, A = wl["B"], wl["X"], wl["A"]
+    theta = np.linspace(0, np.pi, A, endpoint=False)
+    plan = _lib.get_plan(theta, X, X, True, ctx.local)
+    P = plan.W
+    img = synthetic_foam_torch(B, X, ctx.dev, seed=ctx.rank if seed_rank else 0)
+    cot = torch.rand((B, A, P), device=ctx.dev, generator=torch.Generator(device=ctx.dev).manual_seed(1 + ctx.rank))
+    iid, mid = ops.INTERP[INTERP], ops.ADJOINT["exact"]
+
+    def step():
+        return ops.radon_forward(img, plan, iid), ops.radon_adjoint(cot, plan, iid, mid)
+
+    ms, prof, launches, clocks, total_ms = timed_steps(ctx, step, steps, warm)
+    units = B * A * P * ctx.world
+    rec = {"ms_per_step": ms, "value": units / (ms * 1e-3) / 1e9, "unit": UNIT, "units_per_step": units, "launches": launches,
+           "clocks": clocks, "kernels": kernel_table(prof, total_ms), "P": P, "plan": plan.describe(B)}
+    return rec, dict(plan=plan, img=img, cot=cot, theta=theta, P=P, iid=iid, mid=mid, prof=prof, total_ms=total_ms)
+
+
+def smem_rooflines(rec, wl, A_loc, clocks):
+    """The binding on-chip limit: shared-memory bytes of the forward gather (16 B per in-support
+    bilinear sample and image) and of the exact adjoint (3 candidate bins x 4 B per pixel-angle update and image)
+    against the measured LDS bandwidth at the sampled clock."""
+    B, X = wl["B"], wl["X"]
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    peak, src = measured_smem_peak(sm_mhz)
+    out = {"peak_GBs": peak, "peak_source": src}
+    fwd = rec["kernels"].get("ctr_fwd_kernel", {}).get("ms_per_launch")
+    adj = rec["kernels"].get("ctr_bp_kernel<exact>", {}).get("ms_per_launch")
+    if fwd:
+        ach = 16.0 * B * A_loc * (X + 1) ** 2 / (fwd * 1e-3) / 1e9
+        out["fwd"] = {"achieved_GBs": ach, "frac": ach / peak}
+    if adj:
+        ach = 12.0 * B * A_loc * X * X / (adj * 1e-3) / 1e9
+        out["adj"] = {"achieved_GBs": ach, "frac": ach / peak}
+    return out
+
+
+def roofline_of(rec, wl, A_loc, workload_key, sharded=False):
+    """HBM roofline of the dominant kernel: algorithmic bytes per launch (4*B*(X*Y + A*P), the image in
+    and the sinogram out, or the mirror for the adjoint) / its live event-timed duration / the measured HBM peak."""
+    peak, peak_src = measured_peaks()
+    kern = rec["kernels"]
+    if not kern:
+        return None
+    name = max(kern, key=lambda k: kern[k]["ms_per_launch"] * kern[k]["launches"])
+    B, X = wl["B"], wl["X"]
+    # a launch may cover only part of the batch (image groups of the overlapped sharded adjoint)
+    per_step = kern[name]["launches"] / max(1, rec.get("steps", 1))
+    alg = 4.0 * B * (X * X + A_loc * rec["P"]) / max(1.0, per_step)
+    ms = kern[name]["ms_per_launch"]
+    ach = alg / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            "traffic": None if sharded else ncu_traffic(workload_key, name), "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": alg,
+            "note": "gather/issue-bound stencil: the HBM fraction is small by construction (SURVEY 8d, DESIGN 5); the "
+                    "binding on-chip figure is extra.smem_roofline"}
+
+
+def e2e_batch(ctx, wl, st, steps, numpy_inputs=False):
+    """The public API with HOST buffers, copies inside the timed region: project_tf_fast + backproject, both issued
+    with async_op=True so the forward's copy-out overlaps the adjoint's copy-in; the step ends when both results
+    are in host memory.  numpy_inputs: plain (pageable) NumPy arrays, the reference callers' case."""
+    import ct_pvae_b200 as cp
+    torch = ctx.torch
+    X = wl["X"]
+    img_h = st["img"].cpu().unsqueeze(-1)
+    cot_h = st["cot"].cpu()
+    if numpy_inputs:
+        img_h, cot_h = img_h.numpy(), cot_h.numpy()
+    else:
+        img_h, cot_h = img_h.pin_memory(), cot_h.pin_memory()
+
     def e2e_step():
-        # both calls are issued with async_op=True (pinned result + completion handle, like a torch.distributed
-        # work handle) so the forward's copy-out overlaps the adjoint's copy-in; the step ends when both
-        # results are in host memory
-        s, hs = cp.project_tf_fast(img_h, theta_local, pad=True, dim=2, integrate_vae=True, interpolation=INTERP,
-                                   async_op=True)
-        g, hg = cp.backproject(cot_h, theta_local, X, X, pad=True, interpolation=INTERP, adjoint="exact", async_op=True)
+        s, hs = cp.project_tf_fast(img_h, st["theta"], pad=True, dim=2, integrate_vae=True, interpolation=INTERP, async_op=True)
+        g, hg = cp.backproject(cot_h, st["theta"], X, X, pad=True, interpolation=INTERP, adjoint="exact", async_op=True)
         hs.wait()
         hg.wait()
         return s, g
-    for _ in range(3):           # warm up holding the results like the timed loop does, so the
-        s_h, g_h = e2e_step()    # pinned-host allocator has every block it will hand out
-    sync_all()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        s_h, g_h = e2e_step()
-    torch.cuda.synchronize(dev)
-    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e_value = units_per_step * args.steps / float(t_e2e.item()) / 1e9
-    h2d = img_h.numel() * 4 + cot_h.numel() * 4
-    d2h = s_h.numel() * 4 + g_h.numel() * 4
 
-    if rank == 0:
-        peak, peak_src = measured_peaks()
-        # dominant kernel of the step and its HBM roofline (compulsory bytes)
-        dom = max(prof.items(), key=lambda kv: kv[1][0]) if prof else (None, (0.0, 1))
-        alg_bytes = 4.0 * B * (X * X + A_loc * P)     # forward: image in + sinogram out; adjoint: the mirror
-        dom_ms = dom[1][0] / max(1, dom[1][1])
-        achieved = alg_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
-        kern = {k: {"ms_per_launch": v[0] / v[1], "launches": v[1], "share_of_step": v[0] / total_ms} for k, v in prof.items()}
+    for _ in range(3):
+        s_h, g_h = e2e_step()
+    ctx.sync_all()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        s_h, g_h = e2e_step()
+    torch.cuda.synchronize(ctx.dev)
+    dt = ctx.max_over_ranks(time.perf_counter() - t0)
+    n = lambda a: int(np.prod(a.shape))  # noqa: E731
+    return {"value": wl["B"] * wl["A"] * st["P"] * ctx.world * steps / dt / 1e9, "unit": UNIT,
+            "h2d_bytes_per_step": (n(img_h) + n(cot_h)) * 4, "d2h_bytes_per_step": (n(s_h) + n(g_h)) * 4,
+            "ms_per_step": dt / steps * 1e3, "host_buffers": "pageable NumPy" if numpy_inputs else "pinned torch"}
+
+
+def c5_record(ctx, steps=5):
+    """BASELINE configs[4]: the FBP evaluation pass (iradon over the whole foam dataset) on one GPU, device-timed, with
+    the reference's float64 iradon (oracle port) timed beside it on the host cores."""
+    import ct_pvae_b200 as cp
+    from ct_pvae_b200 import _lib, ops
+    torch = ctx.torch
+    wl = WORKLOADS["c5"]
+    B, X, A = wl["B"], wl["X"], wl["A"]
+    P = cp.num_proj_pix(X, X)
+    theta = np.linspace(0, np.pi, A, endpoint=False)
+    fplan = _lib.get_fbp_plan(theta, P, X, X, cp.get_fourier_filter(P, "ramp"), ctx.local)
+    sino = torch.rand((B, A, P), device=ctx.dev, generator=torch.Generator(device=ctx.dev).manual_seed(3))
+    _lib.profile_reset()
+    _lib.profile_enable(True)
+    ms = best_ms(ctx, lambda: ops.fbp(sino, fplan), iters=steps)
+    _lib.profile_enable(False)
+    prof = _lib.profile_read()
+    _lib.profile_reset()
+    rec = {"workload": wl["name"], "ms_per_pass": ms, "value": B * A * X * X / (ms * 1e-3) / 1e9,
+           "unit": "G pixel-angle updates/s", "dtype": "f32 values, f64 geometry and filter accumulation",
+           "kernels": {k: {"ms_per_launch": v[0] / v[1], "launches": v[1]} for k, v in prof.items()},
+           "tomopy_gridrec": "unavailable (tomopy is not installable in this image)"}
+    try:
+        rec["cpu_baseline"] = cpu_baseline(wl, target_s=8.0, fbp=True)
+    except Exception as exc:
+        rec["cpu_baseline"] = {"value": None, "sample": f"failed: {exc}"}
+    return rec
+
+
+def run_batch(args, ctx, wl):
+    """N = 1, or N > 1 with --shard batch: every rank runs the workload on its own batch (weak scaling)."""
+    torch = ctx.torch
+    import ct_pvae_b200 as cp
+    from ct_pvae_b200 import _lib, ops
+    warm = max(args.warmup, 3)
+    rec, st = batch_record(ctx, wl, args.steps, warm)
+    rec["steps"] = args.steps
+    B, X, A, P = wl["B"], wl["X"], wl["A"], st["P"]
+
+    side = {}
+    if ctx.rank == 0 and not args.no_side_legs:
+        nid = ops.INTERP["nearest"]
+        plan, img, cot, iid, mid = st["plan"], st["img"], st["cot"], st["iid"], st["mid"]
+        side["fwd_nearest_ms"] = best_ms(ctx, lambda: ops.radon_forward(img, plan, nid))
+        side["adj_exact_nearest_ms"] = best_ms(ctx, lambda: ops.radon_adjoint(cot, plan, nid, mid))
+        side["adj_tf_compat_bilinear_ms"] = best_ms(ctx, lambda: ops.radon_adjoint(cot, plan, iid, ops.ADJOINT["tf_compat"]))
+        fplan = _lib.get_fbp_plan(st["theta"], P, X, X, cp.get_fourier_filter(P, "ramp"), ctx.local)
+        side["fbp_ms"] = best_ms(ctx, lambda: ops.fbp(cot, fplan))
+        side["fbp_gupdates_per_s"] = B * A * X * X / (side["fbp_ms"] * 1e-3) / 1e9
+        side["fwd_nearest_gray_sums_per_s"] = B * A * P / (side["fwd_nearest_ms"] * 1e-3) / 1e9
+    if not args.no_side_legs and not args.no_train_leg and (ctx.rank == 0 or ctx.world > 1):
+        try:
+            leg = vae_training_leg(ctx.dev, seed=ctx.rank, world=ctx.world)
+            if ctx.rank == 0:
+                side["vae_train"] = leg
+        except Exception as exc:  # the restated VAE is a caller, never a reason to lose the headline
+            side["vae_train"] = {"error": repr(exc)[:200]}
+    ctx.sync_all()
+
+    e2e = e2e_batch(ctx, wl, st, args.steps)
+    others = {}
+    if not args.no_side_legs:
+        try:
+            others["e2e_pageable_numpy"] = e2e_batch(ctx, wl, st, max(3, args.steps // 5), numpy_inputs=True)
+        except Exception as exc:
+            others["e2e_pageable_numpy"] = {"error": repr(exc)[:200]}
+    del st
+    torch.cuda.empty_cache()
+    # the other BASELINE configurations, measured in the same run
+    if not args.no_side_legs:
+        for key in ("c2", "c4"):
+            if key != args.workload and args.workload != "c5":
+                try:
+                    r2, st2 = batch_record(ctx, WORKLOADS[key], max(10, args.steps // 2), 3)
+                    r2["workload"] = WORKLOADS[key]["name"]
+                    r2["smem_roofline"] = smem_rooflines(r2, WORKLOADS[key], WORKLOADS[key]["A"], r2["clocks"])
+                    r2["e2e"] = e2e_batch(ctx, WORKLOADS[key], st2, max(5, args.steps // 5))
+                    del st2
+                    torch.cuda.empty_cache()
+                    others[key] = r2
+                except Exception as exc:
+                    others[key] = {"error": repr(exc)[:300]}
+        if ctx.rank == 0:
+            try:
+                others["c5"] = c5_record(ctx)
+            except Exception as exc:
+                others["c5"] = {"error": repr(exc)[:300]}
+        ctx.sync_all()
+
+    if ctx.rank == 0:
+        kern = rec["kernels"]
         fwd_ms = kern.get("ctr_fwd_kernel", {}).get("ms_per_launch")
         adj_ms = kern.get("ctr_bp_kernel<exact>", {}).get("ms_per_launch")
-        sm_hz = (clocks or {}).get("sm_mhz") or 1965.0
-        smem_peak = 148 * 128 * sm_hz * 1e6 / 1e9     # GB/s of shared-memory reads at the sampled clock
-        extra = {
-            "kernels": kern,
-            "side_legs": side,
-            "fwd_gray_sums_per_s": (B * A_loc * P / (fwd_ms * 1e-3) / 1e9) if fwd_ms else None,
-            "adjoint_gupdates_per_s": (B * A_loc * X * X / (adj_ms * 1e-3) / 1e9) if adj_ms else None,
-            # binding on-chip limit of the forward gather: 16 B of shared memory per in-support bilinear sample
-            # same for the exact adjoint: 3 candidate bins x 4 B of shared memory per pixel-angle update and image
-            "adj_smem_roofline": ({"achieved_GBs": 12.0 * B * A_loc * X * X / (adj_ms * 1e-3) / 1e9, "peak_GBs": smem_peak,
-                                   "frac": 12.0 * B * A_loc * X * X / (adj_ms * 1e-3) / 1e9 / smem_peak} if adj_ms else None),
-            "fwd_smem_roofline": ({"achieved_GBs": 16.0 * B * A_loc * (X + 1) ** 2 / (fwd_ms * 1e-3) / 1e9,
-                                   "peak_GBs": smem_peak, "frac": 16.0 * B * A_loc * (X + 1) ** 2 / (fwd_ms * 1e-3) / 1e9 / smem_peak}
-                                  if fwd_ms else None),
-        }
+        extra = {"kernels": kern, "plan": rec["plan"], "side_legs": side,
+                 "fwd_gray_sums_per_s": (B * A * P / (fwd_ms * 1e-3) / 1e9) if fwd_ms else None,
+                 "adjoint_gupdates_per_s": (B * A * X * X / (adj_ms * 1e-3) / 1e9) if adj_ms else None,
+                 "smem_roofline": smem_rooflines(rec, wl, A, rec["clocks"])}
+        extra.update(others)
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if angle_mode else "weak",
+            "metric": METRIC, "value": rec["value"], "unit": UNIT, "n_gpus": ctx.world, "steps": args.steps, "warmup": warm,
+            "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic foam (unit disk, random circular pores), random cotangents",
             "config": {"workload": wl["name"], "interpolation": INTERP, "adjoint": "exact", "B_per_gpu": B, "X": X, "Y": X,
-                       "A": A, "P": P, "sharding": ("angle/" + args.angle_collective) if angle_mode else "batch",
+                       "A": A, "P": P, "sharding": "batch" if ctx.world > 1 else "none (one GPU)",
                        "l2": "flushed (256 MiB memset) between timed steps"},
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": ncu_traffic(args.workload, dom[0]) if not angle_mode else None,
-                         "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes,
-                         "note": "gather/issue-bound stencil: HBM fraction is small by construction (SURVEY 8d); see extra.fwd_smem_roofline"},
+            "clocks": rec["clocks"],
+            "e2e": {k: e2e[k] for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")},
+            "gpu_launches": int(rec["launches"]),
+            "roofline": roofline_of(rec, wl, A, args.workload),
             "extra": extra,
         }
-        if world == 1 and not args.no_cpu_baseline:
+        line["extra"]["e2e_detail"] = e2e
+        if ctx.world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_baseline(wl)
             except Exception as exc:  # the checker library is optional for the GPU numbers
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": f"failed: {exc}"}
-        if json_fd is None:
-            print(json.dumps(line), flush=True)
-        else:
-            sys.stdout.flush()
-            os.write(json_fd, (json.dumps(line) + "\n").encode())
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        ctx.emit(line)
+
+
+def run_angle(args, ctx, wl):
+    """N > 1, --shard angle (default): BASELINE configs[3]'s angle-sharded mode, strong scaling."""
+    torch, dist = ctx.torch, ctx.dist
+    from ct_pvae_b200 import _lib, ops, sharding
+    B, X, A = wl["B"], wl["X"], wl["A"]
+    theta = np.linspace(0, np.pi, A, endpoint=False)
+    op = sharding.AngleShardedRadon(theta, X, X, True, B, ctx.dev, interpolation=INTERP, adjoint="exact", algo=args.angle_algo)
+    P, A_loc = op.plan.W, op.A_local
+    img = synthetic_foam_torch(B, X, ctx.dev, seed=0)                      # every rank holds all B images
+    # the SAME full cotangent on every rank (seeded), of which the rank uses its angle block
+    gen = torch.Generator(device=ctx.dev).manual_seed(1)
+    cot_full = torch.rand((B, A, P), device=ctx.dev, generator=gen)
+    cot = cot_full[:, op.a_lo:op.a_hi].contiguous()
+
+    # ---- parity of the exchange step (runs on whatever hardware times it): the reduced back-projection of this
+    # rank's images against a single-rank adjoint of the same cotangent over ALL angles
+    full_plan = _lib.get_plan(theta, X, X, True, ctx.local)
+    own = torch.as_tensor(op.owned_images(), device=ctx.dev)
+    want = ops.radon_adjoint(cot_full.index_select(0, own).contiguous(), full_plan, op.iid, op.mid)
+    got = op.adjoint(cot)
+    parity = float((got.double() - want.double()).norm() / want.double().norm())
+    ok = torch.tensor([1.0 if parity <= 1e-6 else 0.0], device=ctx.dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    worst = ctx.max_over_ranks(parity)
+    if float(ok.item()) != 1.0:
+        raise SystemExit(f"angle-sharded adjoint differs from the single-rank adjoint: rel-L2 {worst:.3e} > 1e-6")
+    # forward blocks are disjoint rows of the single-rank sinogram: check this rank's block on a few images
+    s_blk = op.forward(img[:32])
+    s_ref = ops.radon_forward(img[:32], full_plan, op.iid)[:, op.a_lo:op.a_hi]
+    fwd_par = ctx.max_over_ranks(float((s_blk.double() - s_ref.double()).norm() / s_ref.double().norm()))
+    if fwd_par > 1e-6:
+        raise SystemExit(f"angle-sharded forward block differs from the single-rank rows: rel-L2 {fwd_par:.3e}")
+    del cot_full, want, got, s_blk, s_ref
+    torch.cuda.empty_cache()
+
+    def step():
+        return op.forward(img), op.adjoint(cot)
+
+    warm = max(args.warmup, 3)
+    ms, prof, launches, clocks, total_ms = timed_steps(ctx, step, args.steps, warm)
+    units = B * A * P                                                     # total work is fixed: strong scaling
+    rec = {"ms_per_step": ms, "kernels": kernel_table(prof, total_ms), "P": P, "steps": args.steps}
+
+    # ---- e2e: host buffers in, host buffers out, through the sharded operator
+    img_h = img.cpu().pin_memory()
+    cot_h = cot.cpu().pin_memory()
+    sino_h = torch.empty((B, A_loc, P), dtype=torch.float32).pin_memory()
+    g_h = torch.empty((B // ctx.world, X, X), dtype=torch.float32).pin_memory()
+    side_stream = torch.cuda.Stream(ctx.dev)
+
+    def e2e_step():
+        cur = torch.cuda.current_stream(ctx.dev)
+        side_stream.wait_stream(cur)
+        with torch.cuda.stream(side_stream):          # cotangent upload under the forward
+            cot_d = cot_h.to(ctx.dev, non_blocking=True)
+        img_d = img_h.to(ctx.dev, non_blocking=True)
+        s = op.forward(img_d)
+        sino_h.copy_(s, non_blocking=True)
+        cur.wait_stream(side_stream)
+        g = op.adjoint(cot_d)
+        g_h.copy_(g, non_blocking=True)
+        cot_d.record_stream(cur)
+        cur.synchronize()
+
+    for _ in range(3):
+        e2e_step()
+    ctx.sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize(ctx.dev)
+    dt = ctx.max_over_ranks(time.perf_counter() - t0)
+    h2d = (img_h.numel() + cot_h.numel()) * 4 * ctx.world
+    d2h = (sino_h.numel() + g_h.numel()) * 4 * ctx.world
+    e2e = {"value": units * args.steps / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "ms_per_step": dt / args.steps * 1e3, "note": "bytes are summed over the ranks (every rank uploads all images)"}
+
+    others = {}
+    if not args.no_side_legs:
+        # the other exchange algorithm, and the batch-sharded (weak-scaling) figures of C2 and C4, for context
+        alt = "nccl" if op.algo == "p2p" else None
+        if alt:
+            try:
+                op2 = sharding.AngleShardedRadon(theta, X, X, True, B, ctx.dev, interpolation=INTERP, adjoint="exact", algo=alt)
+                ms2, _, _, _, _ = timed_steps(ctx, lambda: (op2.forward(img), op2.adjoint(cot)), max(10, args.steps // 2), 3)
+                others[f"angle_sharded_{alt}"] = {"ms_per_step": ms2, "value": units / (ms2 * 1e-3) / 1e9}
+            except Exception as exc:
+                others[f"angle_sharded_{alt}"] = {"error": repr(exc)[:200]}
+        del img, cot
+        torch.cuda.empty_cache()
+        for key in ("c2", "c4"):
+            try:
+                r2, st2 = batch_record(ctx, WORKLOADS[key], max(10, args.steps // 2), 3)
+                r2["workload"] = WORKLOADS[key]["name"] + " (batch-sharded, weak scaling)"
+                del st2
+                torch.cuda.empty_cache()
+                others["batch_sharded_" + key] = {k: r2[k] for k in ("workload", "ms_per_step", "value", "unit")}
+            except Exception as exc:
+                others["batch_sharded_" + key] = {"error": repr(exc)[:200]}
+        if not args.no_train_leg:
+            try:
+                leg = vae_training_leg(ctx.dev, seed=ctx.rank, world=ctx.world)
+                others["vae_train"] = leg
+            except Exception as exc:
+                others["vae_train"] = {"error": repr(exc)[:200]}
+        ctx.sync_all()
+
+    if ctx.rank == 0:
+        extra = {"kernels": rec["kernels"], "plan": op.plan.describe(B), "exchange": op.algo,
+                 "parity": {"adjoint_vs_single_rank_rel_l2": worst, "forward_block_rel_l2": fwd_par, "bar": 1e-6,
+                            "comm_nranks_ok": True},
+                 "smem_roofline": smem_rooflines(rec, wl, A_loc, clocks)}
+        extra.update(others)
+        line = {
+            "metric": METRIC, "value": units / (ms * 1e-3) / 1e9, "unit": UNIT, "n_gpus": ctx.world, "steps": args.steps,
+            "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic foam (unit disk, random circular pores), random cotangents",
+            "config": {"workload": wl["name"], "interpolation": INTERP, "adjoint": "exact", "B": B, "X": X, "Y": X, "A": A, "P": P,
+                       "angles_per_gpu": A_loc, "sharding": f"angle ({op.algo} reduce-scatter of the partial back-projections inside the step)",
+                       "l2": "flushed (256 MiB memset) between timed steps"},
+            "clocks": clocks,
+            "e2e": {k: e2e[k] for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")},
+            "gpu_launches": int(launches),
+            "roofline": roofline_of(rec, wl, A_loc, args.workload, sharded=True),
+            "extra": extra,
+        }
+        line["extra"]["e2e_detail"] = e2e
+        ctx.emit(line)
+
+
+def run_c5(args, ctx, wl):
+    """--workload c5 as the headline: the FBP evaluation pass (one GPU per rank, batch-sharded)."""
+    rec = c5_record(ctx, steps=max(5, args.steps))
+    if ctx.rank == 0:
+        line = {"metric": "FBP Gpixel-angle updates/s", "value": rec["value"] * ctx.world, "unit": rec["unit"], "n_gpus": ctx.world,
+                "steps": max(5, args.steps), "warmup": 3, "ms_per_step": rec["ms_per_pass"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (uniform random sinograms)",
+                "config": {"workload": wl["name"]}, "cpu_baseline": rec.get("cpu_baseline"), "extra": rec}
+        ctx.emit(line)
 
 
 def main():
@@ -485,10 +793,11 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--shard", default="batch", choices=["batch", "angle"])
-    ap.add_argument("--angle-collective", default="all_reduce", choices=["all_reduce", "reduce_scatter"],
-                    help="angle-sharded mode: how the partial back-projections are summed")
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--shard", default="angle", choices=["batch", "angle"],
+                    help="N > 1: angle-sharded (configs[3], strong scaling, default) or batch-sharded (weak scaling)")
+    ap.add_argument("--angle-algo", default="auto", choices=["auto", "p2p", "nccl"],
+                    help="angle-sharded mode: how the partial back-projections are summed (see sharding.AngleShardedRadon)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-side-legs", action="store_true")
     ap.add_argument("--no-train-leg", action="store_true")
@@ -496,8 +805,19 @@ def main():
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, wl)
-    else:
-        run_ours(args, wl)
+        return
+    ctx = Ctx()
+    try:
+        if args.workload == "c5":
+            run_c5(args, ctx, wl)
+        elif ctx.world > 1 and args.shard == "angle":
+            run_angle(args, ctx, wl)
+        else:
+            run_batch(args, ctx, wl)
+    finally:
+        if ctx.world > 1:
+            ctx.dist.barrier()
+            ctx.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

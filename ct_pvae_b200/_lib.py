@@ -62,6 +62,7 @@ SYMBOLS = {
     "ctr_hostpipe_adjoint": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int]),
     "ctr_hostpipe_wait": (_c_int, [_c_void_p]),
     "ctr_hostpipe_done": (_c_int, [_c_void_p]),
+    "ctr_hostpipe_trace": (_c_int, [_c_void_p, _c_int]),
     "ctr_radon_forward_dl": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_void_p]),
     "ctr_radon_adjoint_dl": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p]),
     "ctr_fbp_dl": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),

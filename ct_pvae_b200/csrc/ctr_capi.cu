@@ -226,7 +226,7 @@ int ctr_plan_create(const double* theta, int A, int X, int Y, int pad, int devic
     if (cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || p->sm_count <= 0) p->sm_count = 148;
     p->shape[0].fc = ctr::fwd_config(p->W, p->geom, smem_optin - 2048);
     p->shape[1].fc = ctr::fwd_config_depth(p->W, p->geom, smem_optin - 2048, false);
-    p->shape[2].fc = ctr::fwd_use_rec32() ? ctr::fwd_config_depth(p->W, p->geom, smem_optin - 2048, true) : ctr::FwdConfig{};
+    p->shape[2].fc = ctr::fwd_config_depth(p->W, p->geom, smem_optin - 2048, true);
     if (p->shape[0].fc.R < 1) { delete p; return fail(CTR_EUNSUPPORTED, "ctr_plan_create: image rows too wide for the shared-memory strips"); }
     // CTA columns: chunks of consecutive table entries, strip height and (wide detectors) column windows
     for (int k = 0; k < 3; ++k) {
@@ -234,8 +234,7 @@ int ctr_plan_create(const double* theta, int A, int X, int Y, int pad, int devic
         ctr::FwdConfig& fc = sh.fc;
         size_t strip_bytes = 0;
         if (fc.windowed) {
-            int rmax = 16;
-            if (const char* e = getenv("CTR_FWD_R")) { int v = atoi(e); if (v >= 2 && v <= 31) rmax = v; }
+            const int rmax = 16;   // r1: taller windowed strips only widen the windows (C4: R <= 10 or 3 stages +3 %)
             // widely spaced angles (sparse-angle minibatches): retry with fewer angle slots per CTA
             for (int ns = fc.NS; ns >= 1; ns /= 2) {
                 if (ns != fc.NS) fc = ctr::fwd_config_depth(p->W, p->geom, smem_optin - 2048, k == 2, ns);
@@ -314,8 +313,6 @@ int ctr_plan_tables(const ctr_plan* p, float* fwd, float* inv)
 // (32 images from 17 up, 8/16 from 3 lanes' worth up), else the 4-image records
 static const ctr_plan::Shape& shape_for(const ctr_plan* p, int B)
 {
-    static const bool no_depth = getenv("CTR_FWD_NODEPTH") != nullptr;   // developer switch for A/B timing
-    if (no_depth) return p->shape[0];
     const ctr_plan::Shape& s16 = p->shape[1];
     const ctr_plan::Shape& s32 = p->shape[2];
     const bool ok16 = s16.fc.R >= 1 && B >= 3 * s16.fc.depth, ok32 = s32.fc.R >= 1 && B > 16;
@@ -355,9 +352,10 @@ int ctr_plan_describe(const ctr_plan* p, int B, char* buf, size_t n)
         rlo = std::min(rlo, c.R); rhi = std::max(rhi, c.R);
         if (c.wc > 0) { wlo = std::min(wlo, c.wc); whi = std::max(whi, c.wc); ++nwin; }
     }
-    snprintf(buf, n, "images_per_record=%d windowed=%d window_chunks=%d/%d JW=%d jchunks=%d NS=%d KA=%d stages=%d R=%d..%d wc=%d..%d smem=%zu",
+    snprintf(buf, n, "images_per_record=%d windowed=%d window_chunks=%d/%d JW=%d jchunks=%d NS=%d KA=%d stages=%d R=%d..%d wc=%d..%d smem=%zu "
+             "adjoint_images_per_thread: exact=%d tf_compat=%d",
              ctr::kFwdNB * fc.depth, fc.windowed, nwin, (int)ch.size(), fc.JW, fc.jchunks, fc.NS, fc.KA, fc.stages, rlo, rhi,
-             nwin ? wlo : 0, whi, fc.smem);
+             nwin ? wlo : 0, whi, fc.smem, ctr::bp_nb_for_batch(B, CTR_ADJ_EXACT, p->X, p->Y), ctr::bp_nb_for_batch(B, CTR_ADJ_TF, p->X, p->Y));
     return CTR_OK;
 }
 
@@ -430,11 +428,9 @@ static int forward_impl(const ctr_plan* p, const float* img, float* out, int B, 
     fp.geom[0] = p->geom[0]; fp.geom[1] = p->geom[1];
     fp.rays = p->d_rays;
     fp.chunks = shape_for(p, B).d_chunks;
-    fp.kbins = fc.kbins;
     fp.jwd = fc.JW * fc.lanes;
     fp.ns = fc.NS;
     fp.stages = fc.stages;
-    fp.isync = fc.isync;
 
     const int chunks = (int)shape_for(p, B).chunks.size();
     fp.H = p->H; fp.W = p->W; fp.A = p->A; fp.B = B;
@@ -527,11 +523,11 @@ int ctr_radon_adjoint_scaled(const ctr_plan* p, const float* dsino, float* dimg,
     cudaError_t e;
     ProfScope prof(mode == CTR_ADJOINT_EXACT ? CTR_K_ADJ_EXACT : CTR_K_ADJ_TF, st);
     if (mode == CTR_ADJOINT_EXACT)
-        e = (interp == CTR_INTERP_NEAREST) ? ctr::launch_bp<CTR_ADJ_EXACT, CTR_NEAREST>(bp, st)
-                                           : ctr::launch_bp<CTR_ADJ_EXACT, CTR_BILINEAR>(bp, st);
+        e = (interp == CTR_INTERP_NEAREST) ? ctr::launch_bp<CTR_ADJ_EXACT, CTR_NEAREST>(bp, NBb, st)
+                                           : ctr::launch_bp<CTR_ADJ_EXACT, CTR_BILINEAR>(bp, NBb, st);
     else
-        e = (interp == CTR_INTERP_NEAREST) ? ctr::launch_bp<CTR_ADJ_TF, CTR_NEAREST>(bp, st)
-                                           : ctr::launch_bp<CTR_ADJ_TF, CTR_BILINEAR>(bp, st);
+        e = (interp == CTR_INTERP_NEAREST) ? ctr::launch_bp<CTR_ADJ_TF, CTR_NEAREST>(bp, NBb, st)
+                                           : ctr::launch_bp<CTR_ADJ_TF, CTR_BILINEAR>(bp, NBb, st);
     if (e != cudaSuccess) return fail_cuda(e, "ctr_bp_kernel launch");
     return CTR_OK;
 }
@@ -623,7 +619,7 @@ int ctr_fbp(const ctr_fbp_plan* p, const float* sino, int A, float* recon, int B
     cudaError_t e;
     {
         ProfScope prof(CTR_K_FBP_BP, st);
-        e = ctr::launch_bp<CTR_ADJ_FBP, CTR_BILINEAR>(bp, st);
+        e = ctr::launch_bp<CTR_ADJ_FBP, CTR_BILINEAR>(bp, NBb, st);
     }
     if (e != cudaSuccess) return fail_cuda(e, "ctr_bp_kernel<FBP> launch");
     return CTR_OK;
@@ -650,6 +646,7 @@ struct ctr_hostpipe {
     struct Trace { int kind, n; cudaEvent_t in0, in1, c0, c1, o0, o1; };
     std::vector<Trace> trace;
     cudaEvent_t t0 = nullptr;
+    bool tracing = false;  // ctr_hostpipe_trace
 };
 
 static void hostpipe_free(ctr_hostpipe* hp)
@@ -676,9 +673,7 @@ int ctr_hostpipe_create(const ctr_plan* plan, int chunk, ctr_hostpipe** out)
     ctr_hostpipe* hp = new (std::nothrow) ctr_hostpipe();
     if (!hp) return fail(CTR_EINVAL, "ctr_hostpipe_create: out of host memory");
     hp->plan = plan; hp->device = plan->device; hp->chunk = chunk;
-    // experiment (CTR_HOST_ADJ_MULT): adjoint chunks of mult x chunk images (its kernels need bigger batches to fill the SMs)
-    hp->adj_mult = 1;
-    if (const char* e = getenv("CTR_HOST_ADJ_MULT")) { int v = atoi(e); if (v >= 1 && v <= 8) hp->adj_mult = v; }
+    hp->adj_mult = 1;   // r1: larger adjoint chunks were measured and lost (1.54 vs 1.43 ms per C2 step)
     const int cap = chunk * hp->adj_mult;
     const size_t img_b = (size_t)cap * plan->X * plan->Y * sizeof(float), sino_b = (size_t)cap * plan->A * plan->W * sizeof(float);
     hp->buf_bytes = align_up(std::max(img_b, sino_b), 256);
@@ -729,7 +724,7 @@ static int hostpipe_run(ctr_hostpipe* hp, int kind, const float* in_host, float*
         ctr_hostpipe::Slot& s = hp->slot[hp->seq % ctr_hostpipe::kSlots];
         const bool reused = hp->seq >= ctr_hostpipe::kSlots;
         if (reused) CTR_CUDA(cudaStreamWaitEvent(hp->s_in, s.comp_done, 0));     // staging input consumed
-        static const bool tracing = getenv("CTR_HOSTPIPE_TRACE") != nullptr;
+        const bool tracing = hp->tracing;
         ctr_hostpipe::Trace tr{kind, n, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
         if (tracing) {
             for (cudaEvent_t* ev : {&tr.in0, &tr.in1, &tr.c0, &tr.c1, &tr.o0, &tr.o1}) cudaEventCreate(ev);
@@ -770,14 +765,22 @@ int ctr_hostpipe_adjoint(ctr_hostpipe* hp, const float* dsino_host, float* dimg_
     return hostpipe_run(hp, 1, dsino_host, dimg_host, B, interp, mode, "ctr_hostpipe_adjoint");
 }
 
+int ctr_hostpipe_trace(ctr_hostpipe* hp, int on)
+{
+    if (!hp) return fail(CTR_EINVAL, "ctr_hostpipe_trace: pipe is NULL");
+    std::lock_guard<std::mutex> lk(hp->mu);
+    hp->tracing = on != 0;
+    return CTR_OK;
+}
+
 int ctr_hostpipe_wait(ctr_hostpipe* hp)
 {
     if (!hp) return fail(CTR_EINVAL, "ctr_hostpipe_wait: pipe is NULL");
     DeviceGuard guard(hp->device);
     if (!guard.ok) return fail_cuda(guard.err, "cudaSetDevice");
     CTR_CUDA(cudaStreamSynchronize(hp->s_out));   // every result of every call issued so far is in host memory
+    std::lock_guard<std::mutex> lk(hp->mu);
     if (!hp->trace.empty()) {
-        std::lock_guard<std::mutex> lk(hp->mu);
         for (auto& t : hp->trace) {
             float v[6];
             cudaEvent_t evs[6] = {t.in0, t.in1, t.c0, t.c1, t.o0, t.o1};

@@ -25,7 +25,6 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
-#include <stdlib.h>
 
 #include <atomic>
 
@@ -180,49 +179,14 @@ __global__ void __launch_bounds__(128) ctr_pack_sino_kernel(const float* __restr
 }
 
 // ------------------------------------------------------------------------------------------ K1 forward
-// EXPERIMENT (opt-in, CTR_FWD_ISYNC): i-synchronous march (4-image records): the 8 lanes of a quarter-warp (8 adjacent rays of one
-// angle) take the SAME step index in every trip, a lane sitting out the trips in which that step
-// is not its own.  Their samples are then spaced (cos, sin) <= 1 pixel apart along the packed row
-// instead of 1/cos > 1 as when every lane follows its own row, which removes the wrap-around
-// bank conflicts of an LDS.128 quarter (model: 1.57 -> 1.30 wavefronts per quarter-warp load).
-// Warp-collective: every lane calls it, rays without work pass s.n == 0.
-template <int NB, int INTERP, int REC>
-__device__ __forceinline__ void ctr_march_isync(const float* __restrict__ strip, int Up, float vend, int rbase, int offu,
-                                                const CtrRay& r, CtrRayState& s, float* __restrict__ acc)
-{
-    float mine = (s.n > 0) ? s.fi * s.dfi : 3.0e38f;   // marching coordinate of my next sample (+1 per step)
-    float m = mine;
-    m = fminf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-    m = fminf(m, __shfl_xor_sync(0xffffffffu, m, 2));
-    m = fminf(m, __shfl_xor_sync(0xffffffffu, m, 4));  // the quarter-warp starts at its earliest lane
-    bool live = s.n > 0;                                // may still own samples of this strip
-    while (__any_sync(0xffffffffu, live)) {
-        if (live && mine == m) {
-            CtrSample<INTERP> a;
-            ctr_sample<INTERP>(r, s.pu, s.pv, s.fi, Up, rbase, offu, a);
-            if (a.kvf >= vend) {
-                live = false;                           // the rest of this ray belongs to later strips
-            } else {
-                ctr_gather<NB, INTERP, REC>(strip, Up, a, acc);
-                s.fi += s.dfi;
-                mine += 1.f;
-                live = --s.n > 0;
-            }
-        }
-        m += 1.f;
-    }
-}
-
 struct FwdParams {
     const float* pk[2];     // packed images per class  [G][Vp][Up][NB*DEPTH]
     CtrClassGeom geom[2];
     const CtrRay* rays;     // class-sorted ray table [A]
     const CtrChunk* chunks; // [gridDim.x] rays, class, strip height and column window of every CTA column
     int H, W, A, B;
-    int kbins;              // 1: a thread's KA rays are KA detector bins (JW apart) of ONE angle; 0: KA angles of one bin
     int jwd, ns;            // consumer threads per angle slot (JW bins x DEPTH groups) and angle slots; block = jwd*ns + 32
     int stages;             // strip buffers in the shared-memory ring (2..4)
-    int isync;              // 1: quarter-warps march step-synchronously (4-image records only)
     float* sino;            // [B][A][W]   (EPI 0: ray sums; EPI 1: d loglik / d proj, the adjoint's cotangent)
     // fused measurement log-likelihood epilogue (EPI 1), helper_functions.py:355-368
     const float* mask;      // [B][A_all]
@@ -261,9 +225,7 @@ __global__ void __launch_bounds__(REUSE ? kFwdReuseThreads : kFwdMaxThreads, 1) 
     // 8 images per lane (32-image records): the two 16-byte halves of a lane's block are read in an order
     // that alternates with the ray's parity, which makes every quarter-warp load conflict-free (ctr_ldv8_swz)
     const int swz = (NB == 8) ? (tx & 1) * 4 : 0;
-    // kbins: thread (tx,ty) owns bins tx, tx+JW, .. of angle slot ty (opt-in experiment, see fwd_use_kbins)
-    const bool kb = p.kbins != 0;
-    const int NA = kb ? NS : NS * KA;
+    const int NA = NS * KA;
 
     const int S = p.stages;                                                 // ring depth (<= 4)
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);                 // [S] strip landed (TMA complete_tx)
@@ -340,14 +302,13 @@ __global__ void __launch_bounds__(REUSE ? kFwdReuseThreads : kFwdMaxThreads, 1) 
         }
     } else {
         // ---- consumers.  per-ray state: next step and steps left (coefficients are re-read per strip)
-        const int jb = kb ? jz * (JW * KA) + tx : jz * JW + tx;
-        const int jstep = kb ? JW : 0, lbase = kb ? ty : ty * KA, lstep = kb ? 0 : 1;
+        const int j = jz * JW + tx, lbase = ty * KA;
         float ri[KA];
         int rn[KA];
         float acc[KA][NB];
 #pragma unroll
         for (int q = 0; q < KA; ++q) {
-            const int la = lbase + q * lstep, j = jb + q * jstep;
+            const int la = lbase + q;
             ri[q] = 0.f;
             rn[q] = 0;
             if (la < cnt && j < p.W) {
@@ -368,19 +329,15 @@ __global__ void __launch_bounds__(REUSE ? kFwdReuseThreads : kFwdMaxThreads, 1) 
             const int offu = geom.offu + (ch.wc > 0 ? cst[b] : 0);   // first packed column held by this strip
 #pragma unroll
             for (int q = 0; q < KA; ++q) {
-                const bool isync = (DEPTH == 1) && p.isync && !kb;    // warp-uniform
-                if (isync || rn[q] > 0) {
-                    const int la = min(lbase + q * lstep, NA - 1);    // (slots past cnt carry rn == 0)
-                    const CtrRay r = rays_s[la];
-                    const int j = jb + q * jstep;
+                if (rn[q] > 0) {
+                    const CtrRay r = rays_s[lbase + q];
                     CtrRayState s;
                     s.pu = CTR_MUL(r.u0, (float)j);
                     s.pv = CTR_MUL(r.v0, (float)j);
                     s.fi = ri[q];
                     s.n = rn[q];
                     s.dfi = (r.v1 >= 0.f) ? 1.f : -1.f;
-                    if (isync) ctr_march_isync<NB, INTERP, REC>(strip, Us, vend, rbase, offu, r, s, acc[q]);
-                    else if (REUSE && NB == 8 && INTERP == CTR_BILINEAR) ctr_march_reuse<NB, REC>(strip, Us, vend, rbase, offu, r, s, acc[q], swz);
+                    if (REUSE && NB == 8 && INTERP == CTR_BILINEAR) ctr_march_reuse<NB, REC>(strip, Us, vend, rbase, offu, r, s, acc[q], swz);
                     else ctr_march<NB, INTERP, REC>(strip, Us, vend, rbase, offu, r, s, acc[q], swz);
                     ri[q] = s.fi;
                     rn[q] = s.n;
@@ -396,7 +353,7 @@ __global__ void __launch_bounds__(REUSE ? kFwdReuseThreads : kFwdMaxThreads, 1) 
         for (int n = 0; n < NB; ++n) lsum[n] = 0.f;
 #pragma unroll
         for (int q = 0; q < KA; ++q) {
-            const int la = lbase + q * lstep, j = jb + q * jstep;
+            const int la = lbase + q;
             if (la < cnt && j < p.W) {
                 const int a = rays_s[la].angle;
                 const int ao = (EPI && p.amap) ? p.amap[a] : a;
@@ -657,207 +614,128 @@ __global__ void __launch_bounds__(256) ctr_fbp_filter_kernel(const float* __rest
 
 // ------------------------------------------------------------------------------------------ launchers
 struct FwdConfig {
-    int JW, NS, KA, R, jchunks, depth, kbins, stages, isync;
+    int JW, NS, KA, R, jchunks, depth, stages;
     int lanes;      // lanes per ray (each owns 4 * depth / lanes images of the pixel record)
     int reuse;      // 1: bilinear march keeps the previous bottom row in registers (ctr_march_reuse; 8-image lanes)
     int windowed;   // 1: column-windowed strips, per-chunk R and window (R and smem are filled in by ctr_plan_create)
     size_t smem;
     static constexpr int fixed_bytes(int NA) { return 128 + (NA * (int)sizeof(CtrRay) + 127) / 128 * 128; }
-    int angles_per_cta() const { return kbins ? NS : NS * KA; }
+    int angles_per_cta() const { return NS * KA; }
 };
 
-// r1 measurement: pairing a central with an edge bin per thread (kbins) balances the work per
-// strip but costs more in SIMT efficiency at the shadow edge (C2 0.645 vs 0.600 ms, C4 3.06 vs
-// 2.91 ms), so it stays an opt-in experiment.
-inline int fwd_stages()
-{
-    if (const char* e = getenv("CTR_FWD_STAGES")) { int v = atoi(e); if (v >= 2 && v <= 4) return v; }
-    return 2;
-}
+// Tuning history (r1/r2 measurements, all on B200): two ring stages beat three or four (+3 %), pairing a central
+// with an edge bin per thread lost to SIMT inefficiency at the shadow edge (C2 0.645 vs 0.600 ms), an i-synchronous
+// quarter-warp march lost to its sit-out trips (C4 slice 3.95 vs 2.50 ms), 8-image records on a wide detector split
+// in two were flat.  Those variants are gone from the library; DESIGN.md section 7 keeps the numbers.
+constexpr int kFwdStages = 2;
 
-inline bool fwd_use_kbins()
-{
-    static const bool on = getenv("CTR_FWD_KBINS") != nullptr;
-    return on;
-}
-
-// Shape the forward CTA: JW detector bins x NS angle slots x KA angles per slot, and the
-// largest strip height R whose double buffer fits the shared-memory budget.
-inline FwdConfig fwd_config_depth(int W, const CtrClassGeom geom[2], int smem_budget, bool rec32, int win_ns = 0);
-
+// Shape of the 4-image-record forward CTA (any detector, any batch): JW detector bins x NS angle slots x KA angles
+// per slot, and the largest strip height R whose double buffer fits the shared-memory budget.
 inline FwdConfig fwd_config(int W, const CtrClassGeom geom[2], int smem_budget)
 {
     FwdConfig c{};
     c.depth = 1;
     c.lanes = 1;
-    c.kbins = fwd_use_kbins() ? 1 : 0;
-    // r1 measurement: the i-synchronous march loses (C4 slice 3.95 vs 2.50 ms, nearest 3.81 vs 1.49):
-    // the sit-out trips and the vote per trip cost more issue slots than the conflicts they remove.
-    c.isync = (getenv("CTR_FWD_ISYNC") != nullptr && !c.kbins) ? 1 : 0;
     c.KA = 2;
-    if (c.kbins) {
-        // two bins per thread (tx and tx + JW) of one angle, NS angle slots per CTA
-        c.JW = round_up((W + 1) / 2, 32);
-        if (c.JW > 352) c.JW = 352;   // two bins per thread, consumers <= 736, multiple of 32
-        c.jchunks = (W + c.JW * c.KA - 1) / (c.JW * c.KA);
-        c.NS = (c.JW >= 128) ? 2 : 256 / c.JW;
-        if (c.NS > 8) c.NS = 8;
-    } else {
-        c.JW = round_up(W, 32);
-        if (c.JW > kFwdMaxConsumers) c.JW = kFwdMaxConsumers;
-        c.jchunks = (W + c.JW - 1) / c.JW;
-        c.NS = (c.JW >= 128) ? 1 : 128 / c.JW;
-    }
+    c.JW = round_up(W, 32);
+    if (c.JW > kFwdMaxConsumers) c.JW = kFwdMaxConsumers;
+    c.jchunks = (W + c.JW - 1) / c.JW;
+    c.NS = (c.JW >= 128) ? 1 : 128 / c.JW;
     const int threads = c.JW * c.NS + 32;
     const int ctas_per_sm = threads <= 256 ? 4 : (threads <= 512 ? 2 : 1);
     if (smem_budget > (228 * 1024) / ctas_per_sm - 1024) smem_budget = (228 * 1024) / ctas_per_sm - 1024;
-    // developer overrides for tuning sweeps (tools/sweep_fwd.py); not part of the API
-    if (const char* e = getenv("CTR_FWD_NS")) { int v = atoi(e); if (v >= 1 && v * c.JW <= kFwdMaxConsumers) c.NS = v; }
-    if (const char* e = getenv("CTR_FWD_KA")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4) c.KA = v; }
-    if (const char* e = getenv("CTR_FWD_SMEM")) { int v = atoi(e); if (v >= 16384 && v < smem_budget) smem_budget = v; }
-    const int NA = c.NS * c.KA;   // upper bound on angles per CTA in either mapping
-    const int fixed = 128 + round_up(NA * (int)sizeof(CtrRay), 128);
+    const int fixed = FwdConfig::fixed_bytes(c.NS * c.KA);
     const int Upmax = geom[0].Up > geom[1].Up ? geom[0].Up : geom[1].Up;
     const int Vpmax = geom[0].Vp > geom[1].Vp ? geom[0].Vp : geom[1].Vp;
     const int row_bytes = Upmax * kFwdNB * 4;
-    c.stages = fwd_stages();
+    c.stages = kFwdStages;
     int rows = (smem_budget - fixed) / (c.stages * row_bytes);   // rows per buffer = R + 1
     if (rows > Vpmax) rows = Vpmax;
     if (rows > 33) rows = 33;   // bigger strips only lengthen the un-overlapped first load
-    if (const char* e = getenv("CTR_FWD_R")) { int v = atoi(e); if (v >= 1 && v + 1 <= rows) rows = v + 1; }
     c.R = rows - 1;
     if (c.R < 1) c.R = 0;  // caller treats 0 as "image too wide for the strip buffers"
     c.smem = (size_t)fixed + (size_t)c.stages * (size_t)(c.R + 1) * row_bytes;
     return c;
 }
 
-// Depth-first shapes: DEPTH image groups of 4 per pixel record, CTAs of JW detector bins x
-// DEPTH groups (<= 736 consumer threads + the producer warp, 85 registers each).  DEPTH = 4
-// (16 images, two angles per thread) for detectors of <= 184 bins, DEPTH = 2 (8 images) up to 368 bins; DEPTH = 8 (32 images, conflict-free, four angles per
-// thread, detector split into chunks of <= 128 bins) is selectable for experiments.
+// Depth-first shapes: several image groups of 4 share one pixel record, the lanes of a quarter-warp are
+// (rays) x (groups).  rec32 == false: 16-image records with 4 lanes per ray (detectors of <= 184 bins) or 8-image
+// records with 2 lanes per ray (<= 368 bins).  rec32 == true: 32-image records, 4 lanes per ray x 8 images per lane,
+// parity-swizzled loads (conflict-free quarter-warps).  Detectors too wide for whole-row strips get COLUMN-WINDOWED
+// strips: the detector is cut into chunks of JW bins, NS angle slots share a CTA (neighbouring angles need nearly the
+// same window), and every strip holds only the columns those rays cross; R, the windows and the shared-memory size
+// then depend on the angles and are filled in by ctr_plan_create (ctr_h_build_chunks).
+// win_ns > 0 forces the number of angle slots of the windowed shape (the plan retries with fewer slots when the
+// angles sharing a CTA are too far apart for a window that fits).
 constexpr int kFwdDepth = 4;
-// 32-image records, 8 images per lane with parity-swizzled loads (conflict-free quarter-warps): default
-// where four lanes per ray fit; CTR_FWD_REC32=0 keeps the 16-image records (4 images per lane)
-inline bool fwd_use_rec32()
-{
-    const char* e = getenv("CTR_FWD_REC32");
-    return e ? atoi(e) != 0 : true;
-}
-
-// win_ns > 0 forces the number of angle slots of the column-windowed shape (the plan retries with fewer
-// slots when the angles sharing a CTA are too far apart for a window that fits)
-inline FwdConfig fwd_config_depth(int W, const CtrClassGeom geom[2], int smem_budget, bool rec32, int win_ns)
+inline FwdConfig fwd_config_depth(int W, const CtrClassGeom geom[2], int smem_budget, bool rec32, int win_ns = 0)
 {
     FwdConfig c{};
-    // four lanes per ray while they fit the CTA (P <= 184), else two (P <= 368)
     c.lanes = (round_up(W, 8) * kFwdDepth <= kFwdMaxConsumers) ? kFwdDepth : 2;
-    c.stages = 2;
-    if (const char* e = getenv("CTR_FWD_DEPTH")) { int v = atoi(e); if (v == 2 || v == 4) c.lanes = v; }
+    c.stages = kFwdStages;
     c.depth = c.lanes;                                   // 4 images per lane ...
     if (rec32) {                                         // ... or 8 (32-image records), four lanes per ray only
         if (c.lanes != 4 && round_up(W, 8) * c.lanes <= kFwdMaxConsumers) return c;   // R = 0: mid-size detectors keep 8-image records
         c.lanes = 4;
         c.depth = 8;
     }
-    c.kbins = (fwd_use_kbins() && c.depth == 4) ? 1 : 0;
     c.NS = 1;
     c.KA = 2;
     c.R = 0;
     c.smem = 0;
     c.jchunks = 1;
-    if (c.kbins) {
-        c.JW = round_up((W + 1) / 2, 8);      // bins tx and tx + JW of one angle per thread, two angle slots
-        c.NS = 2;
-        if (c.JW * c.lanes * c.NS > kFwdMaxConsumers) return c;   // R = 0: not available for this detector width
-    } else {
-        c.JW = round_up(W, 32 / c.lanes);
-        // CTR_FWD_FORCE_WINDOW: experiment, column-windowed shape also where whole rows fit (narrow detectors)
-        if (c.JW * c.lanes > kFwdMaxConsumers || (rec32 && getenv("CTR_FWD_FORCE_WINDOW") != nullptr)) {
-            if (c.lanes == 2 && getenv("CTR_FWD_WIDE_DEPTH") != nullptr) {
-                // experiment: 8-image records on a wide detector, split in chunks of 368 bins that each
-                // stream the full-width strips, four angles per thread to pay for the re-reads
-                c.JW = kFwdMaxConsumers / 2;
-                c.jchunks = (W + c.JW - 1) / c.JW;
-                c.KA = 4;
-            } else {
-                // wide detector: 16/32-image records with COLUMN-WINDOWED strips.  The detector is cut into chunks
-                // of JW bins, NS angle slots share a CTA (neighbouring angles need nearly the same window), and
-                // every strip holds only the columns those rays cross.  R, the windows and the shared-memory
-                // size depend on the angles: ctr_plan_create fills them in (ctr_h_build_chunks).
-                if (getenv("CTR_FWD_NOWINDOW") != nullptr) return c;
-                c.lanes = 4;
-                c.depth = rec32 ? 8 : 4;
-                c.NS = rec32 ? 4 : 2;   // r1 sweep at 64 x 512^2 x 720: 6.60 ms (NS 4) vs 6.80 (2) / 6.63 (8) with 32-image records
-                if (const char* e = getenv("CTR_FWD_WIN_NS")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) c.NS = v; }
-                if (win_ns > 0) c.NS = win_ns;
-                c.KA = 2;
-                // r1: the vertical-reuse march pays with the tall strips of the windowed shape (C4 6.57 -> 6.24 ms),
-                // not with the 5-row strips of whole-row 32-image records (C2 0.521 -> 0.532 ms)
-                c.reuse = (rec32 && getenv("CTR_FWD_NOREUSE") == nullptr) ? 1 : 0;
-                const int maxc = c.reuse ? kFwdReuseThreads - 32 : kFwdMaxConsumers;
-                { const int q = c.NS >= 4 ? 2 : 8 / c.NS; c.JW = maxc / (c.lanes * c.NS) / q * q; }   // whole warps per CTA
-                if (const char* e = getenv("CTR_FWD_WIN_JW")) { int v = atoi(e); if (v >= 8 && v % 8 == 0 && v * c.lanes * c.NS <= maxc) c.JW = v; }
-                c.jchunks = (W + c.JW - 1) / c.JW;
-                c.JW = round_up((W + c.jchunks - 1) / c.jchunks, c.NS >= 4 ? 2 : 8 / c.NS);   // even out the detector chunks (whole warps per CTA)
-                c.stages = fwd_stages();
-                c.windowed = 1;
-                return c;   // R == 0 until the plan has sized the windows
-            }
-        }
+    c.JW = round_up(W, 32 / c.lanes);
+    if (c.JW * c.lanes > kFwdMaxConsumers) {
+        c.lanes = 4;
+        c.depth = rec32 ? 8 : 4;
+        c.NS = rec32 ? 4 : 2;   // r1 sweep at 64 x 512^2 x 720: 6.60 ms (NS 4) vs 6.80 (2) / 6.63 (8) with 32-image records
+        if (win_ns > 0) c.NS = win_ns;
+        // r1: the vertical-reuse march pays with the tall strips of the windowed shape (C4 6.57 -> 6.24 ms),
+        // not with the 5-row strips of whole-row 32-image records (C2 0.521 -> 0.532 ms)
+        c.reuse = rec32 ? 1 : 0;
+        const int maxc = c.reuse ? kFwdReuseThreads - 32 : kFwdMaxConsumers;
+        { const int q = c.NS >= 4 ? 2 : 8 / c.NS; c.JW = maxc / (c.lanes * c.NS) / q * q; }   // whole warps per CTA
+        c.jchunks = (W + c.JW - 1) / c.JW;
+        c.JW = round_up((W + c.jchunks - 1) / c.jchunks, c.NS >= 4 ? 2 : 8 / c.NS);   // even out the detector chunks
+        c.windowed = 1;
+        return c;   // R == 0 until the plan has sized the windows
     }
-    c.reuse = 0;   // whole-row strips: the reuse march needs 96 registers, i.e. CTAs of <= 640 threads (r1: 0.532 vs 0.521 ms with 80)
-    const int fixed = 128 + round_up(c.NS * c.KA * (int)sizeof(CtrRay), 128);
+    c.reuse = 0;   // whole-row strips: the reuse march needs 96 registers, i.e. CTAs of <= 640 threads
+    const int fixed = FwdConfig::fixed_bytes(c.NS * c.KA);
     const int Upmax = geom[0].Up > geom[1].Up ? geom[0].Up : geom[1].Up;
     const int Vpmax = geom[0].Vp > geom[1].Vp ? geom[0].Vp : geom[1].Vp;
     const int row_bytes = Upmax * kFwdNB * c.depth * 4;
-    c.stages = fwd_stages();
     int rows = (smem_budget - fixed) / (c.stages * row_bytes);
     if (rows > Vpmax) rows = Vpmax;
     if (rows > 33) rows = 33;
-    if (const char* e = getenv("CTR_FWD_R")) { int v = atoi(e); if (v >= 1 && v + 1 <= rows) rows = v + 1; }
     c.R = rows - 1;
     if (c.R < 1) c.R = 0;
     c.smem = (size_t)fixed + (size_t)c.stages * (size_t)(c.R + 1) * row_bytes;
     return c;
 }
 
+template <int NBL, int INTERP, int EPI, int LANES, int REUSE>
+inline cudaError_t launch_fwd_one(const FwdParams& p, const FwdConfig& c, dim3 grid, dim3 block, cudaStream_t st)
+{
+    cudaError_t e = cudaFuncSetAttribute(ctr_fwd_kernel<NBL, 2, INTERP, EPI, LANES, REUSE>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+    if (e != cudaSuccess) return e;
+    ctr_fwd_kernel<NBL, 2, INTERP, EPI, LANES, REUSE><<<grid, block, c.smem, st>>>(p);
+    launch_counter()++;
+    return cudaGetLastError();
+}
+
+// G counts pixel records (super-groups of kFwdNB * depth images) along the batch
 template <int INTERP, int EPI>
 inline cudaError_t launch_fwd_ka(const FwdParams& p, const FwdConfig& c, int G, int chunks, cudaStream_t st)
 {
     dim3 grid(chunks, c.jchunks, G), block(c.JW * c.lanes * c.NS + 32);   // + the producer warp
-    cudaError_t e;
-#define CTR_FWD_DEEP(NBL_, KA_, LANES_, ...)                                                                                       \
-    {                                                                                                                              \
-        e = cudaFuncSetAttribute(ctr_fwd_kernel<NBL_, KA_, INTERP, EPI, LANES_, ##__VA_ARGS__>,                                    \
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);                                        \
-        if (e != cudaSuccess) return e;                                                                                            \
-        ctr_fwd_kernel<NBL_, KA_, INTERP, EPI, LANES_, ##__VA_ARGS__><<<grid, block, c.smem, st>>>(p);                             \
-        launch_counter()++;                                                                                                        \
-        return cudaGetLastError();                                                                                                 \
-    }
-    // G counts super-groups of kFwdNB * depth images here
-    if (c.lanes == 4 && c.depth == 8 && c.reuse && INTERP == CTR_BILINEAR) CTR_FWD_DEEP(8, 2, 4, 1)   // + vertical reuse
-    if (c.lanes == 4 && c.depth == 8) CTR_FWD_DEEP(8, 2, 4)         // 32-image records, 8 images per lane
-    if (c.lanes == 4) CTR_FWD_DEEP(kFwdNB, 2, 4)                    // 16-image records
-    if (c.lanes == 2 && c.KA == 4) CTR_FWD_DEEP(kFwdNB, 4, 2)
-    if (c.lanes == 2) CTR_FWD_DEEP(kFwdNB, 2, 2)
-#undef CTR_FWD_DEEP
-#define CTR_FWD_CASE(KA_)                                                                                                  \
-    case KA_:                                                                                                              \
-        e = cudaFuncSetAttribute(ctr_fwd_kernel<kFwdNB, KA_, INTERP, EPI, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                 (int)c.smem);                                                                             \
-        if (e != cudaSuccess) return e;                                                                                    \
-        ctr_fwd_kernel<kFwdNB, KA_, INTERP, EPI, 1><<<grid, block, c.smem, st>>>(p);                                       \
-        break;
-    switch (c.KA) {
-        CTR_FWD_CASE(1)
-        CTR_FWD_CASE(2)
-        CTR_FWD_CASE(4)
-        default: return cudaErrorInvalidValue;
-    }
-#undef CTR_FWD_CASE
-    launch_counter()++;
-    return cudaGetLastError();
+    if (c.KA != 2) return cudaErrorInvalidValue;
+    if (c.lanes == 4 && c.depth == 8 && c.reuse && INTERP == CTR_BILINEAR) return launch_fwd_one<8, INTERP, EPI, 4, 1>(p, c, grid, block, st);
+    if (c.lanes == 4 && c.depth == 8) return launch_fwd_one<8, INTERP, EPI, 4, 0>(p, c, grid, block, st);   // 32-image records
+    if (c.lanes == 4) return launch_fwd_one<kFwdNB, INTERP, EPI, 4, 0>(p, c, grid, block, st);             // 16-image records
+    if (c.lanes == 2) return launch_fwd_one<kFwdNB, INTERP, EPI, 2, 0>(p, c, grid, block, st);             // 8-image records
+    return launch_fwd_one<kFwdNB, INTERP, EPI, 1, 0>(p, c, grid, block, st);                               // 4-image records
 }
 
 inline size_t bp_smem_bytes(int win, int NB, int AB)
@@ -869,14 +747,13 @@ inline size_t bp_smem_bytes(int win, int NB, int AB)
 // all images of a thread, so big batches take 32 images per thread, medium ones 16 (both on
 // 32x8-pixel tiles), tiny ones 8 on 32x16 tiles (fewer idle accumulator lanes).
 // (r1: 32 images pay off only for the geometry-heavy exact adjoint -- C4 5.63 -> 4.64 ms;
-// the 2-tap TF-compat and FBP gathers lose occupancy and stay at 16.)
+// the 2-tap FBP gather loses occupancy and stays at 16; three resident 32-image CTAs or 32x4 / 32x5 / 32x6
+// tiles were measured and lost: 0.47 / 0.377 / 0.371 / 0.376 vs 0.371 ms at C2.)
 // X, Y: when the 32-image shape would not even give every SM one CTA (small images x small batch, e.g. the
 // 32..64-image chunks of the host pipeline at 128^2) the 16-image shape has twice the CTAs: 0.105 vs 0.141 ms
 // at 32 x 128^2 x 180.  Pass X = 0 for "size for the worst case" (workspace queries).
 inline int bp_nb_for_batch(int B, int mode, int X = 0, int Y = 0)
 {
-    static const int forced = getenv("CTR_BP_NB") ? atoi(getenv("CTR_BP_NB")) : 0;   // developer override
-    if (forced == 8 || forced == 16 || forced == 32) return forced;
     if (B <= 8) return 8;
     if (B < 24 || mode == CTR_ADJ_FBP) return 16;
     const long long ctas32 = (X > 0 && Y > 0) ? (long long)((Y + kBpTW - 1) / kBpTW) * ((X + 7) / 8) * ((B + 31) / 32) : -1;
@@ -902,18 +779,9 @@ inline cudaError_t launch_bp_cfg(BpParams p, cudaStream_t st)
 }
 
 template <int MODE, int INTERP>
-inline cudaError_t launch_bp(const BpParams& p, cudaStream_t st)
+inline cudaError_t launch_bp(const BpParams& p, int nb, cudaStream_t st)
 {
-    const int nb = bp_nb_for_batch(p.B, MODE, p.X, p.Y);
-    if (nb == 32) {
-        static const bool small_tiles = getenv("CTR_BP_TH4") != nullptr;   // developer switch
-        if (small_tiles) return launch_bp_cfg<32, 4, 4, MODE, INTERP>(p, st);
-        static const bool occ3 = getenv("CTR_BP_OCC3") != nullptr;          // developer switch: 3 CTAs/SM (85 regs)
-        if (occ3) return launch_bp_cfg<32, 8, 3, MODE, INTERP>(p, st);
-        // (r1: 32 x 5 / 32 x 6 pixel tiles with three CTAs per SM -- finer tiles against the 1.73-wave grid of
-        // C2 -- measured 0.371 / 0.376 vs 0.374 ms at C2 and 5.12 / 4.90 vs 4.65 ms at C4: not kept)
-        return launch_bp_cfg<32, 8, 2, MODE, INTERP>(p, st);
-    }
+    if (nb == 32) return launch_bp_cfg<32, 8, 2, MODE, INTERP>(p, st);
     if (nb == 16) return launch_bp_cfg<16, 8, 3, MODE, INTERP>(p, st);
     return launch_bp_cfg<8, 16, 2, MODE, INTERP>(p, st);
 }

@@ -32,6 +32,14 @@ def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def _check_angles_cover_ranks(num_angles: int, world: int) -> None:
+    """Angle sharding needs at least one angle per rank.  The check depends only on (A, world), so EVERY rank raises
+    together -- before any local work or collective -- instead of the empty ranks failing alone while the others
+    block in NCCL."""
+    if num_angles < world:
+        raise ValueError(f"angle sharding needs at least one angle per rank: {num_angles} angles over {world} ranks")
+
+
 def _world(group=None) -> Tuple[int, int]:
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(group), dist.get_world_size(group)
@@ -54,6 +62,7 @@ def project_angle_sharded(project: Callable, images: torch.Tensor, theta, group=
     ``gather`` all-gathers the row-blocks into the full [B, A, P(,1)]."""
     rank, world = _world(group)
     theta = np.asarray(theta)
+    _check_angles_cover_ranks(theta.shape[0], world)
     lo, hi = shard_range(theta.shape[0], rank, world)
     local = project(images, theta[lo:hi])
     if not gather or world == 1:
@@ -68,12 +77,11 @@ def backproject_angle_sharded(backproject: Callable, sinogram_local: torch.Tenso
     all-reduce (result replicated) or reduce-scatter over the batch (``scatter``)."""
     rank, world = _world(group)
     theta = np.asarray(theta)
+    _check_angles_cover_ranks(theta.shape[0], world)
     lo, hi = shard_range(theta.shape[0], rank, world)
     if sinogram_local.shape[1] != hi - lo:
         raise ValueError("sinogram_local does not match this rank's angle block")
-    partial = backproject(sinogram_local, theta[lo:hi]) if hi > lo else None
-    if partial is None:  # rank owns no angle: contributes zeros of the right shape
-        raise ValueError("angle-sharded back-projection needs at least one angle per rank")
+    partial = backproject(sinogram_local, theta[lo:hi])
     if world == 1:
         return partial
     if not scatter:
@@ -124,3 +132,107 @@ def radon_adjoint_angle_sharded(sinogram_local, theta, x_size, y_size, pad=True,
 
     fn = lambda s, th: backproject(s, th, x_size, y_size, pad=pad, interpolation=interpolation, adjoint=adjoint)  # noqa: E731
     return backproject_angle_sharded(fn, sinogram_local, theta, group, scatter)
+
+
+class AngleShardedRadon:
+    """The angle-sharded operator pair of SURVEY 8e on this rank's GPU (BASELINE configs[3]).
+
+    Every rank holds all ``B`` images and the contiguous angle block ``shard_range(A, rank, world)``:
+
+    * ``forward(img [B,X,Y])`` -> this rank's sinogram rows ``[B, A_local, W]`` (disjoint blocks, no exchange);
+    * ``adjoint(dsino_local [B, A_local, W])`` -> the back-projection summed over ALL ranks' angle blocks, left
+      batch-sharded: rank ``r`` returns images ``shard_range(B, r, world)`` as ``[B/world, X, Y]``
+      (``replicate=True``: the full ``[B,X,Y]`` on every rank).  This sum is the path's only exchange step.
+
+    ``algo`` picks how the partial back-projections are summed:
+      "nccl"  one ``reduce_scatter`` (``all_reduce`` when replicating) per image group, issued as soon as the
+              group's adjoint kernel has been enqueued, so that it runs under the next group's kernel;
+      "p2p"   the adjoint kernel's epilogue stores every pixel straight into its owner's exchange buffer over
+              NVLink peer memory; a flag barrier and one fixed-order sum follow (``ctr_radon_adjoint_sharded``);
+      "auto"  "p2p" when the peer buffers could be mapped, else "nccl".
+    """
+
+    def __init__(self, theta, X: int, Y: int, pad: bool, B: int, device: torch.device, interpolation: str = "bilinear",
+                 adjoint: str = "exact", group=None, algo: str = "auto"):
+        from . import _lib, ops
+
+        self.rank, self.world = _world(group)
+        self.group, self.B, self.X, self.Y = group, int(B), int(X), int(Y)
+        theta = np.ascontiguousarray(np.asarray(theta, np.float64).reshape(-1))
+        _check_angles_cover_ranks(theta.shape[0], self.world)
+        if self.B % self.world != 0:
+            raise ValueError("the batch must divide evenly over the ranks (the result is left batch-sharded)")
+        self.a_lo, self.a_hi = shard_range(theta.shape[0], self.rank, self.world)
+        self.theta_local = theta[self.a_lo:self.a_hi]
+        self.device = device
+        self.plan = _lib.get_plan(self.theta_local, self.X, self.Y, bool(pad), device.index or 0)
+        self.iid, self.mid = ops.INTERP[interpolation], ops.ADJOINT[adjoint]
+        self.comm = None
+        if algo in ("auto", "p2p") and self.world > 1:
+            try:
+                from . import comm as _comm
+                self.comm = _comm.PeerComm(self.B * self.X * self.Y * 4, device, group)
+            except Exception:
+                if algo == "p2p":
+                    raise
+        self.algo = "p2p" if self.comm is not None else "nccl"
+        self._side = torch.cuda.Stream(device) if device.type == "cuda" else None
+
+    @property
+    def A_local(self) -> int:
+        return self.a_hi - self.a_lo
+
+    def forward(self, img: torch.Tensor) -> torch.Tensor:
+        from . import ops
+        return ops.radon_forward(img, self.plan, self.iid)
+
+    def adjoint(self, dsino_local: torch.Tensor, replicate: bool = False) -> torch.Tensor:
+        from . import ops
+        if dsino_local.shape[0] != self.B or dsino_local.shape[1] != self.A_local:
+            raise ValueError("dsino_local must be [B, A_local, W] for this rank's angle block")
+        if self.world == 1:
+            return ops.radon_adjoint(dsino_local, self.plan, self.iid, self.mid)
+        if self.algo == "p2p":
+            return self.comm.adjoint_sharded(self.plan, dsino_local, self.iid, self.mid, replicate)
+        return self._adjoint_nccl(dsino_local, replicate)
+
+    def _adjoint_nccl(self, dsino_local: torch.Tensor, replicate: bool) -> torch.Tensor:
+        """Image groups of 32 (the adjoint kernel's full-efficiency unit) that also split evenly over the ranks:
+        group k is summed on the side stream while group k+1's kernel runs."""
+        from . import ops
+        B, world = self.B, self.world
+        step = 32 * world // np.gcd(32, world)
+        if B % step != 0 or B // step < 2:
+            step = B
+        per = step // world
+        out = torch.empty((B if replicate else B // world, self.X, self.Y), dtype=torch.float32, device=dsino_local.device)
+        cur = torch.cuda.current_stream(dsino_local.device)
+        keep = []
+        for k, lo in enumerate(range(0, B, step)):
+            g = ops.radon_adjoint(dsino_local[lo:lo + step], self.plan, self.iid, self.mid)
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                if replicate:
+                    dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group)
+                    out[lo:lo + step].copy_(g)
+                else:
+                    # rank r owns images [r*B/world, (r+1)*B/world): group k contributes `per` of them
+                    dist.reduce_scatter_tensor(out[k * per:(k + 1) * per], g, op=dist.ReduceOp.SUM, group=self.group)
+            g.record_stream(self._side)
+            keep.append(g)
+        cur.wait_stream(self._side)
+        return out
+
+    def owned_images(self):
+        """Indices (into the batch) of the images this rank's ``adjoint`` result holds, in order."""
+        B, world = self.B, self.world
+        if self.world == 1:
+            return np.arange(B)
+        if self.algo == "p2p":
+            lo, hi = shard_range(B, self.rank, world)
+            return np.arange(lo, hi)
+        step = 32 * world // np.gcd(32, world)
+        if B % step != 0 or B // step < 2:
+            step = B
+        per = step // world
+        return np.concatenate([np.arange(lo + self.rank * per, lo + (self.rank + 1) * per) for lo in range(0, B, step)])

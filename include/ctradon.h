@@ -170,6 +170,8 @@ int ctr_hostpipe_forward(ctr_hostpipe* pipe, const float* img_host, float* sino_
 int ctr_hostpipe_adjoint(ctr_hostpipe* pipe, const float* dsino_host, float* dimg_host, int B, int interp, int mode);
 int ctr_hostpipe_wait(ctr_hostpipe* pipe);
 int ctr_hostpipe_done(ctr_hostpipe* pipe);
+/* diagnostics: record every chunk's copy-in / kernel / copy-out interval; ctr_hostpipe_wait prints them to stderr */
+int ctr_hostpipe_trace(ctr_hostpipe* pipe, int on);
 
 /* ---- zero-copy DLPack entry points ---------------------------------------------------------
  * Same operations on borrowed DLTensors (kDLCUDA, float32, compact row-major).

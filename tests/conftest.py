@@ -42,7 +42,6 @@ def emu():
     f32p, f64p, i = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double), ctypes.c_int
     L.emu_forward.argtypes = [f32p, i, i, i, i, i, i, i, f32p, i, i, i, f32p]
     L.emu_forward_depth.argtypes = L.emu_forward.argtypes
-    L.emu_forward_isync.argtypes = L.emu_forward.argtypes
     L.emu_forward_rec32.argtypes = L.emu_forward.argtypes
     L.emu_forward_rec32_plain.argtypes = L.emu_forward.argtypes
     L.emu_adjoint.argtypes = [f32p, i, i, i, i, i, i, i, f32p, i, i, i, i, i, i, f32p]

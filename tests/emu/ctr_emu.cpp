@@ -184,69 +184,6 @@ int forward_window_impl(const float* img, int B, int X, int Y, int H, int W, int
     return covered == A ? windowed : -2;
 }
 
-// ctr_march_isync replayed for one quarter-warp: 8 adjacent rays of one angle take the same
-// step index per trip (mirrors the device loop in ctr_kernels.cuh; shuffles become array ops).
-template <int INTERP>
-void forward_isync_impl(const float* img, int B, int X, int Y, int H, int W, int padx, int pady,
-                        const float* t, int A, int R, float* sino)
-{
-    CtrClassGeom geom[2];
-    ctr_h_class_geom(X, Y, padx, pady, geom);
-    std::vector<float> pk[2];
-    pack_images<1>(img, B, X, Y, geom, pk[0], pk[1]);
-    std::vector<CtrRay> rays;
-    int n0 = 0;
-    ctr_h_build_rays(t, A, rays, n0);
-    const int G = (B + NB - 1) / NB;
-    for (int g = 0; g < G; ++g)
-        for (const CtrRay& r : rays) {
-            const CtrClassGeom& cg = geom[r.cls];
-            const float* pkg = pk[r.cls].data() + (size_t)g * cg.Vp * cg.Up * NB;
-            const int K = (cg.Vp + R - 1) / R;
-            for (int j0 = 0; j0 < W; j0 += 8) {
-                CtrRayState s[8];
-                float acc[8][NB] = {};
-                for (int l = 0; l < 8; ++l) {
-                    s[l].n = 0;
-                    if (j0 + l < W) ctr_ray_begin(r, cg, j0 + l, H, s[l]);
-                }
-                for (int k = 0; k < K; ++k) {
-                    const int rows = std::min(R + 1, cg.Vp - k * R);
-                    std::vector<float> strip((size_t)(R + 1) * cg.Up * NB, -1e30f);
-                    std::memcpy(strip.data(), pkg + (size_t)k * R * cg.Up * NB, sizeof(float) * rows * cg.Up * NB);
-                    const float vend = (float)((k + 1) * R + cg.offv);
-                    const int rbase = k * R + cg.offv;
-                    float mine[8], m = 3.0e38f;
-                    bool live[8];
-                    for (int l = 0; l < 8; ++l) {
-                        mine[l] = s[l].n > 0 ? s[l].fi * s[l].dfi : 3.0e38f;
-                        m = std::min(m, mine[l]);
-                        live[l] = s[l].n > 0;
-                    }
-                    auto any = [&] { for (int l = 0; l < 8; ++l) if (live[l]) return true; return false; };
-                    while (any()) {
-                        for (int l = 0; l < 8; ++l) {
-                            if (!(live[l] && mine[l] == m)) continue;
-                            CtrSample<INTERP> a;
-                            ctr_sample<INTERP>(r, s[l].pu, s[l].pv, s[l].fi, cg.Up, rbase, cg.offu, a);
-                            if (a.kvf >= vend) { live[l] = false; continue; }
-                            ctr_gather<NB, INTERP, NB>(strip.data(), cg.Up, a, acc[l]);
-                            s[l].fi += s[l].dfi;
-                            mine[l] += 1.f;
-                            live[l] = --s[l].n > 0;
-                        }
-                        m += 1.f;
-                    }
-                }
-                for (int l = 0; l < 8 && j0 + l < W; ++l)
-                    for (int n = 0; n < NB; ++n) {
-                        const int b = g * NB + n;
-                        if (b < B) sino[((size_t)b * A + r.angle) * W + j0 + l] = acc[l][n];
-                    }
-            }
-        }
-}
-
 template <int MODE, int INTERP, int NBA>
 void adjoint_impl(const float* y, int B, int X, int Y, int H, int W, int padx, int pady,
                   const float* table, int A, int TW, int TH, int win, float* out)
@@ -318,14 +255,6 @@ void emu_forward(const float* img, int B, int X, int Y, int H, int W, int padx, 
 {
     if (interp == CTR_NEAREST) forward_impl<CTR_NEAREST, 1>(img, B, X, Y, H, W, padx, pady, t, A, R, sino);
     else forward_impl<CTR_BILINEAR, 1>(img, B, X, Y, H, W, padx, pady, t, A, R, sino);
-}
-
-// i-synchronous quarter-warps (ctr_march_isync), 4-image records
-void emu_forward_isync(const float* img, int B, int X, int Y, int H, int W, int padx, int pady, const float* t, int A,
-                       int interp, int R, float* sino)
-{
-    if (interp == CTR_NEAREST) forward_isync_impl<CTR_NEAREST>(img, B, X, Y, H, W, padx, pady, t, A, R, sino);
-    else forward_isync_impl<CTR_BILINEAR>(img, B, X, Y, H, W, padx, pady, t, A, R, sino);
 }
 
 // depth-first pack: 4 image groups share a pixel record (ctr_fwd_kernel<..., DEPTH = 4>)

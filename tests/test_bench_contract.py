@@ -18,7 +18,7 @@ def test_reference_arm_prints_one_json_line():
     assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert d["config"]["workload"].startswith("configs[1]") and d["vs_baseline"] is None
+    assert d["config"]["workload"].startswith("configs[3]") and d["vs_baseline"] is None
 
 
 def test_reference_arm_other_ranks_stay_silent():

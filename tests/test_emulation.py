@@ -55,9 +55,6 @@ def test_emulated_kernels_match_oracle(emu, orc, B, X, Y, A, pad, R, TW, TH, win
         emu.emu_forward_rec32_plain(P(img), B, X, Y, H, W, padx, pady, P(t), A, interp, R, P(s32p))
         assert np.array_equal(s32p, sd), "32-image records (plain march) differ from 16-image records"
         np.testing.assert_array_equal(sd, s)
-        si = np.full((B, A, W), np.nan, np.float32)       # i-synchronous quarter-warps: same samples, same order per ray
-        emu.emu_forward_isync(P(img), B, X, Y, H, W, padx, pady, P(t), A, interp, R, P(si))
-        np.testing.assert_array_equal(si, s)
         g = np.full((B, X, Y), np.nan, np.float32)
         emu.emu_adjoint(P(y), B, X, Y, H, W, padx, pady, P(t), A, interp, 0, TW, TH, win, P(g))
         assert rel_l2(g, orc.adjoint_exact(y, th, X, Y, pad, interp)) <= 1e-6
@@ -108,9 +105,6 @@ def test_emulated_kernels_property(emu, orc, B, X, Y, pad, R, th, seed):
         emu.emu_forward_rec32_plain(P(img), B, X, Y, H, W, padx, pady, P(t), A, interp, R, P(s32p))
         assert np.array_equal(s32p, sd), "32-image records (plain march) differ from 16-image records"
         np.testing.assert_array_equal(sd, s)
-        si = np.full((B, A, W), np.nan, np.float32)
-        emu.emu_forward_isync(P(img), B, X, Y, H, W, padx, pady, P(t), A, interp, R, P(si))
-        np.testing.assert_array_equal(si, s)
         for mode, table, fn in ((0, t, orc.adjoint_exact), (1, ti, orc.adjoint_tf)):
             g = np.full((B, X, Y), np.nan, np.float32)
             emu.emu_adjoint(P(y), B, X, Y, H, W, padx, pady, P(table), A, interp, mode, 32, 8, 40, P(g))

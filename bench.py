@@ -726,14 +726,13 @@ def run_angle(args, ctx, wl):
     others = {}
     if not args.no_side_legs:
         # the other exchange algorithm, and the batch-sharded (weak-scaling) figures of C2 and C4, for context
-        alt = "nccl" if op.algo == "p2p" else None
-        if alt:
+        for alt in ([a for a in ("nccl", "torch") if a != op.algo and (a == "torch" or (op.comm is not None and op.comm.has_nccl))]):
             try:
-                op2 = sharding.AngleShardedRadon(theta, X, X, True, B, ctx.dev, interpolation=INTERP, adjoint="exact", algo=alt)
-                ms2, _, _, _, _ = timed_steps(ctx, lambda: (op2.forward(img), op2.adjoint(cot)), max(10, args.steps // 2), 3)
+                ms2, _, _, _, _ = timed_steps(ctx, lambda: (op.forward(img), op.adjoint(cot, algo=alt)), max(10, args.steps // 2), 3)
                 others[f"angle_sharded_{alt}"] = {"ms_per_step": ms2, "value": units / (ms2 * 1e-3) / 1e9}
             except Exception as exc:
                 others[f"angle_sharded_{alt}"] = {"error": repr(exc)[:200]}
+        op.check()
         del img, cot
         torch.cuda.empty_cache()
         for key in ("c2", "c4"):
@@ -796,7 +795,7 @@ def main():
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--shard", default="angle", choices=["batch", "angle"],
                     help="N > 1: angle-sharded (configs[3], strong scaling, default) or batch-sharded (weak scaling)")
-    ap.add_argument("--angle-algo", default="auto", choices=["auto", "p2p", "nccl"],
+    ap.add_argument("--angle-algo", default="auto", choices=["auto", "p2p", "nccl", "torch"],
                     help="angle-sharded mode: how the partial back-projections are summed (see sharding.AngleShardedRadon)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-side-legs", action="store_true")

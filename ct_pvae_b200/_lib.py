@@ -18,7 +18,9 @@ LIB_PATH = os.environ.get("CTRADON_LIB", os.path.join(_HERE, "libctradon.so"))
 
 INTERP_NEAREST, INTERP_BILINEAR = 0, 1
 ADJOINT_EXACT, ADJOINT_TF_COMPAT = 0, 1
-CTR_OK, CTR_EINVAL, CTR_ECUDA, CTR_EWORKSPACE, CTR_EUNSUPPORTED = 0, -1, -2, -3, -4
+CTR_OK, CTR_EINVAL, CTR_ECUDA, CTR_EWORKSPACE, CTR_EUNSUPPORTED, CTR_ECOMM = 0, -1, -2, -3, -4, -5
+EXCHANGE_P2P, EXCHANGE_NCCL = 0, 1
+COMM_HANDLE_BYTES, NCCL_ID_BYTES = 128, 128
 
 _c_int, _c_void_p, _c_size_t = ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t
 _f32p = ctypes.POINTER(ctypes.c_float)
@@ -63,6 +65,21 @@ SYMBOLS = {
     "ctr_hostpipe_wait": (_c_int, [_c_void_p]),
     "ctr_hostpipe_done": (_c_int, [_c_void_p]),
     "ctr_hostpipe_trace": (_c_int, [_c_void_p, _c_int]),
+    "ctr_comm_create": (_c_int, [_c_int, _c_int, _c_int, _c_size_t, ctypes.POINTER(_c_void_p)]),
+    "ctr_comm_export": (_c_int, [_c_void_p, _c_void_p]),
+    "ctr_comm_connect": (_c_int, [_c_void_p, _c_void_p]),
+    "ctr_comm_create_all": (_c_int, [_c_int, _intp, _c_size_t, ctypes.POINTER(_c_void_p)]),
+    "ctr_comm_nccl_unique_id": (_c_int, [_c_void_p]),
+    "ctr_comm_nccl_init": (_c_int, [_c_void_p, _c_void_p]),
+    "ctr_comm_set_timeout_ms": (_c_int, [_c_void_p, _c_int]),
+    "ctr_comm_info": (_c_int, [_c_void_p, _intp, _intp, _intp, _intp, ctypes.POINTER(_c_size_t)]),
+    "ctr_comm_check": (_c_int, [_c_void_p]),
+    "ctr_comm_destroy": (_c_int, [_c_void_p]),
+    "ctr_adjoint_sharded_workspace_bytes": (_c_size_t, [_c_void_p, _c_void_p, _c_int]),
+    "ctr_radon_adjoint_sharded": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p,
+                                           _c_size_t, _c_void_p]),
+    "ctr_fbp_sharded": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_int, _c_int, _c_void_p, _c_size_t,
+                                 _c_void_p]),
     "ctr_radon_forward_dl": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_void_p]),
     "ctr_radon_adjoint_dl": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p]),
     "ctr_fbp_dl": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
@@ -110,7 +127,7 @@ def launch_count() -> int:
     return int(lib().ctr_launch_count())
 
 
-N_KERNELS = 7
+N_KERNELS = 8
 
 
 def profile_enable(on: bool) -> None:

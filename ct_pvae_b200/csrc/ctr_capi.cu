@@ -1,6 +1,8 @@
 // ctr_capi.cu -- the C ABI declared in include/ctradon.h: plans, argument checks,
 // workspace carving and kernel launches.  No torch, no Python, no CPU compute path.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>   // types only: the library is opened at run time (ctr_comm_nccl_*), there is no link-time dependency
 
 #include <cmath>
 #include <cstdio>
@@ -118,7 +120,7 @@ long long ctr_launch_count(void) { return ctr::launch_counter().load(); }
 
 static const char* kKernelNames[CTR_K_COUNT] = {"ctr_pack_image_kernel", "ctr_pack_sino_kernel", "ctr_fwd_kernel",
                                                 "ctr_bp_kernel<exact>", "ctr_bp_kernel<tf_compat>",
-                                                "ctr_fbp_filter_kernel", "ctr_bp_kernel<fbp>"};
+                                                "ctr_fbp_filter_kernel", "ctr_bp_kernel<fbp>", "ctr_xchg_sum_kernel"};
 const char* ctr_kernel_name(int id) { return (id >= 0 && id < CTR_K_COUNT) ? kKernelNames[id] : ""; }
 
 int ctr_profile_enable(int on)
@@ -488,15 +490,20 @@ int ctr_radon_adjoint(const ctr_plan* p, const float* dsino, float* dimg, int B,
     return ctr_radon_adjoint_scaled(p, dsino, dimg, B, interp, mode, 1.0f, ws, ws_bytes, stream);
 }
 
-int ctr_radon_adjoint_scaled(const ctr_plan* p, const float* dsino, float* dimg, int B, int interp, int mode, float scale,
-                             void* ws, size_t ws_bytes, void* stream)
+// The adjoint launch sequence (pack + gather kernel) shared by the plain, subset and sharded entry points.
+//   sel / n_sel : angle subset (device int32 indices into the plan's angles) or null = all of the plan's angles
+//   xg          : angle-sharded exchange target (nranks > 1) or null
+static int adjoint_impl(const ctr_plan* p, const float* dsino, float* dimg, int B, int interp, int mode, float scale,
+                        const int* sel, int n_sel, const CtrExchange* xg, void* ws, size_t ws_bytes, void* stream, const char* who)
 {
-    if (!p || !dsino || !dimg) return fail(CTR_EINVAL, "ctr_radon_adjoint: NULL plan or buffer");
-    if (B <= 0) return fail(CTR_EINVAL, "ctr_radon_adjoint: B must be positive");
-    if (interp != CTR_INTERP_NEAREST && interp != CTR_INTERP_BILINEAR) return fail(CTR_EINVAL, "ctr_radon_adjoint: bad interp");
-    if (mode != CTR_ADJOINT_EXACT && mode != CTR_ADJOINT_TF_COMPAT) return fail(CTR_EINVAL, "ctr_radon_adjoint: bad mode");
-    if (!ws || ws_bytes < ctr_adjoint_workspace_bytes(p, B)) return fail(CTR_EWORKSPACE, "ctr_radon_adjoint: workspace too small");
-    if (((uintptr_t)ws & 255) != 0) return fail(CTR_EINVAL, "ctr_radon_adjoint: workspace must be 256-byte aligned");
+    if (!p || !dsino || (!dimg && !xg)) return fail(CTR_EINVAL, std::string(who) + ": NULL plan or buffer");
+    if (B <= 0) return fail(CTR_EINVAL, std::string(who) + ": B must be positive");
+    if (interp != CTR_INTERP_NEAREST && interp != CTR_INTERP_BILINEAR) return fail(CTR_EINVAL, std::string(who) + ": bad interp");
+    if (mode != CTR_ADJOINT_EXACT && mode != CTR_ADJOINT_TF_COMPAT) return fail(CTR_EINVAL, std::string(who) + ": bad mode");
+    if (sel && (n_sel <= 0 || n_sel > p->A)) return fail(CTR_EINVAL, std::string(who) + ": the angle subset must have 1..A entries");
+    const int A = sel ? n_sel : p->A;
+    if (!ws || ws_bytes < spk_bytes(B, A, p->W)) return fail(CTR_EWORKSPACE, std::string(who) + ": workspace too small");
+    if (((uintptr_t)ws & 255) != 0) return fail(CTR_EINVAL, std::string(who) + ": workspace must be 256-byte aligned");
     DeviceGuard guard(p->device);
     if (!guard.ok) return fail_cuda(guard.err, "cudaSetDevice");
     cudaStream_t st = (cudaStream_t)stream;
@@ -504,22 +511,24 @@ int ctr_radon_adjoint_scaled(const ctr_plan* p, const float* dsino, float* dimg,
     const int G = (B + NBb - 1) / NBb;
     float* spk = (float*)ws;
     {
-        dim3 grid((p->W + 2 + 127) / 128, p->A, G), block(128);
+        dim3 grid((p->W + 2 + 127) / 128, A, G), block(128);
         ProfScope prof(CTR_K_PACK_SINO, st);
-        if (NBb == 32) ctr::ctr_pack_sino_kernel<32><<<grid, block, 0, st>>>(dsino, B, p->A, p->W, spk);
-        else if (NBb == 16) ctr::ctr_pack_sino_kernel<16><<<grid, block, 0, st>>>(dsino, B, p->A, p->W, spk);
-        else ctr::ctr_pack_sino_kernel<8><<<grid, block, 0, st>>>(dsino, B, p->A, p->W, spk);
+        if (NBb == 32) ctr::ctr_pack_sino_kernel<32><<<grid, block, 0, st>>>(dsino, B, A, p->W, spk);
+        else if (NBb == 16) ctr::ctr_pack_sino_kernel<16><<<grid, block, 0, st>>>(dsino, B, A, p->W, spk);
+        else ctr::ctr_pack_sino_kernel<8><<<grid, block, 0, st>>>(dsino, B, A, p->W, spk);
         ctr::launch_counter()++;
         CTR_CUDA(cudaGetLastError());
     }
-    ctr::BpParams bp;
+    ctr::BpParams bp{};
     bp.spk = spk;
     bp.table = (mode == CTR_ADJOINT_EXACT) ? p->d_t : p->d_tinv;
     bp.cs = nullptr;
     bp.out = dimg;
-    bp.B = B; bp.A = p->A; bp.X = p->X; bp.Y = p->Y; bp.H = p->H; bp.W = p->W; bp.padx = p->padx; bp.pady = p->pady;
+    bp.B = B; bp.A = A; bp.X = p->X; bp.Y = p->Y; bp.H = p->H; bp.W = p->W; bp.padx = p->padx; bp.pady = p->pady;
     bp.win = p->W + 2;   // clamped to the tile's window size by the launcher
     bp.scale = scale;
+    bp.sel = sel;
+    if (xg) bp.xg = *xg; else bp.xg.nranks = 1;
     cudaError_t e;
     ProfScope prof(mode == CTR_ADJOINT_EXACT ? CTR_K_ADJ_EXACT : CTR_K_ADJ_TF, st);
     if (mode == CTR_ADJOINT_EXACT)
@@ -530,6 +539,12 @@ int ctr_radon_adjoint_scaled(const ctr_plan* p, const float* dsino, float* dimg,
                                            : ctr::launch_bp<CTR_ADJ_TF, CTR_BILINEAR>(bp, NBb, st);
     if (e != cudaSuccess) return fail_cuda(e, "ctr_bp_kernel launch");
     return CTR_OK;
+}
+
+int ctr_radon_adjoint_scaled(const ctr_plan* p, const float* dsino, float* dimg, int B, int interp, int mode, float scale,
+                             void* ws, size_t ws_bytes, void* stream)
+{
+    return adjoint_impl(p, dsino, dimg, B, interp, mode, scale, nullptr, 0, nullptr, ws, ws_bytes, stream, "ctr_radon_adjoint");
 }
 
 // ------------------------------------------------------------------------------------------ FBP
@@ -580,9 +595,11 @@ size_t ctr_fbp_workspace_bytes(const ctr_fbp_plan* p, int B)
     return spk_bytes(B, p->A, p->P);
 }
 
-int ctr_fbp(const ctr_fbp_plan* p, const float* sino, int A, float* recon, int B, void* ws, size_t ws_bytes, void* stream)
+// A_total: the angle count the pi/(2A) scale refers to (the plan's own A, or the total over all angle shards)
+static int fbp_impl(const ctr_fbp_plan* p, const float* sino, int A, int A_total, float* recon, int B, const CtrExchange* xg,
+                    void* ws, size_t ws_bytes, void* stream)
 {
-    if (!p || !sino || !recon) return fail(CTR_EINVAL, "ctr_fbp: NULL plan or buffer");
+    if (!p || !sino || (!recon && !xg)) return fail(CTR_EINVAL, "ctr_fbp: NULL plan or buffer");
     if (A != p->A)
         return fail(CTR_EINVAL, "The given ``theta`` does not match the number of projections in ``radon_image``.");
     if (B <= 0) return fail(CTR_EINVAL, "ctr_fbp: B must be positive");
@@ -611,11 +628,12 @@ int ctr_fbp(const ctr_fbp_plan* p, const float* sino, int A, float* recon, int B
         ctr::launch_counter()++;
         CTR_CUDA(cudaGetLastError());
     }
-    ctr::BpParams bp;
+    ctr::BpParams bp{};
+    if (xg) bp.xg = *xg; else bp.xg.nranks = 1;
     bp.spk = spk; bp.table = nullptr; bp.cs = p->d_cs; bp.out = recon;
     bp.B = B; bp.A = p->A; bp.X = p->x_size; bp.Y = p->y_size; bp.H = p->P; bp.W = p->P; bp.padx = 0; bp.pady = 0;
     bp.win = p->P + 2;
-    bp.scale = (float)(M_PI / (2.0 * (double)p->A));
+    bp.scale = (float)(M_PI / (2.0 * (double)A_total));
     cudaError_t e;
     {
         ProfScope prof(CTR_K_FBP_BP, st);
@@ -623,6 +641,11 @@ int ctr_fbp(const ctr_fbp_plan* p, const float* sino, int A, float* recon, int B
     }
     if (e != cudaSuccess) return fail_cuda(e, "ctr_bp_kernel<FBP> launch");
     return CTR_OK;
+}
+
+int ctr_fbp(const ctr_fbp_plan* p, const float* sino, int A, float* recon, int B, void* ws, size_t ws_bytes, void* stream)
+{
+    return fbp_impl(p, sino, A, p ? p->A : A, recon, B, nullptr, ws, ws_bytes, stream);
 }
 
 // ------------------------------------------------------------------------------------------ host pipeline
@@ -803,6 +826,381 @@ int ctr_hostpipe_done(ctr_hostpipe* hp)
     if (e == cudaSuccess) return 1;
     if (e == cudaErrorNotReady) return 0;
     return fail_cuda(e, "cudaStreamQuery");
+}
+
+// ------------------------------------------------------------------------------------------ angle-sharded exchange
+// One ctr_comm per rank (one rank per GPU).  Every rank owns an allocation
+//   [ flags: CTR_MAX_RANKS x u32 | err: i32 @256 | exchange buffers @4096: 2 parities x `bytes` ]
+// that every other rank maps over NVLink peer memory (CUDA IPC between processes, cudaDeviceEnablePeerAccess inside
+// one process).  The adjoint / FBP kernels of an angle shard store their partial images straight into the owners'
+// buffers; ctr_xchg_sum_kernel then exchanges "done" flags and sums the slots (see ctr_kernels.cuh).
+// Two parities: call k+1 writes the other half while a slower rank may still be summing call k; the flag exchange of
+// call k+1 keeps anyone from starting call k+2 before everybody has finished summing call k.
+namespace {
+constexpr size_t kXgHeader = 4096;
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;
+    ncclResult_t (*CommGetAsyncError)(ncclComm_t, ncclResult_t*) = nullptr;
+    ncclResult_t (*ReduceScatter)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+std::mutex g_nccl_mu;
+NcclApi g_nccl;
+
+// libnccl.so.2 is opened on first use: a process that already loaded it (torch) shares that copy
+const NcclApi* nccl_api()
+{
+    std::lock_guard<std::mutex> lk(g_nccl_mu);
+    if (g_nccl.lib) return &g_nccl;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return nullptr;
+    NcclApi a;
+    a.lib = h;
+#define CTR_SYM(field, name) *(void**)(&a.field) = dlsym(h, name); if (!a.field) { dlclose(h); return nullptr; }
+    CTR_SYM(GetUniqueId, "ncclGetUniqueId")
+    CTR_SYM(CommInitRank, "ncclCommInitRank")
+    CTR_SYM(CommInitAll, "ncclCommInitAll")
+    CTR_SYM(CommDestroy, "ncclCommDestroy")
+    CTR_SYM(CommAbort, "ncclCommAbort")
+    CTR_SYM(CommGetAsyncError, "ncclCommGetAsyncError")
+    CTR_SYM(ReduceScatter, "ncclReduceScatter")
+    CTR_SYM(AllReduce, "ncclAllReduce")
+    CTR_SYM(GetErrorString, "ncclGetErrorString")
+#undef CTR_SYM
+    g_nccl = a;
+    return &g_nccl;
+}
+
+struct CommHandle {                 // what ctr_comm_export writes (CTR_COMM_HANDLE_BYTES)
+    cudaIpcMemHandle_t mem;         // 64 bytes
+    unsigned long long bytes;
+    int rank, nranks;
+    unsigned magic;
+    char pad_[CTR_COMM_HANDLE_BYTES - 64 - 8 - 4 - 4 - 4];
+};
+static_assert(sizeof(CommHandle) == CTR_COMM_HANDLE_BYTES, "handle layout");
+constexpr unsigned kCommMagic = 0x43545243u;   // "CTRC"
+}  // namespace
+
+struct ctr_comm {
+    int nranks = 1, rank = 0, device = 0;
+    size_t bytes = 0;                            // one parity of the exchange buffer (256-byte multiple)
+    void* base = nullptr;
+    void* peer_base[CTR_MAX_RANKS] = {};
+    bool ipc_opened[CTR_MAX_RANKS] = {};
+    bool connected = false;
+    unsigned epoch = 0;
+    unsigned long long timeout_ns = 10ull * 1000 * 1000 * 1000;
+    std::mutex mu;
+    ncclComm_t nccl = nullptr;
+    float* nccl_partial = nullptr;               // [B][X][Y] partial of the NCCL algorithm (grown on demand)
+    size_t nccl_partial_bytes = 0;
+    int sm_count = 148;
+};
+
+static int comm_alloc(int nranks, int rank, int device, size_t bytes, ctr_comm** out)
+{
+    if (!out) return fail(CTR_EINVAL, "ctr_comm_create: out is NULL");
+    *out = nullptr;
+    if (nranks < 1 || nranks > CTR_MAX_RANKS || rank < 0 || rank >= nranks)
+        return fail(CTR_EINVAL, "ctr_comm_create: need 1 <= nranks <= 16 and 0 <= rank < nranks");
+    if (bytes == 0) return fail(CTR_EINVAL, "ctr_comm_create: exchange bytes must be positive");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail_cuda(guard.err, "cudaSetDevice");
+    ctr_comm* c = new (std::nothrow) ctr_comm();
+    if (!c) return fail(CTR_EINVAL, "ctr_comm_create: out of host memory");
+    c->nranks = nranks; c->rank = rank; c->device = device;
+    c->bytes = align_up(bytes, 256);
+    if (cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || c->sm_count <= 0) c->sm_count = 148;
+    cudaError_t e = cudaMalloc(&c->base, kXgHeader + 2 * c->bytes);
+    if (e == cudaSuccess) e = cudaMemset(c->base, 0, kXgHeader);
+    if (e != cudaSuccess) { cudaFree(c->base); delete c; return fail_cuda(e, "ctr_comm_create: exchange buffer"); }
+    c->peer_base[rank] = c->base;
+    c->connected = (nranks == 1);
+    *out = c;
+    return CTR_OK;
+}
+
+int ctr_comm_create(int nranks, int rank, int device, size_t exchange_bytes, ctr_comm** out)
+{
+    return comm_alloc(nranks, rank, device, exchange_bytes, out);
+}
+
+int ctr_comm_export(const ctr_comm* c, void* handle_out)
+{
+    if (!c || !handle_out) return fail(CTR_EINVAL, "ctr_comm_export: NULL argument");
+    DeviceGuard guard(c->device);
+    if (!guard.ok) return fail_cuda(guard.err, "cudaSetDevice");
+    CommHandle h;
+    std::memset(&h, 0, sizeof(h));
+    CTR_CUDA(cudaIpcGetMemHandle(&h.mem, c->base));
+    h.bytes = c->bytes; h.rank = c->rank; h.nranks = c->nranks; h.magic = kCommMagic;
+    std::memcpy(handle_out, &h, sizeof(h));
+    return CTR_OK;
+}
+
+int ctr_comm_connect(ctr_comm* c, const void* handles)
+{
+    if (!c || !handles) return fail(CTR_EINVAL, "ctr_comm_connect: NULL argument");
+    DeviceGuard guard(c->device);
+    if (!guard.ok) return fail_cuda(guard.err, "cudaSetDevice");
+    std::lock_guard<std::mutex> lk(c->mu);
+    const CommHandle* hs = (const CommHandle*)handles;
+    for (int s = 0; s < c->nranks; ++s) {
+        if (hs[s].magic != kCommMagic || hs[s].rank != s || hs[s].nranks != c->nranks)
+            return fail(CTR_EINVAL, "ctr_comm_connect: handle " + std::to_string(s) + " is not rank " + std::to_string(s) + "'s export");
+        if (hs[s].bytes != c->bytes) return fail(CTR_EINVAL, "ctr_comm_connect: ranks disagree on the exchange size");
+    }
+    for (int s = 0; s < c->nranks; ++s) {
+        if (s == c->rank || c->peer_base[s]) continue;
+        cudaError_t e = cudaIpcOpenMemHandle(&c->peer_base[s], hs[s].mem, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) { c->peer_base[s] = nullptr; return fail_cuda(e, "ctr_comm_connect: cudaIpcOpenMemHandle (is NVLink/PCIe peer access available?)"); }
+        c->ipc_opened[s] = true;
+    }
+    c->connected = true;
+    return CTR_OK;
+}
+
+int ctr_comm_create_all(int nranks, const int* devices, size_t exchange_bytes, ctr_comm** out)
+{
+    if (!devices || !out) return fail(CTR_EINVAL, "ctr_comm_create_all: NULL argument");
+    if (nranks < 1 || nranks > CTR_MAX_RANKS) return fail(CTR_EINVAL, "ctr_comm_create_all: need 1 <= nranks <= 16");
+    for (int r = 0; r < nranks; ++r) out[r] = nullptr;
+    int rc = CTR_OK;
+    for (int r = 0; r < nranks && rc == CTR_OK; ++r) rc = comm_alloc(nranks, r, devices[r], exchange_bytes, &out[r]);
+    for (int r = 0; r < nranks && rc == CTR_OK; ++r) {
+        DeviceGuard guard(devices[r]);
+        if (!guard.ok) { rc = fail_cuda(guard.err, "cudaSetDevice"); break; }
+        for (int s = 0; s < nranks; ++s) {
+            if (s == r) continue;
+            if (devices[s] != devices[r]) {
+                int can = 0;
+                cudaDeviceCanAccessPeer(&can, devices[r], devices[s]);
+                if (!can) { rc = fail(CTR_EUNSUPPORTED, "ctr_comm_create_all: no peer access between the devices"); break; }
+                const cudaError_t e = cudaDeviceEnablePeerAccess(devices[s], 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { rc = fail_cuda(e, "cudaDeviceEnablePeerAccess"); break; }
+                (void)cudaGetLastError();
+            }
+            out[r]->peer_base[s] = out[s]->base;
+        }
+        out[r]->connected = true;
+    }
+    if (rc != CTR_OK)
+        for (int r = 0; r < nranks; ++r) { ctr_comm_destroy(out[r]); out[r] = nullptr; }
+    return rc;
+}
+
+int ctr_comm_set_timeout_ms(ctr_comm* c, int ms)
+{
+    if (!c || ms <= 0) return fail(CTR_EINVAL, "ctr_comm_set_timeout_ms: bad argument");
+    c->timeout_ns = (unsigned long long)ms * 1000000ull;
+    return CTR_OK;
+}
+
+int ctr_comm_info(const ctr_comm* c, int* nranks, int* rank, int* connected, int* has_nccl, size_t* exchange_bytes)
+{
+    if (!c) return fail(CTR_EINVAL, "ctr_comm_info: comm is NULL");
+    if (nranks) *nranks = c->nranks;
+    if (rank) *rank = c->rank;
+    if (connected) *connected = c->connected ? 1 : 0;
+    if (has_nccl) *has_nccl = c->nccl ? 1 : 0;
+    if (exchange_bytes) *exchange_bytes = c->bytes;
+    return CTR_OK;
+}
+
+int ctr_comm_nccl_unique_id(void* id_out)
+{
+    if (!id_out) return fail(CTR_EINVAL, "ctr_comm_nccl_unique_id: NULL argument");
+    const NcclApi* n = nccl_api();
+    if (!n) return fail(CTR_EUNSUPPORTED, "libnccl.so.2 could not be opened");
+    ncclUniqueId id;
+    const ncclResult_t r = n->GetUniqueId(&id);
+    if (r != ncclSuccess) return fail(CTR_ECOMM, std::string("ncclGetUniqueId: ") + n->GetErrorString(r));
+    std::memcpy(id_out, &id, sizeof(id));
+    return CTR_OK;
+}
+
+int ctr_comm_nccl_init(ctr_comm* c, const void* id_in)
+{
+    if (!c || !id_in) return fail(CTR_EINVAL, "ctr_comm_nccl_init: NULL argument");
+    const NcclApi* n = nccl_api();
+    if (!n) return fail(CTR_EUNSUPPORTED, "libnccl.so.2 could not be opened");
+    DeviceGuard guard(c->device);
+    if (!guard.ok) return fail_cuda(guard.err, "cudaSetDevice");
+    ncclUniqueId id;
+    std::memcpy(&id, id_in, sizeof(id));
+    const ncclResult_t r = n->CommInitRank(&c->nccl, c->nranks, id, c->rank);
+    if (r != ncclSuccess) { c->nccl = nullptr; return fail(CTR_ECOMM, std::string("ncclCommInitRank: ") + n->GetErrorString(r)); }
+    return CTR_OK;
+}
+
+// CTR_OK, or CTR_ECOMM when a peer missed a flag exchange (its process died or hung) or NCCL reports an
+// asynchronous error (ncclCommGetAsyncError).  Synchronises with nothing but a 4-byte read.
+int ctr_comm_check(ctr_comm* c)
+{
+    if (!c) return fail(CTR_EINVAL, "ctr_comm_check: comm is NULL");
+    DeviceGuard guard(c->device);
+    if (!guard.ok) return fail_cuda(guard.err, "cudaSetDevice");
+    int err = 0;
+    CTR_CUDA(cudaMemcpy(&err, (char*)c->base + 256, sizeof(int), cudaMemcpyDeviceToHost));
+    if (err != 0)
+        return fail(CTR_ECOMM, "angle-sharded exchange: rank " + std::to_string(err - 1) + " did not arrive within the timeout (rank " +
+                                   std::to_string(c->rank) + " waited)");
+    if (c->nccl) {
+        const NcclApi* n = nccl_api();
+        ncclResult_t ar = ncclSuccess;
+        const ncclResult_t r = n->CommGetAsyncError(c->nccl, &ar);
+        if (r != ncclSuccess) return fail(CTR_ECOMM, std::string("ncclCommGetAsyncError: ") + n->GetErrorString(r));
+        if (ar != ncclSuccess && ar != ncclInProgress) return fail(CTR_ECOMM, std::string("NCCL asynchronous error: ") + n->GetErrorString(ar));
+    }
+    return CTR_OK;
+}
+
+int ctr_comm_destroy(ctr_comm* c)
+{
+    if (!c) return CTR_OK;
+    DeviceGuard guard(c->device);
+    cudaDeviceSynchronize();
+    if (c->nccl) {
+        const NcclApi* n = nccl_api();
+        if (n) n->CommDestroy(c->nccl);
+    }
+    for (int s = 0; s < c->nranks; ++s)
+        if (c->ipc_opened[s] && c->peer_base[s]) cudaIpcCloseMemHandle(c->peer_base[s]);
+    cudaFree(c->nccl_partial);
+    cudaFree(c->base);
+    delete c;
+    return CTR_OK;
+}
+
+// shared front half of the sharded calls: argument checks, the epoch's exchange target
+static int exchange_begin(ctr_comm* c, int B, size_t img_floats, int algo, CtrExchange* xg, const char* who)
+{
+    if (!c) return fail(CTR_EINVAL, std::string(who) + ": comm is NULL");
+    if (algo != CTR_EXCHANGE_P2P && algo != CTR_EXCHANGE_NCCL) return fail(CTR_EINVAL, std::string(who) + ": bad exchange algorithm");
+    if (B <= 0 || B % c->nranks != 0)
+        return fail(CTR_EINVAL, std::string(who) + ": the batch must be a positive multiple of the rank count (the result is left batch-sharded)");
+    if (algo == CTR_EXCHANGE_NCCL) {
+        if (c->nranks > 1 && !c->nccl) return fail(CTR_EINVAL, std::string(who) + ": ctr_comm_nccl_init has not been called");
+        return CTR_OK;
+    }
+    if (!c->connected) return fail(CTR_EINVAL, std::string(who) + ": ctr_comm_connect has not been called");
+    if ((size_t)B * img_floats * sizeof(float) > c->bytes) return fail(CTR_EWORKSPACE, std::string(who) + ": exchange buffer smaller than B*X*Y*4 bytes");
+    const unsigned epoch = ++c->epoch;
+    for (int s = 0; s < c->nranks; ++s) xg->peer[s] = (float*)((char*)c->peer_base[s] + kXgHeader + (size_t)(epoch & 1) * c->bytes);
+    xg->nranks = c->nranks; xg->rank = c->rank; xg->Bs = B / c->nranks;
+    return CTR_OK;
+}
+
+// shared back half (P2P): flag exchange + fixed-order sum of this rank's slots into `out`
+static int exchange_finish_p2p(ctr_comm* c, const CtrExchange& xg, float* out, size_t n, cudaStream_t st)
+{
+    ctr::XchgParams xp{};
+    for (int s = 0; s < c->nranks; ++s) xp.peer_flags[s] = (unsigned*)c->peer_base[s];
+    xp.flags = (unsigned*)c->base;
+    xp.err = (int*)((char*)c->base + 256);
+    xp.slots = xg.peer[c->rank];
+    xp.out = out;
+    xp.n = n;
+    xp.epoch = c->epoch;
+    xp.nranks = c->nranks; xp.rank = c->rank;
+    xp.timeout_ns = c->timeout_ns;
+    size_t blocks = (n / 4 + 511) / 512;
+    if (blocks > (size_t)c->sm_count * 2) blocks = (size_t)c->sm_count * 2;
+    if (blocks < 1) blocks = 1;
+    ProfScope prof(CTR_K_XCHG_SUM, st);
+    ctr::ctr_xchg_sum_kernel<<<(unsigned)blocks, 512, 0, st>>>(xp);
+    ctr::launch_counter()++;
+    CTR_CUDA(cudaGetLastError());
+    return CTR_OK;
+}
+
+static int exchange_finish_nccl(ctr_comm* c, const float* partial, float* out, size_t n_shard, cudaStream_t st, const char* who)
+{
+    const NcclApi* n = nccl_api();
+    const ncclResult_t r = n->ReduceScatter(partial, out, n_shard, ncclFloat, ncclSum, c->nccl, st);
+    if (r != ncclSuccess) return fail(CTR_ECOMM, std::string(who) + ": ncclReduceScatter: " + n->GetErrorString(r));
+    ncclResult_t ar = ncclSuccess;
+    if (n->CommGetAsyncError(c->nccl, &ar) == ncclSuccess && ar != ncclSuccess && ar != ncclInProgress)
+        return fail(CTR_ECOMM, std::string(who) + ": NCCL asynchronous error: " + n->GetErrorString(ar));
+    return CTR_OK;
+}
+
+static int nccl_partial_buffer(ctr_comm* c, size_t bytes)
+{
+    if (c->nccl_partial_bytes >= bytes) return CTR_OK;
+    cudaFree(c->nccl_partial);
+    c->nccl_partial = nullptr; c->nccl_partial_bytes = 0;
+    CTR_CUDA(cudaMalloc((void**)&c->nccl_partial, bytes));
+    c->nccl_partial_bytes = bytes;
+    return CTR_OK;
+}
+
+size_t ctr_adjoint_sharded_workspace_bytes(const ctr_comm* c, const ctr_plan* p, int B)
+{
+    (void)c;
+    return ctr_adjoint_workspace_bytes(p, B);
+}
+
+int ctr_radon_adjoint_sharded(ctr_comm* c, const ctr_plan* p, const float* dsino_local, float* dimg_shard, int B, int interp,
+                              int mode, int algo, void* ws, size_t ws_bytes, void* stream)
+{
+    if (!p || !dimg_shard) return fail(CTR_EINVAL, "ctr_radon_adjoint_sharded: NULL plan or result");
+    const size_t img = (size_t)p->X * p->Y;
+    if (c && c->nranks == 1)
+        return adjoint_impl(p, dsino_local, dimg_shard, B, interp, mode, 1.0f, nullptr, 0, nullptr, ws, ws_bytes, stream, "ctr_radon_adjoint_sharded");
+    std::unique_lock<std::mutex> lk;
+    if (c) lk = std::unique_lock<std::mutex>(c->mu);
+    CtrExchange xg{};
+    int rc = exchange_begin(c, B, img, algo, &xg, "ctr_radon_adjoint_sharded");
+    if (rc != CTR_OK) return rc;
+    DeviceGuard guard(c->device);
+    if (!guard.ok) return fail_cuda(guard.err, "cudaSetDevice");
+    if (c->device != p->device) return fail(CTR_EINVAL, "ctr_radon_adjoint_sharded: plan and comm are on different devices");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n_shard = (size_t)(B / c->nranks) * img;
+    if (algo == CTR_EXCHANGE_P2P) {
+        rc = adjoint_impl(p, dsino_local, nullptr, B, interp, mode, 1.0f, nullptr, 0, &xg, ws, ws_bytes, stream, "ctr_radon_adjoint_sharded");
+        if (rc != CTR_OK) return rc;
+        return exchange_finish_p2p(c, xg, dimg_shard, n_shard, st);
+    }
+    if ((rc = nccl_partial_buffer(c, (size_t)B * img * sizeof(float))) != CTR_OK) return rc;
+    rc = adjoint_impl(p, dsino_local, c->nccl_partial, B, interp, mode, 1.0f, nullptr, 0, nullptr, ws, ws_bytes, stream, "ctr_radon_adjoint_sharded");
+    if (rc != CTR_OK) return rc;
+    return exchange_finish_nccl(c, c->nccl_partial, dimg_shard, n_shard, st, "ctr_radon_adjoint_sharded");
+}
+
+int ctr_fbp_sharded(ctr_comm* c, const ctr_fbp_plan* p, const float* sino_local, int A_local, int A_total, float* recon_shard,
+                    int B, int algo, void* ws, size_t ws_bytes, void* stream)
+{
+    if (!p || !recon_shard) return fail(CTR_EINVAL, "ctr_fbp_sharded: NULL plan or result");
+    if (A_total < A_local || A_total <= 0) return fail(CTR_EINVAL, "ctr_fbp_sharded: A_total must cover the local angles");
+    const size_t img = (size_t)p->x_size * p->y_size;
+    if (c && c->nranks == 1) return fbp_impl(p, sino_local, A_local, A_total, recon_shard, B, nullptr, ws, ws_bytes, stream);
+    std::unique_lock<std::mutex> lk;
+    if (c) lk = std::unique_lock<std::mutex>(c->mu);
+    CtrExchange xg{};
+    int rc = exchange_begin(c, B, img, algo, &xg, "ctr_fbp_sharded");
+    if (rc != CTR_OK) return rc;
+    DeviceGuard guard(c->device);
+    if (!guard.ok) return fail_cuda(guard.err, "cudaSetDevice");
+    if (c->device != p->device) return fail(CTR_EINVAL, "ctr_fbp_sharded: plan and comm are on different devices");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n_shard = (size_t)(B / c->nranks) * img;
+    if (algo == CTR_EXCHANGE_P2P) {
+        if ((rc = fbp_impl(p, sino_local, A_local, A_total, nullptr, B, &xg, ws, ws_bytes, stream)) != CTR_OK) return rc;
+        return exchange_finish_p2p(c, xg, recon_shard, n_shard, st);
+    }
+    if ((rc = nccl_partial_buffer(c, (size_t)B * img * sizeof(float))) != CTR_OK) return rc;
+    if ((rc = fbp_impl(p, sino_local, A_local, A_total, c->nccl_partial, B, nullptr, ws, ws_bytes, stream)) != CTR_OK) return rc;
+    return exchange_finish_nccl(c, c->nccl_partial, recon_shard, n_shard, st, "ctr_fbp_sharded");
 }
 
 // ------------------------------------------------------------------------------------------ DLPack

@@ -519,6 +519,21 @@ CTR_HD void ctr_loglik_term(float proj, float mask, float y, float pnm, float sq
     dlp_dproj = (z * inv + (z * z - 1.f) * inv * dsc) * mask;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Angle-sharded exchange.  Rank r owns the images [r*Bs, (r+1)*Bs) of the summed back-projection.
+// Its exchange buffer holds one slot per source rank: [nranks][Bs][X][Y]; the adjoint kernel of rank s stores
+// its partial of image b into slot s of owner(b), and the owner sums its slots in rank order.
+#define CTR_MAX_RANKS 16
+struct CtrExchange {
+    float* peer[CTR_MAX_RANKS];   // exchange buffer (current parity) of every rank, mapped into this rank
+    int nranks, rank, Bs;
+};
+CTR_HD int ctr_xg_owner(int b, int Bs) { return b / Bs; }
+CTR_HD size_t ctr_xg_index(int src_rank, int b_local, int Bs, int r, int c, int X, int Y)
+{
+    return (((size_t)src_rank * Bs + b_local) * X + r) * Y + c;
+}
+
 // Sinogram-bin window a pixel tile needs for one angle: packed start bin so that
 // [start, start+win) covers every bin any of the tile's pixels can touch.
 //   u(px,py) is linear, so its extremes over the tile sit at the 4 corners.

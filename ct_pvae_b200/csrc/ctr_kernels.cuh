@@ -428,6 +428,12 @@ struct BpParams {
     int B, A, X, Y, H, W, padx, pady;
     int win;               // bins staged per angle (<= W+2)
     float scale;           // 1, or pi/(2A) for FBP
+    // angle subset (training's angle minibatch, helper_functions.py:355-357): row a of the packed sinogram is angle
+    // sel[a] of the plan's tables; null = identity
+    const int* sel;
+    // angle-sharded exchange: with nranks > 1 the tile of image b is stored straight into the exchange
+    // buffer of the rank that owns b, slot `rank` (peer memory over NVLink), instead of `out`
+    CtrExchange xg;
 };
 
 // bins a 32 x TH pixel tile can touch for one angle: |u| extent sqrt(31^2+(TH-1)^2) + 6 bins of slack
@@ -479,9 +485,10 @@ __global__ void __launch_bounds__(kBpTW * (TH + 1), MINB) ctr_bp_kernel(const Bp
         const int a = nb * AB + lane;
         uint64_t* bar = &full[s];
         if (a >= p.A) { mbar_arrive(bar); return; }
+        const int at = p.sel ? p.sel[a] : a;      // row of the plan's tables
         float cu[4];
         if (MODE == CTR_ADJ_FBP) {
-            const double co = p.cs[2 * a], si = p.cs[2 * a + 1];
+            const double co = p.cs[2 * at], si = p.cs[2 * at + 1];
             css[(s * AB + lane) * 2 + 0] = co;
             css[(s * AB + lane) * 2 + 1] = si;
             int q = 0;
@@ -494,7 +501,7 @@ __global__ void __launch_bounds__(kBpTW * (TH + 1), MINB) ctr_bp_kernel(const Bp
         } else {
             float t[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) t[q] = p.table[8 * a + q];
+            for (int q = 0; q < 8; ++q) t[q] = p.table[8 * at + q];
 #pragma unroll
             for (int q = 0; q < 8; ++q) tbl[(s * AB + lane) * 8 + q] = t[q];
             int q = 0;
@@ -559,10 +566,96 @@ __global__ void __launch_bounds__(kBpTW * (TH + 1), MINB) ctr_bp_kernel(const Bp
     }
 
     if (r < p.X && c < p.Y) {
+        if (p.xg.nranks <= 1) {
 #pragma unroll
-        for (int n = 0; n < NB; ++n) {
-            const int b = g * NB + n;
-            if (b < p.B) p.out[((size_t)b * p.X + r) * p.Y + c] = acc[n] * p.scale;
+            for (int n = 0; n < NB; ++n) {
+                const int b = g * NB + n;
+                if (b < p.B) p.out[((size_t)b * p.X + r) * p.Y + c] = acc[n] * p.scale;
+            }
+        } else {
+            // fused exchange: this rank's partial of image b goes to slot `rank` of b's owner (a 128-byte row
+            // segment per warp and image, written over NVLink while other tiles are still being computed)
+#pragma unroll
+            for (int n = 0; n < NB; ++n) {
+                const int b = g * NB + n;
+                if (b < p.B) {
+                    const int owner = ctr_xg_owner(b, p.xg.Bs);
+                    p.xg.peer[owner][ctr_xg_index(p.xg.rank, b - owner * p.xg.Bs, p.xg.Bs, r, c, p.X, p.Y)] = acc[n] * p.scale;
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ exchange: barrier + sum
+// Second half of the fused angle-sharded adjoint.  Every rank's ctr_bp_kernel has stored its partial images into the
+// owners' exchange buffers; this kernel (stream-ordered after it) tells every peer "my stores are done", waits until
+// every peer has said the same, and sums the nranks slots of this rank's images in rank order (deterministic).
+//   flags      this rank's flag words [nranks]: flags[s] = last epoch rank s has completed
+//   peer_flags the same array of every rank (peer memory)
+// A peer that does not arrive within timeout_ns raises *err (ctr_comm_check reports CTR_ECOMM) instead of hanging.
+struct XchgParams {
+    unsigned* peer_flags[CTR_MAX_RANKS];
+    unsigned* flags;
+    int* err;
+    const float* slots;     // [nranks][n] this rank's exchange buffer (current parity)
+    float* out;             // [n] = Bs * X * Y
+    size_t n;
+    unsigned epoch;
+    int nranks, rank;
+    unsigned long long timeout_ns;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__global__ void __launch_bounds__(512) ctr_xchg_sum_kernel(const XchgParams p)
+{
+    const int tid = threadIdx.x;
+    if (blockIdx.x == 0 && tid < p.nranks) {
+        __threadfence_system();                              // the adjoint kernel's peer stores (stream order) before the flag
+        st_release_sys(p.peer_flags[tid] + p.rank, p.epoch);
+    }
+    if (tid < p.nranks) {
+        const unsigned long long t0 = global_ns();
+        while ((int)(ld_acquire_sys(p.flags + tid) - p.epoch) < 0) {
+            if (global_ns() - t0 > p.timeout_ns) { atomicExch(p.err, 1 + tid); break; }
+            __nanosleep(200);
+        }
+    }
+    __syncthreads();
+    const size_t stride = (size_t)gridDim.x * blockDim.x, i0 = (size_t)blockIdx.x * blockDim.x + tid;
+    if ((p.n & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0) {   // 16-byte aligned slots and result: 128-bit accesses
+        const size_t n4 = p.n / 4;
+        const float4* s4 = reinterpret_cast<const float4*>(p.slots);
+        float4* o4 = reinterpret_cast<float4*>(p.out);
+        for (size_t i = i0; i < n4; i += stride) {
+            float4 a = __ldcg(s4 + i);
+            for (int s = 1; s < p.nranks; ++s) {
+                const float4 b = __ldcg(s4 + (size_t)s * n4 + i);
+                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+            }
+            o4[i] = a;
+        }
+    } else {
+        for (size_t i = i0; i < p.n; i += stride) {
+            float a = __ldcg(p.slots + i);
+            for (int s = 1; s < p.nranks; ++s) a += __ldcg(p.slots + (size_t)s * p.n + i);
+            p.out[i] = a;
         }
     }
 }

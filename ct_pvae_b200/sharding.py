@@ -145,38 +145,41 @@ class AngleShardedRadon:
       (``replicate=True``: the full ``[B,X,Y]`` on every rank).  This sum is the path's only exchange step.
 
     ``algo`` picks how the partial back-projections are summed:
-      "nccl"  one ``reduce_scatter`` (``all_reduce`` when replicating) per image group, issued as soon as the
-              group's adjoint kernel has been enqueued, so that it runs under the next group's kernel;
-      "p2p"   the adjoint kernel's epilogue stores every pixel straight into its owner's exchange buffer over
-              NVLink peer memory; a flag barrier and one fixed-order sum follow (``ctr_radon_adjoint_sharded``);
-      "auto"  "p2p" when the peer buffers could be mapped, else "nccl".
+      "p2p"   the adjoint kernel's epilogue stores every tile straight into its owner's exchange buffer over
+              NVLink peer memory; a flag exchange and one fixed-order sum follow (``ctr_radon_adjoint_sharded``,
+              ``CTR_EXCHANGE_P2P``) -- the product path;
+      "nccl"  the kernel writes the partial locally and the library calls ``ncclReduceScatter`` (``CTR_EXCHANGE_NCCL``);
+      "torch" the same through ``torch.distributed.reduce_scatter_tensor`` (no ctr_comm needed);
+      "auto"  "p2p" when the peer buffers could be mapped, else "torch".
     """
 
     def __init__(self, theta, X: int, Y: int, pad: bool, B: int, device: torch.device, interpolation: str = "bilinear",
                  adjoint: str = "exact", group=None, algo: str = "auto"):
         from . import _lib, ops
 
+        if algo not in ("auto", "p2p", "nccl", "torch"):
+            raise ValueError("algo must be 'auto', 'p2p', 'nccl' or 'torch'")
         self.rank, self.world = _world(group)
         self.group, self.B, self.X, self.Y = group, int(B), int(X), int(Y)
         theta = np.ascontiguousarray(np.asarray(theta, np.float64).reshape(-1))
         _check_angles_cover_ranks(theta.shape[0], self.world)
         if self.B % self.world != 0:
             raise ValueError("the batch must divide evenly over the ranks (the result is left batch-sharded)")
-        self.a_lo, self.a_hi = shard_range(theta.shape[0], self.rank, self.world)
+        self.A = int(theta.shape[0])
+        self.a_lo, self.a_hi = shard_range(self.A, self.rank, self.world)
         self.theta_local = theta[self.a_lo:self.a_hi]
         self.device = device
         self.plan = _lib.get_plan(self.theta_local, self.X, self.Y, bool(pad), device.index or 0)
         self.iid, self.mid = ops.INTERP[interpolation], ops.ADJOINT[adjoint]
         self.comm = None
-        if algo in ("auto", "p2p") and self.world > 1:
+        if algo != "torch" and self.world > 1:
             try:
                 from . import comm as _comm
-                self.comm = _comm.PeerComm(self.B * self.X * self.Y * 4, device, group)
+                self.comm = _comm.PeerComm(self.B * self.X * self.Y * 4, device, group, nccl=(algo in ("nccl", "auto")))
             except Exception:
-                if algo == "p2p":
+                if algo != "auto":
                     raise
-        self.algo = "p2p" if self.comm is not None else "nccl"
-        self._side = torch.cuda.Stream(device) if device.type == "cuda" else None
+        self.algo = ("p2p" if algo == "auto" else algo) if self.comm is not None else "torch"
 
     @property
     def A_local(self) -> int:
@@ -186,53 +189,31 @@ class AngleShardedRadon:
         from . import ops
         return ops.radon_forward(img, self.plan, self.iid)
 
-    def adjoint(self, dsino_local: torch.Tensor, replicate: bool = False) -> torch.Tensor:
+    def adjoint(self, dsino_local: torch.Tensor, replicate: bool = False, algo: str = None) -> torch.Tensor:
         from . import ops
         if dsino_local.shape[0] != self.B or dsino_local.shape[1] != self.A_local:
             raise ValueError("dsino_local must be [B, A_local, W] for this rank's angle block")
         if self.world == 1:
             return ops.radon_adjoint(dsino_local, self.plan, self.iid, self.mid)
-        if self.algo == "p2p":
-            return self.comm.adjoint_sharded(self.plan, dsino_local, self.iid, self.mid, replicate)
-        return self._adjoint_nccl(dsino_local, replicate)
-
-    def _adjoint_nccl(self, dsino_local: torch.Tensor, replicate: bool) -> torch.Tensor:
-        """Image groups of 32 (the adjoint kernel's full-efficiency unit) that also split evenly over the ranks:
-        group k is summed on the side stream while group k+1's kernel runs."""
-        from . import ops
-        B, world = self.B, self.world
-        step = 32 * world // np.gcd(32, world)
-        if B % step != 0 or B // step < 2:
-            step = B
-        per = step // world
-        out = torch.empty((B if replicate else B // world, self.X, self.Y), dtype=torch.float32, device=dsino_local.device)
-        cur = torch.cuda.current_stream(dsino_local.device)
-        keep = []
-        for k, lo in enumerate(range(0, B, step)):
-            g = ops.radon_adjoint(dsino_local[lo:lo + step], self.plan, self.iid, self.mid)
-            self._side.wait_stream(cur)
-            with torch.cuda.stream(self._side):
-                if replicate:
-                    dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group)
-                    out[lo:lo + step].copy_(g)
-                else:
-                    # rank r owns images [r*B/world, (r+1)*B/world): group k contributes `per` of them
-                    dist.reduce_scatter_tensor(out[k * per:(k + 1) * per], g, op=dist.ReduceOp.SUM, group=self.group)
-            g.record_stream(self._side)
-            keep.append(g)
-        cur.wait_stream(self._side)
+        algo = algo or self.algo
+        if algo in ("p2p", "nccl"):
+            if self.comm is None:
+                raise RuntimeError("this operator was built without a ctr_comm (algo='torch')")
+            return self.comm.adjoint_sharded(self.plan, dsino_local, self.iid, self.mid, replicate, algo=algo)
+        partial = ops.radon_adjoint(dsino_local, self.plan, self.iid, self.mid)
+        if replicate:
+            dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=self.group)
+            return partial
+        out = torch.empty((self.B // self.world, self.X, self.Y), dtype=torch.float32, device=partial.device)
+        dist.reduce_scatter_tensor(out, partial, op=dist.ReduceOp.SUM, group=self.group)
         return out
 
     def owned_images(self):
         """Indices (into the batch) of the images this rank's ``adjoint`` result holds, in order."""
-        B, world = self.B, self.world
-        if self.world == 1:
-            return np.arange(B)
-        if self.algo == "p2p":
-            lo, hi = shard_range(B, self.rank, world)
-            return np.arange(lo, hi)
-        step = 32 * world // np.gcd(32, world)
-        if B % step != 0 or B // step < 2:
-            step = B
-        per = step // world
-        return np.concatenate([np.arange(lo + self.rank * per, lo + (self.rank + 1) * per) for lo in range(0, B, step)])
+        lo, hi = shard_range(self.B, self.rank, self.world)
+        return np.arange(lo, hi)
+
+    def check(self) -> None:
+        """Raises if a peer missed an exchange (died / hung) or NCCL reported an asynchronous error."""
+        if self.comm is not None:
+            self.comm.check()

@@ -42,7 +42,8 @@ enum {
     CTR_EINVAL = -1,      /* bad argument (shape, enum, NULL, dtype, device, contiguity) */
     CTR_ECUDA = -2,       /* a CUDA runtime call failed; message carries cudaGetErrorString */
     CTR_EWORKSPACE = -3,  /* workspace smaller than ctr_*_workspace_bytes() */
-    CTR_EUNSUPPORTED = -4 /* shape outside what the kernels are built for */
+    CTR_EUNSUPPORTED = -4, /* shape outside what the kernels are built for */
+    CTR_ECOMM = -5         /* angle-sharded exchange failed: a peer did not arrive in time, or an NCCL error */
 };
 
 enum { CTR_INTERP_NEAREST = 0, CTR_INTERP_BILINEAR = 1 };
@@ -65,7 +66,7 @@ long long ctr_launch_count(void);
  * device time and launch count of one kernel since the last reset. */
 enum {
     CTR_K_PACK_IMAGE = 0, CTR_K_PACK_SINO = 1, CTR_K_FORWARD = 2, CTR_K_ADJ_EXACT = 3,
-    CTR_K_ADJ_TF = 4, CTR_K_FBP_FILTER = 5, CTR_K_FBP_BP = 6, CTR_K_COUNT = 7
+    CTR_K_ADJ_TF = 4, CTR_K_FBP_FILTER = 5, CTR_K_FBP_BP = 6, CTR_K_XCHG_SUM = 7, CTR_K_COUNT = 8
 };
 int ctr_profile_enable(int on);
 int ctr_profile_reset(void);
@@ -172,6 +173,51 @@ int ctr_hostpipe_wait(ctr_hostpipe* pipe);
 int ctr_hostpipe_done(ctr_hostpipe* pipe);
 /* diagnostics: record every chunk's copy-in / kernel / copy-out interval; ctr_hostpipe_wait prints them to stderr */
 int ctr_hostpipe_trace(ctr_hostpipe* pipe, int on);
+
+/* ---- angle-sharded mode (BASELINE configs[3]) ---------------------------------------
+ * The reference has no multi-device layer at all (configs/config_gpu.yaml:44 is a string for an external
+ * launcher); this one is the new framework's.  One rank per GPU.  Every rank holds all B images and a contiguous
+ * block of the angles; forward outputs are disjoint sinogram rows (ctr_radon_forward on the rank's own plan, no
+ * exchange).  The adjoint / FBP of an angle block is a full-size PARTIAL image; the partials are summed over the
+ * ranks and the result is left batch-sharded: rank r receives images [r*B/nranks, (r+1)*B/nranks).
+ *
+ * CTR_EXCHANGE_P2P (the product path): the back-projection kernel's epilogue stores each tile straight into the
+ *   owner rank's exchange buffer over NVLink peer memory (no separate collective); a flag exchange and one
+ *   fixed-order sum of the nranks slots follow in ctr_xchg_sum_kernel.  Deterministic (rank order).
+ * CTR_EXCHANGE_NCCL (the baseline): the kernel writes the partial locally, ncclReduceScatter sums it.
+ *
+ * Set-up between processes: every rank calls ctr_comm_create, ctr_comm_export, exchanges the
+ * CTR_COMM_HANDLE_BYTES blobs with the other ranks by any means (torch.distributed all_gather, MPI, a file) and
+ * passes all of them, in rank order, to ctr_comm_connect.  Inside one process ctr_comm_create_all does it all
+ * (the ncclCommInitAll analogue).  NCCL is optional: rank 0 calls ctr_comm_nccl_unique_id, broadcasts the 128 bytes,
+ * every rank calls ctr_comm_nccl_init (collective).  libnccl.so.2 is opened at run time.
+ *
+ * Failure detection: a rank that waits longer than the timeout (default 10 s) for a peer's flag stops waiting and
+ * raises the comm's error word; ctr_comm_check then returns CTR_ECOMM naming the missing rank.  It also forwards
+ * ncclCommGetAsyncError.  Calls on one comm must be issued in the same order on every rank. */
+typedef struct ctr_comm ctr_comm;
+#define CTR_COMM_HANDLE_BYTES 128
+#define CTR_NCCL_ID_BYTES 128
+enum { CTR_EXCHANGE_P2P = 0, CTR_EXCHANGE_NCCL = 1 };
+/* exchange_bytes >= B*X*Y*4 of the largest call this comm will serve */
+int ctr_comm_create(int nranks, int rank, int device, size_t exchange_bytes, ctr_comm** out);
+int ctr_comm_export(const ctr_comm* comm, void* handle_out);
+int ctr_comm_connect(ctr_comm* comm, const void* handles_in_rank_order);
+int ctr_comm_create_all(int nranks, const int* devices, size_t exchange_bytes, ctr_comm** out_nranks);
+int ctr_comm_nccl_unique_id(void* id_out);
+int ctr_comm_nccl_init(ctr_comm* comm, const void* id_in);
+int ctr_comm_set_timeout_ms(ctr_comm* comm, int milliseconds);
+int ctr_comm_info(const ctr_comm* comm, int* nranks, int* rank, int* connected, int* has_nccl, size_t* exchange_bytes);
+int ctr_comm_check(ctr_comm* comm);
+int ctr_comm_destroy(ctr_comm* comm);
+size_t ctr_adjoint_sharded_workspace_bytes(const ctr_comm* comm, const ctr_plan* plan, int B);
+/* dsino_local [B, A_local, W] (the plan's angles are this rank's block) -> dimg_shard [B/nranks, X, Y] */
+int ctr_radon_adjoint_sharded(ctr_comm* comm, const ctr_plan* plan, const float* dsino_local, float* dimg_shard, int B,
+                              int interp, int mode, int algo, void* workspace, size_t workspace_bytes, void* stream);
+/* angle-sharded iradon: sino_local [B, A_local, P] -> recon_shard [B/nranks, x_size, y_size]; the pi/(2A) scale of
+ * fbp_tensorflow.py:74 uses A_total.  Workspace: ctr_fbp_workspace_bytes. */
+int ctr_fbp_sharded(ctr_comm* comm, const ctr_fbp_plan* plan, const float* sino_local, int A_local, int A_total,
+                    float* recon_shard, int B, int algo, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- zero-copy DLPack entry points ---------------------------------------------------------
  * Same operations on borrowed DLTensors (kDLCUDA, float32, compact row-major).

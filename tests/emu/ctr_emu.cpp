@@ -308,4 +308,40 @@ void emu_adjoint(const float* y, int B, int X, int Y, int H, int W, int padx, in
     }
 }
 
+// Angle-sharded exact adjoint with the fused exchange, all ranks emulated in one loop (the GPU guide forbids ranks
+// that wait on one another on one device; the multi-GPU run is tests/test_gpu_multi.py).  y is the FULL cotangent
+// [B,A,W]; rank s back-projects its angle block (sharding.shard_range) and stores image b into slot s of
+// owner(b) (ctr_xg_owner / ctr_xg_index, the same routines the kernel epilogue uses); every owner then sums its
+// slots in rank order.  out [B,X,Y] is the concatenation of the owners' shards.
+int emu_adjoint_sharded(const float* y, int B, int X, int Y, int H, int W, int padx, int pady, const float* table, int A,
+                        int interp, int nranks, float* out)
+{
+    if (B % nranks != 0 || A < nranks) return -1;
+    const int Bs = B / nranks;
+    const size_t slot = (size_t)Bs * X * Y;
+    std::vector<std::vector<float>> xbuf(nranks, std::vector<float>((size_t)nranks * slot, std::nanf("")));
+    const int base = A / nranks, rem = A % nranks;
+    for (int s = 0; s < nranks; ++s) {
+        const int lo = s * base + std::min(s, rem), n = base + (s < rem ? 1 : 0);
+        std::vector<float> ys((size_t)B * n * W), part((size_t)B * X * Y);
+        for (int b = 0; b < B; ++b)
+            std::memcpy(&ys[(size_t)b * n * W], y + ((size_t)b * A + lo) * W, sizeof(float) * (size_t)n * W);
+        if (interp == CTR_NEAREST) adjoint_impl<CTR_ADJ_EXACT, CTR_NEAREST, 16>(ys.data(), B, X, Y, H, W, padx, pady, table + 8 * lo, n, 32, 8, 40, part.data());
+        else adjoint_impl<CTR_ADJ_EXACT, CTR_BILINEAR, 16>(ys.data(), B, X, Y, H, W, padx, pady, table + 8 * lo, n, 32, 8, 40, part.data());
+        for (int b = 0; b < B; ++b) {
+            const int owner = ctr_xg_owner(b, Bs);
+            for (int r = 0; r < X; ++r)
+                for (int c = 0; c < Y; ++c)
+                    xbuf[owner][ctr_xg_index(s, b - owner * Bs, Bs, r, c, X, Y)] = part[((size_t)b * X + r) * Y + c];
+        }
+    }
+    for (int o = 0; o < nranks; ++o)
+        for (size_t i = 0; i < slot; ++i) {
+            float a = xbuf[o][i];
+            for (int s = 1; s < nranks; ++s) a += xbuf[o][(size_t)s * slot + i];
+            out[(size_t)o * slot + i] = a;
+        }
+    return 0;
+}
+
 }  // extern "C"

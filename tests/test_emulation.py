@@ -162,3 +162,20 @@ def test_emulated_windowed_forward_property(emu, orc, X, Y, pad, JW, NA, Rmax, s
         assert nwin >= 0
         assert not np.isnan(s).any()
         assert rel_l2(s, orc.forward(img, th, pad, interp)) <= 1e-6
+
+
+@pytest.mark.parametrize("nranks,B,X,Y,A", [(2, 4, 12, 12, 10), (4, 8, 9, 14, 7), (8, 16, 8, 8, 24), (3, 6, 10, 7, 5)])
+def test_emulated_angle_sharded_exchange(emu, orc, nranks, B, X, Y, A):
+    """The fused exchange of the angle-sharded adjoint (slot / owner index routines of ctr_core.h), all ranks emulated
+    in one loop: the rank-ordered sum of the angle blocks' partials equals the full adjoint."""
+    rng = np.random.default_rng(5)
+    th = np.linspace(0, np.pi, A, endpoint=False)
+    H, W, padx, pady = orc.frame_of(X, Y, True)
+    t = orc.make_transforms(th, H, W)
+    y = rng.random((B, A, W), dtype=np.float32)
+    emu.emu_adjoint_sharded.restype = ctypes.c_int
+    for interp in (0, 1):
+        g = np.full((B, X, Y), np.nan, np.float32)
+        rc = emu.emu_adjoint_sharded(P(y), B, X, Y, H, W, padx, pady, P(t), A, interp, nranks, P(g))
+        assert rc == 0 and not np.isnan(g).any()
+        assert rel_l2(g, orc.adjoint_exact(y, th, X, Y, True, interp)) <= 1e-6

@@ -667,11 +667,11 @@ def run_angle(args, ctx, wl):
     want = ops.radon_adjoint(cot_full.index_select(0, own).contiguous(), full_plan, op.iid, op.mid)
     got = op.adjoint(cot)
     parity = float((got.double() - want.double()).norm() / want.double().norm())
-    ok = torch.tensor([1.0 if parity <= 1e-6 else 0.0], device=ctx.dev)
-    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     worst = ctx.max_over_ranks(parity)
-    if float(ok.item()) != 1.0:
-        raise SystemExit(f"angle-sharded adjoint differs from the single-rank adjoint: rel-L2 {worst:.3e} > 1e-6")
+    # bar: 1e-6 (float32 summation order differs between N angle blocks and one 720-angle loop; reported as
+    # comm_nranks_ok).  Beyond north_star's 1e-5 the run is not a measurement of the same operator: stop.
+    if not (worst <= 1e-5):
+        raise SystemExit(f"angle-sharded adjoint differs from the single-rank adjoint: rel-L2 {worst:.3e} > 1e-5")
     # forward blocks are disjoint rows of the single-rank sinogram: check this rank's block on a few images
     s_blk = op.forward(img[:32])
     s_ref = ops.radon_forward(img[:32], full_plan, op.iid)[:, op.a_lo:op.a_hi]
@@ -755,7 +755,7 @@ def run_angle(args, ctx, wl):
     if ctx.rank == 0:
         extra = {"kernels": rec["kernels"], "plan": op.plan.describe(B), "exchange": op.algo,
                  "parity": {"adjoint_vs_single_rank_rel_l2": worst, "forward_block_rel_l2": fwd_par, "bar": 1e-6,
-                            "comm_nranks_ok": True},
+                            "comm_nranks_ok": bool(worst <= 1e-6 and fwd_par <= 1e-6)},
                  "smem_roofline": smem_rooflines(rec, wl, A_loc, clocks)}
         extra.update(others)
         line = {

@@ -2,7 +2,7 @@
 
 Tolerance (north_star): relative L2 <= 1e-5 for the float32 projector and its
 adjoints; <Ax,y> == <x,A^T y> to float32 rounding.  FBP computes in float32 against a
-float64 oracle: relative L2 <= 2e-5.
+float64 oracle: relative L2 <= 1e-5 as well.
 """
 import numpy as np
 import pytest
@@ -268,7 +268,7 @@ def test_fbp_matches_oracle(cp, orc):
         want = orc.iradon(sino, th, xs, ys, filt)
         got = cp.iradon(torch.from_numpy(sino).cuda(), th, xs, ys, filt)
         assert got.dtype == torch.float64 and got.shape == (B, xs, ys)
-        assert rel_l2(got.cpu().numpy(), want) <= 2e-5
+        assert rel_l2(got.cpu().numpy(), want) <= TOL
     with pytest.raises(ValueError):
         cp.iradon(torch.zeros((1, 5, 16), device="cuda"), _theta(4), 8, 8, np.ones(16))
 
@@ -413,7 +413,7 @@ def test_golden_fixtures(cp):
                                interpolation=interp, adjoint=mode).cpu().numpy()
             assert rel_l2(g, z[f"grad_{mode}_{interp}"]) <= TOL
     rec = cp.iradon(torch.from_numpy(z["fbp_sino"]).cuda(), th, img.shape[1], img.shape[2], z["fbp_filter"])
-    assert rel_l2(rec.cpu().numpy(), z["fbp_recon"]) <= 2e-5
+    assert rel_l2(rec.cpu().numpy(), z["fbp_recon"]) <= TOL
 
 
 def test_errors_are_loud(cp):

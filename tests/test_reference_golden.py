@@ -4,7 +4,7 @@ drop-in Python API.  This pins what the reference's own code decides (padding, l
 summed axis, interpolation defaults, iradon conventions); the arithmetic inside the third-party ops is a
 restatement on both sides (parity unpinned there).
 
-Tolerances: float32 forward rel-L2 <= 1e-5 (north_star); iradon (float32 values on the GPU vs float64) 2e-5.
+Tolerances: float32 forward rel-L2 <= 1e-5 (north_star); iradon (float32 values on the GPU vs float64) 1e-5 too.
 """
 import os
 
@@ -113,7 +113,7 @@ def test_gpu_iradon():
     for key, xs, ys, filt in (("fbp_out_ramp", 20, 20, G["fbp_ramp"]), ("fbp_out_none", 20, 20, np.ones(32)),
                               ("fbp_out_rect", 14, 22, G["fbp_ramp"])):
         r = cp.iradon(G["fbp_sino"], G["theta12"], xs, ys, filt)
-        assert np.asarray(r).shape == G[key].shape and rel(r, G[key]) <= 2e-5, key
+        assert np.asarray(r).shape == G[key].shape and rel(r, G[key]) <= 1e-5, key
     with pytest.raises(ValueError):
         cp.iradon(G["fbp_sino"], G["theta12"][:-1], 20, 20, G["fbp_ramp"])
 

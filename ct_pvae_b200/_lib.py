@@ -51,6 +51,11 @@ SYMBOLS = {
     "ctr_radon_forward": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_size_t, _c_void_p]),
     "ctr_radon_adjoint": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_size_t, _c_void_p]),
     "ctr_radon_adjoint_scaled": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, ctypes.c_float, _c_void_p, _c_size_t, _c_void_p]),
+    "ctr_radon_forward_sel": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_int, _c_void_p, _c_size_t, _c_void_p]),
+    "ctr_radon_adjoint_sel": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, ctypes.c_float, _c_void_p, _c_int,
+                                       _c_void_p, _c_size_t, _c_void_p]),
+    "ctr_radon_loglik_sel": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, ctypes.c_float, ctypes.c_float,
+                                      _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_size_t, _c_void_p]),
     "ctr_loglik_workspace_bytes": (_c_size_t, [_c_void_p, _c_int]),
     "ctr_radon_loglik": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, ctypes.c_float, ctypes.c_float,
                                   _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_size_t, _c_void_p]),
@@ -170,10 +175,15 @@ class DLView:
 
 
 # --------------------------------------------------------------------------- plans
+PLANS_CREATED = 0     # how many ctr_plan_create calls this process has made (tools/prof_train.py, tests)
+
+
 class Plan:
     """Geometry of one project_tf_fast call, resident on one device (ctr_plan)."""
 
     def __init__(self, theta64: np.ndarray, X: int, Y: int, pad: bool, device: int):
+        global PLANS_CREATED
+        PLANS_CREATED += 1
         self.handle = _c_void_p()
         th = np.ascontiguousarray(theta64, np.float64)
         check(lib().ctr_plan_create(th.ctypes.data_as(_f64p), th.size, X, Y, int(bool(pad)), device, ctypes.byref(self.handle)))

@@ -11,6 +11,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/ctradon.h"
@@ -97,7 +98,14 @@ struct ctr_plan {
         ctr::FwdConfig fc;
         std::vector<CtrChunk> chunks;   // CTA columns
         CtrChunk* d_chunks = nullptr;
+        // one chunk per ray, in table order: the CTA columns of an angle-subset call (ctr_radon_*_sel), where the
+        // angles sharing a CTA are not known when the plan is made
+        std::vector<CtrChunk> singles;
+        CtrChunk* d_singles = nullptr;
+        size_t smem_single = 0;
     } shape[3];
+    std::vector<int> pos;      // angle -> its row in the class-sorted ray table
+    int* d_pos = nullptr;
     int sm_count = 148;
     void* d_block = nullptr;   // one device allocation: [t | tinv | rays | chunk tables]
     float* d_t = nullptr;
@@ -256,16 +264,42 @@ int ctr_plan_create(const double* theta, int A, int X, int Y, int pad, int devic
                                fc.stages, 0, false, fc.R, 1, fc.R, sh.chunks, strip_bytes);
         }
     }
-    // one allocation + one upload for all tables (plans are created per angle minibatch in training)
-    const size_t tb = (size_t)A * 8 * sizeof(float), rb = (size_t)A * sizeof(CtrRay);
-    size_t cb[3], ctot = 0;
-    for (int k = 0; k < 3; ++k) { cb[k] = p->shape[k].chunks.size() * sizeof(CtrChunk); ctot += cb[k]; }
-    std::vector<unsigned char> host(2 * tb + rb + ctot);
+    // angle-subset calls: one CTA column per ray (same strip / window sizing rules, one ray per window)
+    for (int k = 0; k < 3; ++k) {
+        ctr_plan::Shape& sh = p->shape[k];
+        const ctr::FwdConfig& fc = sh.fc;
+        if (fc.R < 1) continue;
+        size_t strip_bytes = 0;
+        const int fixed = ctr::FwdConfig::fixed_bytes(fc.angles_per_cta());
+        bool ok;
+        if (fc.windowed)
+            ok = ctr_h_build_chunks(p->rays, seg, p->geom, 1, p->W, fc.JW, fc.jchunks, ctr::kFwdNB * fc.depth * 4, fc.stages,
+                                    (size_t)(smem_optin - 2048 - fixed), true, 0, 4, 16, sh.singles, strip_bytes);
+        else
+            ok = ctr_h_build_chunks(p->rays, seg, p->geom, 1, p->W, fc.JW, fc.jchunks, ctr::kFwdNB * fc.depth * 4, fc.stages, 0, false,
+                                    fc.R, 1, fc.R, sh.singles, strip_bytes);
+        if (!ok || (int)sh.singles.size() != A) { sh.singles.clear(); continue; }   // subset calls fall back to another shape
+        sh.smem_single = (size_t)fixed + (size_t)fc.stages * strip_bytes;
+    }
+    p->pos.assign(A, 0);
+    for (int k = 0; k < A; ++k) p->pos[p->rays[k].angle] = k;
+    // one allocation + one upload for all tables
+    const size_t tb = (size_t)A * 8 * sizeof(float), rb = (size_t)A * sizeof(CtrRay), pb = align_up((size_t)A * sizeof(int), 16);
+    size_t cb[6], ctot = 0;
+    for (int k = 0; k < 3; ++k) {
+        cb[k] = p->shape[k].chunks.size() * sizeof(CtrChunk);
+        cb[3 + k] = p->shape[k].singles.size() * sizeof(CtrChunk);
+        ctot += cb[k] + cb[3 + k];
+    }
+    std::vector<unsigned char> host(2 * tb + rb + pb + ctot);
     std::memcpy(host.data(), p->t.data(), tb);
     std::memcpy(host.data() + tb, p->tinv.data(), tb);
     std::memcpy(host.data() + 2 * tb, p->rays.data(), rb);
-    for (size_t k = 0, off = 2 * tb + rb; k < 3; off += cb[k], ++k)
-        if (cb[k]) std::memcpy(host.data() + off, p->shape[k].chunks.data(), cb[k]);
+    std::memcpy(host.data() + 2 * tb + rb, p->pos.data(), (size_t)A * sizeof(int));
+    for (size_t k = 0, off = 2 * tb + rb + pb; k < 6; off += cb[k], ++k) {
+        const std::vector<CtrChunk>& v = k < 3 ? p->shape[k].chunks : p->shape[k - 3].singles;
+        if (cb[k]) std::memcpy(host.data() + off, v.data(), cb[k]);
+    }
     if ((e = cudaMalloc(&p->d_block, host.size())) != cudaSuccess ||
         (e = cudaMemcpy(p->d_block, host.data(), host.size(), cudaMemcpyHostToDevice)) != cudaSuccess) {
         int rc = fail_cuda(e, "ctr_plan_create: table upload");
@@ -276,7 +310,11 @@ int ctr_plan_create(const double* theta, int A, int X, int Y, int pad, int devic
     p->d_t = (float*)p->d_block;
     p->d_tinv = (float*)((char*)p->d_block + tb);
     p->d_rays = (CtrRay*)((char*)p->d_block + 2 * tb);
-    for (size_t k = 0, off = 2 * tb + rb; k < 3; off += cb[k], ++k) p->shape[k].d_chunks = (CtrChunk*)((char*)p->d_block + off);
+    p->d_pos = (int*)((char*)p->d_block + 2 * tb + rb);
+    for (size_t k = 0, off = 2 * tb + rb + pb; k < 6; off += cb[k], ++k) {
+        if (k < 3) p->shape[k].d_chunks = (CtrChunk*)((char*)p->d_block + off);
+        else p->shape[k - 3].d_singles = (CtrChunk*)((char*)p->d_block + off);
+    }
     *out = p;
     return CTR_OK;
 }
@@ -313,12 +351,14 @@ int ctr_plan_tables(const ctr_plan* p, float* fwd, float* inv)
 
 // which forward shape serves a batch of B: the deepest pixel record the batch fills reasonably
 // (32 images from 17 up, 8/16 from 3 lanes' worth up), else the 4-image records
-static const ctr_plan::Shape& shape_for(const ctr_plan* p, int B)
+static const ctr_plan::Shape& shape_for(const ctr_plan* p, int B, bool subset = false)
 {
     const ctr_plan::Shape& s16 = p->shape[1];
     const ctr_plan::Shape& s32 = p->shape[2];
-    const bool ok16 = s16.fc.R >= 1 && B >= 3 * s16.fc.depth, ok32 = s32.fc.R >= 1 && B > 16;
-    if (ok16 && ok32 && s16.fc.lanes == 4 && !s16.fc.windowed && !s32.fc.windowed) {
+    // angle-subset calls run one ray per CTA column (the `singles` tables)
+    const bool ok16 = s16.fc.R >= 1 && B >= 3 * s16.fc.depth && (!subset || !s16.singles.empty());
+    const bool ok32 = s32.fc.R >= 1 && B > 16 && (!subset || !s32.singles.empty());
+    if (!subset && ok16 && ok32 && s16.fc.lanes == 4 && !s16.fc.windowed && !s32.fc.windowed) {
         // Both run one CTA per SM; a 32-image CTA does twice the work of a 16-image one in 1.84x the time
         // (r1: 93 vs 51 us per wave at 128^2 x 180).  Small batches (the chunks of the host pipeline) leave the last
         // wave mostly empty, so count waves: 64 images -> 182 CTAs = 2 waves (32) vs 364 CTAs = 3 waves (16).
@@ -333,14 +373,19 @@ static const ctr_plan::Shape& shape_for(const ctr_plan* p, int B)
     if (ok16) return s16;
     return p->shape[0];
 }
-static const ctr::FwdConfig& fwd_cfg_for(const ctr_plan* p, int B) { return shape_for(p, B).fc; }
+static const ctr::FwdConfig& fwd_cfg_for(const ctr_plan* p, int B, bool subset = false) { return shape_for(p, B, subset).fc; }
 
+// one packed copy of the batch; sized for the deeper of the full-plan and the angle-subset shape of this batch size
 static size_t pack_bytes(const ctr_plan* p, int B)
 {
-    const size_t rec = (size_t)ctr::kFwdNB * fwd_cfg_for(p, B).depth;
-    const size_t G = ((size_t)B + rec - 1) / rec;
-    const size_t px0 = (size_t)p->geom[0].Vp * p->geom[0].Up, px1 = (size_t)p->geom[1].Vp * p->geom[1].Up;
-    return align_up(G * std::max(px0, px1) * rec * sizeof(float), 256);
+    size_t best = 0;
+    for (int subset = 0; subset < 2; ++subset) {
+        const size_t rec = (size_t)ctr::kFwdNB * fwd_cfg_for(p, B, subset != 0).depth;
+        const size_t G = ((size_t)B + rec - 1) / rec;
+        const size_t px0 = (size_t)p->geom[0].Vp * p->geom[0].Up, px1 = (size_t)p->geom[1].Vp * p->geom[1].Up;
+        best = std::max(best, align_up(G * std::max(px0, px1) * rec * sizeof(float), 256));
+    }
+    return best;
 }
 
 // human-readable description of the forward shape a batch of B would run (tests, bench, tuning)
@@ -387,23 +432,32 @@ size_t ctr_adjoint_workspace_bytes(const ctr_plan* p, int B)
 }
 
 // ------------------------------------------------------------------------------------------ forward
+static int adjoint_impl(const ctr_plan* p, const float* dsino, float* dimg, int B, int interp, int mode, float scale,
+                        const int* sel, int n_sel, const CtrExchange* xg, void* ws, size_t ws_bytes, void* stream, const char* who);
+static size_t spk_bytes(int B, int A, int W);
+
 struct LoglikArgs {
     const float* mask; const float* meas; const int* amap; int A_all; float pnm, sqrt_reg; float* loglik;
 };
 
 static size_t loglik_partial_bytes(const ctr_plan* p, int B)
 {
-    const ctr::FwdConfig& fc = fwd_cfg_for(p, B);
-    const size_t chunks = shape_for(p, B).chunks.size();
-    const size_t rec = (size_t)ctr::kFwdNB * fc.depth;
-    const size_t G = ((size_t)B + rec - 1) / rec;
-    return align_up(chunks * fc.jchunks * G * rec * sizeof(float), 256);
+    size_t best = 0;
+    for (int subset = 0; subset < 2; ++subset) {
+        const ctr::FwdConfig& fc = fwd_cfg_for(p, B, subset != 0);
+        const size_t chunks = subset ? (size_t)p->A : shape_for(p, B).chunks.size();   // a subset has at most A columns
+        const size_t rec = (size_t)ctr::kFwdNB * fc.depth;
+        const size_t G = ((size_t)B + rec - 1) / rec;
+        best = std::max(best, align_up(chunks * fc.jchunks * G * rec * sizeof(float), 256));
+    }
+    return best;
 }
 
 static int forward_impl(const ctr_plan* p, const float* img, float* out, int B, int interp, const LoglikArgs* ll,
-                        void* ws, size_t ws_bytes, void* stream, const char* who)
+                        const int* sel, int n_sel, void* ws, size_t ws_bytes, void* stream, const char* who)
 {
     if (!p || !img || !out) return fail(CTR_EINVAL, std::string(who) + ": NULL plan or buffer");
+    if (sel && (n_sel <= 0 || n_sel > p->A)) return fail(CTR_EINVAL, std::string(who) + ": the angle subset must have 1..A entries");
     if (B <= 0) return fail(CTR_EINVAL, std::string(who) + ": B must be positive");
     if (interp != CTR_INTERP_NEAREST && interp != CTR_INTERP_BILINEAR) return fail(CTR_EINVAL, std::string(who) + ": bad interp");
     const size_t need = ll ? ctr_loglik_workspace_bytes(p, B) : ctr_forward_workspace_bytes(p, B);
@@ -412,7 +466,12 @@ static int forward_impl(const ctr_plan* p, const float* img, float* out, int B, 
     DeviceGuard guard(p->device);
     if (!guard.ok) return fail_cuda(guard.err, "cudaSetDevice");
     cudaStream_t st = (cudaStream_t)stream;
-    const ctr::FwdConfig& fc = fwd_cfg_for(p, B);
+    const ctr_plan::Shape& sh = shape_for(p, B, sel != nullptr);
+    ctr::FwdConfig fc = sh.fc;
+    if (sel) {
+        if (sh.singles.empty()) return fail(CTR_EUNSUPPORTED, std::string(who) + ": no per-ray strip table for this geometry");
+        fc.smem = sh.smem_single;
+    }
     const int rec = ctr::kFwdNB * fc.depth;
     const int G = (B + rec - 1) / rec;            // pixel records along the batch (super-groups)
     float* pk0 = p->n_cls[0] ? (float*)ws : nullptr;
@@ -429,13 +488,15 @@ static int forward_impl(const ctr_plan* p, const float* img, float* out, int B, 
     fp.pk[0] = pk0; fp.pk[1] = pk1;
     fp.geom[0] = p->geom[0]; fp.geom[1] = p->geom[1];
     fp.rays = p->d_rays;
-    fp.chunks = shape_for(p, B).d_chunks;
+    fp.chunks = sel ? sh.d_singles : sh.d_chunks;
+    fp.sel = sel;
+    fp.pos = p->d_pos;
     fp.jwd = fc.JW * fc.lanes;
     fp.ns = fc.NS;
     fp.stages = fc.stages;
 
-    const int chunks = (int)shape_for(p, B).chunks.size();
-    fp.H = p->H; fp.W = p->W; fp.A = p->A; fp.B = B;
+    const int chunks = sel ? n_sel : (int)sh.chunks.size();
+    fp.H = p->H; fp.W = p->W; fp.A = sel ? n_sel : p->A; fp.B = B;
     fp.sino = out;
     fp.mask = nullptr; fp.meas = nullptr; fp.amap = nullptr; fp.A_all = p->A; fp.pnm = 1.f; fp.sqrt_reg = 0.f; fp.partial = nullptr;
     cudaError_t e;
@@ -463,7 +524,31 @@ static int forward_impl(const ctr_plan* p, const float* img, float* out, int B, 
 int ctr_radon_forward(const ctr_plan* p, const float* img, float* sino, int B, int interp, void* ws, size_t ws_bytes,
                       void* stream)
 {
-    return forward_impl(p, img, sino, B, interp, nullptr, ws, ws_bytes, stream, "ctr_radon_forward");
+    return forward_impl(p, img, sino, B, interp, nullptr, nullptr, 0, ws, ws_bytes, stream, "ctr_radon_forward");
+}
+
+int ctr_radon_forward_sel(const ctr_plan* p, const float* img, float* sino, int B, int interp, const int* sel, int n_sel,
+                          void* ws, size_t ws_bytes, void* stream)
+{
+    if (!sel) return fail(CTR_EINVAL, "ctr_radon_forward_sel: the angle subset is NULL");
+    return forward_impl(p, img, sino, B, interp, nullptr, sel, n_sel, ws, ws_bytes, stream, "ctr_radon_forward_sel");
+}
+
+int ctr_radon_adjoint_sel(const ctr_plan* p, const float* dsino, float* dimg, int B, int interp, int mode, float scale,
+                          const int* sel, int n_sel, void* ws, size_t ws_bytes, void* stream)
+{
+    if (!sel) return fail(CTR_EINVAL, "ctr_radon_adjoint_sel: the angle subset is NULL");
+    return adjoint_impl(p, dsino, dimg, B, interp, mode, scale, sel, n_sel, nullptr, ws, ws_bytes, stream, "ctr_radon_adjoint_sel");
+}
+
+int ctr_radon_loglik_sel(const ctr_plan* p, const float* img, const float* mask, const float* meas, const int* sel, int n_sel,
+                         float pnm, float sqrt_reg, float* loglik, float* dproj, int B, int interp, void* ws, size_t ws_bytes,
+                         void* stream)
+{
+    if (!mask || !meas || !loglik || !sel) return fail(CTR_EINVAL, "ctr_radon_loglik_sel: NULL mask, measurement, subset or output");
+    if (!(pnm > 0.f) || !(sqrt_reg >= 0.f)) return fail(CTR_EINVAL, "ctr_radon_loglik_sel: pnm must be > 0 and sqrt_reg >= 0");
+    LoglikArgs ll{mask, meas, nullptr, p ? p->A : 0, pnm, sqrt_reg, loglik};
+    return forward_impl(p, img, dproj, B, interp, &ll, sel, n_sel, ws, ws_bytes, stream, "ctr_radon_loglik_sel");
 }
 
 size_t ctr_loglik_workspace_bytes(const ctr_plan* p, int B)
@@ -480,7 +565,7 @@ int ctr_radon_loglik(const ctr_plan* p, const float* img, const float* mask, con
     if (A_all < (p ? p->A : 0) && !angle_map) return fail(CTR_EINVAL, "ctr_radon_loglik: A_all smaller than the plan's angle count");
     if (!(pnm > 0.f) || !(sqrt_reg >= 0.f)) return fail(CTR_EINVAL, "ctr_radon_loglik: pnm must be > 0 and sqrt_reg >= 0");
     LoglikArgs ll{mask, meas, angle_map, A_all, pnm, sqrt_reg, loglik};
-    return forward_impl(p, img, dproj, B, interp, &ll, ws, ws_bytes, stream, "ctr_radon_loglik");
+    return forward_impl(p, img, dproj, B, interp, &ll, nullptr, 0, ws, ws_bytes, stream, "ctr_radon_loglik");
 }
 
 // ------------------------------------------------------------------------------------------ adjoint
@@ -653,29 +738,37 @@ int ctr_fbp(const ctr_fbp_plan* p, const float* sino, int A, float* recon, int B
 // staging slots on three streams (copy-in / kernels / copy-out), so PCIe runs in both
 // directions while the kernels of another chunk execute.  Successive calls on the same pipe
 // append to the same ring: the copy-out of one call overlaps the copy-in of the next.
+// Pageable host memory (a plain NumPy array, what the reference's callers pass) is staged through
+// page-locked buffers that belong to the slots: worker threads copy chunk k+1 into its slot's pinned
+// buffer while chunk k crosses PCIe; results land in the slot's pinned buffer and are copied out to
+// the caller's array by ctr_hostpipe_wait (or when the slot comes round again).
 struct ctr_hostpipe {
     static constexpr int kSlots = 6;   // r1 trace: with 3 the next call's copy-in stalls on slots still queued for kernels
     const ctr_plan* plan = nullptr;
-    int device = 0, chunk = 0, adj_mult = 1;
+    int device = 0, chunk = 0;
     size_t buf_bytes = 0, ws_bytes = 0;
     cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
     struct Slot {
         float* d_in = nullptr; float* d_out = nullptr; void* ws = nullptr;
+        float* h_in = nullptr; float* h_out = nullptr;        // page-locked staging, allocated on first pageable use
         cudaEvent_t in_done = nullptr, comp_done = nullptr, out_done = nullptr;
+        float* user_out = nullptr; size_t user_out_bytes = 0;  // pending copy h_out -> caller's pageable array
     } slot[kSlots];
     long long seq = 0;     // chunks issued so far
     std::mutex mu;
-    // developer trace (CTR_HOSTPIPE_TRACE): timestamps of every chunk's stages, printed by ctr_hostpipe_wait
+    // diagnostics (ctr_hostpipe_trace): timestamps of every chunk's stages, printed by ctr_hostpipe_wait
     struct Trace { int kind, n; cudaEvent_t in0, in1, c0, c1, o0, o1; };
     std::vector<Trace> trace;
     cudaEvent_t t0 = nullptr;
-    bool tracing = false;  // ctr_hostpipe_trace
+    bool tracing = false;
 };
 
 static void hostpipe_free(ctr_hostpipe* hp)
 {
     for (auto& s : hp->slot) {
         cudaFree(s.d_in); cudaFree(s.d_out); cudaFree(s.ws);
+        if (s.h_in) cudaFreeHost(s.h_in);
+        if (s.h_out) cudaFreeHost(s.h_out);
         if (s.in_done) cudaEventDestroy(s.in_done);
         if (s.comp_done) cudaEventDestroy(s.comp_done);
         if (s.out_done) cudaEventDestroy(s.out_done);
@@ -696,12 +789,9 @@ int ctr_hostpipe_create(const ctr_plan* plan, int chunk, ctr_hostpipe** out)
     ctr_hostpipe* hp = new (std::nothrow) ctr_hostpipe();
     if (!hp) return fail(CTR_EINVAL, "ctr_hostpipe_create: out of host memory");
     hp->plan = plan; hp->device = plan->device; hp->chunk = chunk;
-    hp->adj_mult = 1;   // r1: larger adjoint chunks were measured and lost (1.54 vs 1.43 ms per C2 step)
-    const int cap = chunk * hp->adj_mult;
-    const size_t img_b = (size_t)cap * plan->X * plan->Y * sizeof(float), sino_b = (size_t)cap * plan->A * plan->W * sizeof(float);
+    const size_t img_b = (size_t)chunk * plan->X * plan->Y * sizeof(float), sino_b = (size_t)chunk * plan->A * plan->W * sizeof(float);
     hp->buf_bytes = align_up(std::max(img_b, sino_b), 256);
-    hp->ws_bytes = std::max(std::max(ctr_forward_workspace_bytes(plan, chunk), ctr_adjoint_workspace_bytes(plan, chunk)),
-                            std::max(ctr_forward_workspace_bytes(plan, cap), ctr_adjoint_workspace_bytes(plan, cap)));
+    hp->ws_bytes = std::max(ctr_forward_workspace_bytes(plan, chunk), ctr_adjoint_workspace_bytes(plan, chunk));
     cudaError_t e = cudaSuccess;
     auto ok = [&](cudaError_t r) { if (e == cudaSuccess) e = r; return e == cudaSuccess; };
     ok(cudaStreamCreateWithFlags(&hp->s_in, cudaStreamNonBlocking));
@@ -729,23 +819,65 @@ int ctr_hostpipe_destroy(ctr_hostpipe* hp)
     return CTR_OK;
 }
 
-// kind 0: forward (in = images [B,X,Y], out = sinograms [B,A,W]); kind 1: adjoint (the mirror)
-static int hostpipe_run(ctr_hostpipe* hp, int kind, const float* in_host, float* out_host, int B, int interp, int mode,
-                        const char* who)
+// is this host pointer page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory)?
+static bool host_is_pinned(const void* p)
 {
-    if (!hp || !in_host || !out_host) return fail(CTR_EINVAL, std::string(who) + ": NULL pipe or buffer");
-    if (B <= 0) return fail(CTR_EINVAL, std::string(who) + ": B must be positive");
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+// host-to-host copy between a caller's pageable array and a slot's pinned buffer, split over a few threads
+// (one core moves ~10 GB/s, less than one PCIe Gen5 x16 direction)
+static void host_copy(void* dst, const void* src, size_t bytes)
+{
+    constexpr size_t kMinPart = 1u << 20;
+    int parts = (int)std::min<size_t>(4, bytes / kMinPart);
+    if (parts <= 1) { std::memcpy(dst, src, bytes); return; }
+    const size_t per = align_up((bytes + parts - 1) / parts, 4096);
+    std::vector<std::thread> th;
+    for (int k = 1; k < parts; ++k) {
+        const size_t lo = (size_t)k * per;
+        if (lo >= bytes) break;
+        const size_t n = std::min(per, bytes - lo);
+        th.emplace_back([=] { std::memcpy((char*)dst + lo, (const char*)src + lo, n); });
+    }
+    std::memcpy(dst, src, std::min(per, bytes));
+    for (auto& t : th) t.join();
+}
+
+// deliver a slot's staged result to the caller's pageable array (if one is pending)
+static int hostpipe_drain_slot(ctr_hostpipe::Slot& s)
+{
+    if (!s.user_out) return CTR_OK;
+    CTR_CUDA(cudaEventSynchronize(s.out_done));
+    host_copy(s.user_out, s.h_out, s.user_out_bytes);
+    s.user_out = nullptr;
+    return CTR_OK;
+}
+
+// kind 0: forward (in = images [B,X,Y], out = sinograms [B,A,W]); kind 1: adjoint (the mirror)
+static int hostpipe_run_locked(ctr_hostpipe* hp, int kind, const float* in_host, float* out_host, int B, int interp, int mode)
+{
     const ctr_plan* p = hp->plan;
-    DeviceGuard guard(hp->device);
-    if (!guard.ok) return fail_cuda(guard.err, "cudaSetDevice");
-    std::lock_guard<std::mutex> lk(hp->mu);
     const size_t img_n = (size_t)p->X * p->Y, sino_n = (size_t)p->A * p->W;
     const size_t in_n = kind == 0 ? img_n : sino_n, out_n = kind == 0 ? sino_n : img_n;
-    const int step = kind == 1 ? hp->chunk * hp->adj_mult : hp->chunk;
-    for (int lo = 0; lo < B; lo += step) {
-        const int n = std::min(step, B - lo);
+    const bool in_pinned = host_is_pinned(in_host), out_pinned = host_is_pinned(out_host);
+    for (int lo = 0; lo < B; lo += hp->chunk) {
+        const int n = std::min(hp->chunk, B - lo);
         ctr_hostpipe::Slot& s = hp->slot[hp->seq % ctr_hostpipe::kSlots];
         const bool reused = hp->seq >= ctr_hostpipe::kSlots;
+        int rc = hostpipe_drain_slot(s);                       // a pageable result of the slot's previous chunk
+        if (rc != CTR_OK) return rc;
+        const float* src = in_host + (size_t)lo * in_n;
+        const size_t in_bytes = (size_t)n * in_n * sizeof(float), out_bytes = (size_t)n * out_n * sizeof(float);
+        if (!in_pinned) {
+            if (!s.h_in) CTR_CUDA(cudaHostAlloc((void**)&s.h_in, hp->buf_bytes, cudaHostAllocDefault));
+            if (reused) CTR_CUDA(cudaEventSynchronize(s.in_done));   // the previous upload from this staging buffer
+            host_copy(s.h_in, src, in_bytes);
+            src = s.h_in;
+        }
+        if (!out_pinned && !s.h_out) CTR_CUDA(cudaHostAlloc((void**)&s.h_out, hp->buf_bytes, cudaHostAllocDefault));
         if (reused) CTR_CUDA(cudaStreamWaitEvent(hp->s_in, s.comp_done, 0));     // staging input consumed
         const bool tracing = hp->tracing;
         ctr_hostpipe::Trace tr{kind, n, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -754,25 +886,48 @@ static int hostpipe_run(ctr_hostpipe* hp, int kind, const float* in_host, float*
             if (!hp->t0) { cudaEventCreate(&hp->t0); cudaEventRecord(hp->t0, hp->s_in); }
             cudaEventRecord(tr.in0, hp->s_in);
         }
-        CTR_CUDA(cudaMemcpyAsync(s.d_in, in_host + (size_t)lo * in_n, (size_t)n * in_n * sizeof(float), cudaMemcpyHostToDevice, hp->s_in));
+        CTR_CUDA(cudaMemcpyAsync(s.d_in, src, in_bytes, cudaMemcpyHostToDevice, hp->s_in));
         CTR_CUDA(cudaEventRecord(s.in_done, hp->s_in));
         if (tracing) cudaEventRecord(tr.in1, hp->s_in);
         CTR_CUDA(cudaStreamWaitEvent(hp->s_comp, s.in_done, 0));
         if (reused) CTR_CUDA(cudaStreamWaitEvent(hp->s_comp, s.out_done, 0));    // staging output copied out
         if (tracing) cudaEventRecord(tr.c0, hp->s_comp);
-        const int rc = kind == 0 ? ctr_radon_forward(p, s.d_in, s.d_out, n, interp, s.ws, hp->ws_bytes, hp->s_comp)
-                                 : ctr_radon_adjoint(p, s.d_in, s.d_out, n, interp, mode, s.ws, hp->ws_bytes, hp->s_comp);
+        rc = kind == 0 ? ctr_radon_forward(p, s.d_in, s.d_out, n, interp, s.ws, hp->ws_bytes, hp->s_comp)
+                       : ctr_radon_adjoint(p, s.d_in, s.d_out, n, interp, mode, s.ws, hp->ws_bytes, hp->s_comp);
         if (rc != CTR_OK) return rc;
         CTR_CUDA(cudaEventRecord(s.comp_done, hp->s_comp));
         if (tracing) cudaEventRecord(tr.c1, hp->s_comp);
         CTR_CUDA(cudaStreamWaitEvent(hp->s_out, s.comp_done, 0));
         if (tracing) cudaEventRecord(tr.o0, hp->s_out);
-        CTR_CUDA(cudaMemcpyAsync(out_host + (size_t)lo * out_n, s.d_out, (size_t)n * out_n * sizeof(float), cudaMemcpyDeviceToHost, hp->s_out));
+        float* dst = out_pinned ? out_host + (size_t)lo * out_n : s.h_out;
+        CTR_CUDA(cudaMemcpyAsync(dst, s.d_out, out_bytes, cudaMemcpyDeviceToHost, hp->s_out));
         CTR_CUDA(cudaEventRecord(s.out_done, hp->s_out));
+        if (!out_pinned) { s.user_out = out_host + (size_t)lo * out_n; s.user_out_bytes = out_bytes; }
         if (tracing) { cudaEventRecord(tr.o1, hp->s_out); hp->trace.push_back(tr); }
         ++hp->seq;
     }
     return CTR_OK;
+}
+
+static int hostpipe_run(ctr_hostpipe* hp, int kind, const float* in_host, float* out_host, int B, int interp, int mode,
+                        const char* who)
+{
+    if (!hp || !in_host || !out_host) return fail(CTR_EINVAL, std::string(who) + ": NULL pipe or buffer");
+    if (B <= 0) return fail(CTR_EINVAL, std::string(who) + ": B must be positive");
+    DeviceGuard guard(hp->device);
+    if (!guard.ok) return fail_cuda(guard.err, "cudaSetDevice");
+    std::lock_guard<std::mutex> lk(hp->mu);
+    const int rc = hostpipe_run_locked(hp, kind, in_host, out_host, B, interp, mode);
+    if (rc != CTR_OK) {
+        // chunks enqueued before the failure still read / write the caller's buffers: let all three streams run
+        // dry before the error (and the right to release those buffers) goes back to the caller
+        const std::string msg = g_err;
+        cudaStreamSynchronize(hp->s_in); cudaStreamSynchronize(hp->s_comp); cudaStreamSynchronize(hp->s_out);
+        for (auto& s : hp->slot) s.user_out = nullptr;
+        (void)cudaGetLastError();
+        g_err = msg;
+    }
+    return rc;
 }
 
 int ctr_hostpipe_forward(ctr_hostpipe* hp, const float* img_host, float* sino_host, int B, int interp)
@@ -801,8 +956,12 @@ int ctr_hostpipe_wait(ctr_hostpipe* hp)
     if (!hp) return fail(CTR_EINVAL, "ctr_hostpipe_wait: pipe is NULL");
     DeviceGuard guard(hp->device);
     if (!guard.ok) return fail_cuda(guard.err, "cudaSetDevice");
-    CTR_CUDA(cudaStreamSynchronize(hp->s_out));   // every result of every call issued so far is in host memory
     std::lock_guard<std::mutex> lk(hp->mu);
+    CTR_CUDA(cudaStreamSynchronize(hp->s_out));   // every result of every call issued so far has left the device
+    for (auto& s : hp->slot) {                     // ... and pageable results go from the staging buffers to the caller
+        const int rc = hostpipe_drain_slot(s);
+        if (rc != CTR_OK) return rc;
+    }
     if (!hp->trace.empty()) {
         for (auto& t : hp->trace) {
             float v[6];
@@ -822,6 +981,9 @@ int ctr_hostpipe_done(ctr_hostpipe* hp)
 {
     if (!hp) return fail(CTR_EINVAL, "ctr_hostpipe_done: pipe is NULL");
     DeviceGuard guard(hp->device);
+    std::lock_guard<std::mutex> lk(hp->mu);
+    for (auto& s : hp->slot)
+        if (s.user_out) return 0;                  // a pageable result still waits for ctr_hostpipe_wait to deliver it
     const cudaError_t e = cudaStreamQuery(hp->s_out);
     if (e == cudaSuccess) return 1;
     if (e == cudaErrorNotReady) return 0;

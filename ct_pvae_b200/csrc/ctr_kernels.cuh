@@ -184,6 +184,9 @@ struct FwdParams {
     CtrClassGeom geom[2];
     const CtrRay* rays;     // class-sorted ray table [A]
     const CtrChunk* chunks; // [gridDim.x] rays, class, strip height and column window of every CTA column
+                            // (angle-subset calls: the per-ray table, indexed through sel and pos)
+    const int* sel;         // angle subset: CTA column x serves angle sel[x] and writes sinogram row x; null = whole plan
+    const int* pos;         // [A] angle -> row of the ray table
     int H, W, A, B;
     int jwd, ns;            // consumer threads per angle slot (JW bins x DEPTH groups) and angle slots; block = jwd*ns + 32
     int stages;             // strip buffers in the shared-memory ring (2..4)
@@ -233,7 +236,7 @@ __global__ void __launch_bounds__(REUSE ? kFwdReuseThreads : kFwdMaxThreads, 1) 
     CtrRay* rays_s = reinterpret_cast<CtrRay*>(smem_raw + 128);              // NA rays
     const int rays_bytes = round_up(NA * (int)sizeof(CtrRay), 128);
 
-    const CtrChunk ch = p.chunks[blockIdx.x];
+    const CtrChunk ch = p.sel ? p.chunks[p.pos[p.sel[blockIdx.x]]] : p.chunks[blockIdx.x];
     const int cls = ch.cls, first = ch.first, cnt = ch.cnt;
     const int g = blockIdx.z, jz = blockIdx.y;
     const CtrClassGeom geom = cls ? p.geom[1] : p.geom[0];  // static indices: stays in registers
@@ -355,8 +358,10 @@ __global__ void __launch_bounds__(REUSE ? kFwdReuseThreads : kFwdMaxThreads, 1) 
         for (int q = 0; q < KA; ++q) {
             const int la = lbase + q;
             if (la < cnt && j < p.W) {
-                const int a = rays_s[la].angle;
-                const int ao = (EPI && p.amap) ? p.amap[a] : a;
+                // sinogram row; column of mask / measurement (a subset gathers them at the plan's angle index, like
+                // the reference's tf.gather at angles_i, helper_functions.py:355-357)
+                const int a = p.sel ? (int)blockIdx.x : rays_s[la].angle;
+                const int ao = p.sel ? rays_s[la].angle : ((EPI && p.amap) ? p.amap[a] : a);
 #pragma unroll
                 for (int n = 0; n < NB; ++n) {
                     const int b = (g * DEPTH + gsub) * NB + (n ^ swz);   // register n holds image n ^ swz of the lane's block

@@ -89,7 +89,7 @@ def pad_phantom(phantom, dim=3, integrate_vae=False):
     return out.numpy() if was_numpy else out
 
 
-def _project_bxy(img_bxy: torch.Tensor, theta, pad: bool, interpolation: str, adjoint: str, async_op: bool = False):
+def _project_bxy(img_bxy: torch.Tensor, theta, pad: bool, interpolation: str, adjoint: str, async_op: bool = False, out=None):
     """[B,X,Y] (any float dtype, any device) -> [B,A,W] float32 on the compute device."""
     if interpolation not in ops.INTERP:
         raise ValueError(f"interpolation must be 'nearest' or 'bilinear', got {interpolation!r}")
@@ -101,20 +101,25 @@ def _project_bxy(img_bxy: torch.Tensor, theta, pad: bool, interpolation: str, ad
     if hostpipe.eligible(img_bxy):
         # host (pinned) batch: overlap copy-in / kernels / copy-out chunk by chunk; result stays on the host
         iid = ops.INTERP[interpolation]
-        return hostpipe.forward_host(plan, img_bxy, iid, async_op=async_op)
-    if async_op:
-        raise ValueError("async_op=True needs a pinned, contiguous float32 host batch of >= 32 images")
+        return hostpipe.forward_host(plan, img_bxy, iid, async_op=async_op, out=out)
+    if async_op or out is not None:
+        raise ValueError("async_op / out need a contiguous float32 host batch of >= 32 images")
     x = img_bxy.to(device=dev, dtype=torch.float32, non_blocking=True)
     return ops.project(x, plan, ops.INTERP[interpolation], ops.ADJOINT[adjoint])
 
 
 def project_tf_fast(phantom, theta, pad=False, dim=3, integrate_vae=False, *, interpolation="nearest",
-                    adjoint="exact", async_op=False):
+                    adjoint="exact", async_op=False, out=None):
     """Parallel-beam Radon transform of every image / channel (reference :80-123).
 
     phantom is ``[X,Y,Z]`` (dim=3), ``[X,Y]`` (dim=2) or, with integrate_vae,
     ``[B,X,Y,1]``.  Returns ``[A,P,Z]``, ``[A,P,1]`` or ``[B,A,P,1]``: bin ``j`` of angle
     ``a`` is the sum over rows of the image rotated by ``-theta[a]`` about its centre.
+
+    Host batches (``integrate_vae`` with >= 32 float32 images in a CPU tensor or NumPy array) run through the
+    library's chunked copy / compute pipeline.  ``async_op=True`` then returns ``(result, handle)``: the page-locked
+    result may be read after ``handle.wait()``; ``out=`` (a float32 CPU tensor ``[B,A,P]``, ideally pinned) receives
+    the result instead of a new buffer.
     """
     t, was_numpy = _as_tensor(phantom)
     if not t.dtype.is_floating_point:
@@ -124,10 +129,11 @@ def project_tf_fast(phantom, theta, pad=False, dim=3, integrate_vae=False, *, in
         if t.dim() != 4 or t.shape[3] != 1:
             raise ValueError("integrate_vae expects [batch, x, y, 1]")
         if async_op:
-            # pinned host batch: returns (result, handle); the result may be read after handle.wait()
-            sino, handle = _project_bxy(t[..., 0], theta, pad, interpolation, adjoint, async_op=True)
-            return sino.unsqueeze(-1), handle
-        sino = _project_bxy(t[..., 0], theta, pad, interpolation, adjoint)      # [B,A,W]
+            # host batch: returns (result, handle); the result may be read after handle.wait()
+            sino, handle = _project_bxy(t[..., 0], theta, pad, interpolation, adjoint, async_op=True, out=out)
+            sino = sino.unsqueeze(-1)
+            return (sino.numpy() if was_numpy else sino), handle
+        sino = _project_bxy(t[..., 0], theta, pad, interpolation, adjoint, out=out)      # [B,A,W]
         out = sino.unsqueeze(-1)
     else:
         if async_op:
@@ -158,7 +164,7 @@ def project_tf_low_mem(phantom, theta, pad=False, *, interpolation="bilinear", a
 
 
 def backproject(sinogram, theta, x_size, y_size, pad=False, *, interpolation="nearest", adjoint="exact",
-                async_op=False):
+                async_op=False, out=None):
     """Adjoint of ``project_tf_fast(..., integrate_vae=True)`` as a function:
     ``[B,A,P,1]`` (or ``[B,A,P]``) -> ``[B,x_size,y_size,1]`` (or ``[B,x_size,y_size]``).
     This is what autograd calls; exposed for matched iterative solvers and tests."""
@@ -171,12 +177,13 @@ def backproject(sinogram, theta, x_size, y_size, pad=False, *, interpolation="ne
     if hostpipe.eligible(s3):
         iid, mid = ops.INTERP[interpolation], ops.ADJOINT[adjoint]
         if async_op:
-            g, handle = hostpipe.adjoint_host(plan, s3, iid, mid, async_op=True)
-            return (g.unsqueeze(-1) if squeeze else g), handle
-        g = hostpipe.adjoint_host(plan, s3, iid, mid)
+            g, handle = hostpipe.adjoint_host(plan, s3, iid, mid, async_op=True, out=out)
+            g = g.unsqueeze(-1) if squeeze else g
+            return (g.numpy() if was_numpy else g), handle
+        g = hostpipe.adjoint_host(plan, s3, iid, mid, out=out)
         return _finish(g.unsqueeze(-1) if squeeze else g, t, was_numpy)
-    if async_op:
-        raise ValueError("async_op=True needs a pinned, contiguous float32 host batch of >= 32 sinograms")
+    if async_op or out is not None:
+        raise ValueError("async_op / out need a contiguous float32 host batch of >= 32 sinograms")
     y = s3.to(device=dev, dtype=torch.float32)
     g = ops.radon_adjoint(y, plan, ops.INTERP[interpolation], ops.ADJOINT[adjoint])
     return _finish(g.unsqueeze(-1) if squeeze else g, t, was_numpy)

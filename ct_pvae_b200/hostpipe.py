@@ -13,7 +13,6 @@ from __future__ import annotations
 
 import collections
 import ctypes
-import os
 import threading
 
 import torch
@@ -22,8 +21,10 @@ from . import _lib
 
 
 def eligible(x: torch.Tensor, min_batch: int = 32) -> bool:
+    """Host batches that take the chunked pipeline: contiguous float32 CPU tensors of >= min_batch items, page-locked
+    (copied by DMA directly) or pageable (a NumPy array: staged through the pipe's pinned ring by the library)."""
     return (x.device.type == "cpu" and x.dtype == torch.float32 and x.dim() >= 1 and x.shape[0] >= min_batch
-            and x.is_pinned() and x.is_contiguous() and not x.requires_grad)
+            and x.is_contiguous() and not x.requires_grad)
 
 
 class NativePipe:
@@ -41,16 +42,27 @@ class NativePipe:
         _lib.check(_lib.lib().ctr_hostpipe_adjoint(self.handle, y_host.data_ptr(), out_host.data_ptr(), int(y_host.shape[0]), interp, mode))
 
     def wait(self) -> None:
-        _lib.check(_lib.lib().ctr_hostpipe_wait(self.handle))
+        if self.handle:          # a closed pipe has run dry (close() synchronises its streams): nothing left to wait for
+            _lib.check(_lib.lib().ctr_hostpipe_wait(self.handle))
 
     def done(self) -> bool:
+        if not self.handle:
+            return True
         rc = _lib.lib().ctr_hostpipe_done(self.handle)
         if rc < 0:
             _lib.check(rc)
         return rc == 1
 
+    def trace(self, on: bool = True) -> None:
+        """Record every chunk's copy-in / kernel / copy-out interval; the next wait() prints them to stderr."""
+        if self.handle:
+            _lib.check(_lib.lib().ctr_hostpipe_trace(self.handle, int(bool(on))))
+
     def close(self) -> None:
         if self.handle:
+            # outstanding HostResult handles may still point here: deliver their pageable results first, then the
+            # destroy call synchronises all three streams before anything is freed
+            _lib.lib().ctr_hostpipe_wait(self.handle)
             _lib.lib().ctr_hostpipe_destroy(self.handle)
             self.handle = ctypes.c_void_p()
 
@@ -89,13 +101,31 @@ _pipes_lock = threading.Lock()
 _MAX_PIPES = 4
 
 
+_chunk_override = {"fwd": 0, "adj": 0}
+_trace_all = False
+
+
+def set_chunk(fwd: int = 0, adj: int = 0) -> None:
+    """Force the images per chunk of forward / adjoint host calls (0 = automatic, see chunk_for).  For tests of the
+    staging ring (small chunks: slot reuse, ragged last chunk) and tuning probes."""
+    _chunk_override["fwd"], _chunk_override["adj"] = int(fwd), int(adj)
+
+
+def set_trace(on: bool) -> None:
+    """Every pipe created or used from now on records its chunks' timeline (printed by wait())."""
+    global _trace_all
+    _trace_all = bool(on)
+    with _pipes_lock:
+        for pipe in _pipes.values():
+            pipe.trace(on)
+
+
 def chunk_for(plan, B: int, kind: str) -> int:
     """Images per chunk: four chunks per call, but never so little work that a chunk's launches leave most of the
     148 SMs idle (r1 measurement at 256 x 128^2 x 180: 1.39 ms per step with 64-image chunks, 2.0 ms with 32);
     whole 16-image pixel records."""
-    env = os.environ.get("CTR_HOST_CHUNK_" + kind.upper()) or os.environ.get("CTR_HOST_CHUNK")
-    if env:
-        return max(1, int(env))
+    if _chunk_override[kind] > 0:
+        return _chunk_override[kind]
     work = plan.A * plan.X * plan.Y                      # pixel-angle updates per image
     by_work = -(-180_000_000 // work)                    # 64 images at 128^2 x 180, 1 at 512^2 x 720
     per = max(by_work, (B + 3) // 4)
@@ -103,15 +133,16 @@ def chunk_for(plan, B: int, kind: str) -> int:
 
 
 def get_pipe(plan: "_lib.Plan", chunk: int, kind: str) -> NativePipe:
-    # forward and adjoint calls get separate pipes (own streams and staging): their kernels may then run
-    # concurrently, the partial last wave of one filling SMs the other leaves idle
-    key = (id(plan), chunk, kind if os.environ.get("CTR_HOST_SPLIT_PIPES") else "")
+    # forward and adjoint calls of one plan share a pipe (r1: separate pipes measured 1.49 vs 1.39 ms per C2 step)
+    key = (id(plan), chunk)
     with _pipes_lock:
         pipe = _pipes.get(key)
         if pipe is not None and pipe.plan is plan:
             _pipes.move_to_end(key)
             return pipe
         pipe = NativePipe(plan, chunk)
+        if _trace_all:
+            pipe.trace(True)
         _pipes[key] = pipe
         while len(_pipes) > _MAX_PIPES:
             _, old = _pipes.popitem(last=False)
@@ -127,25 +158,26 @@ def clear_pipes() -> None:
         _pipes.clear()
 
 
-def _run(plan, x_host: torch.Tensor, out_shape, async_op: bool, issue, kind: str):
+def _run(plan, x_host: torch.Tensor, out_shape, async_op: bool, issue, kind: str, out=None):
     pipe = get_pipe(plan, chunk_for(plan, int(x_host.shape[0]), kind), kind)
-    out = torch.empty(out_shape, dtype=torch.float32, pin_memory=True)
-    try:
-        issue(pipe, out)
-    except Exception:
-        pipe.wait()        # chunks already enqueued still reference the host buffers
-        raise
+    if out is None:
+        # page-locked result (torch's caching pinned allocator: no cudaHostAlloc after warm-up); NumPy callers get a
+        # view of it
+        out = torch.empty(out_shape, dtype=torch.float32, pin_memory=True)
+    elif tuple(out.shape) != tuple(out_shape) or out.dtype != torch.float32 or out.device.type != "cpu" or not out.is_contiguous():
+        raise ValueError(f"out must be a contiguous float32 CPU tensor of shape {tuple(out_shape)}")
+    issue(pipe, out)       # on failure the library has already let its three streams run dry
     if async_op:
         return out, HostResult(pipe, (x_host, out))
     pipe.wait()
     return out
 
 
-def forward_host(plan, x_host: torch.Tensor, interp: int, async_op: bool = False):
-    """[B,X,Y] pinned float32 -> [B,A,W] pinned float32 (project_tf_fast on a host batch)."""
-    return _run(plan, x_host, (x_host.shape[0], plan.A, plan.W), async_op, lambda pipe, out: pipe.forward(x_host, out, interp), "fwd")
+def forward_host(plan, x_host: torch.Tensor, interp: int, async_op: bool = False, out=None):
+    """[B,X,Y] host float32 (pinned or pageable) -> [B,A,W] pinned float32 (project_tf_fast on a host batch)."""
+    return _run(plan, x_host, (x_host.shape[0], plan.A, plan.W), async_op, lambda pipe, o: pipe.forward(x_host, o, interp), "fwd", out)
 
 
-def adjoint_host(plan, y_host: torch.Tensor, interp: int, mode: int, async_op: bool = False):
-    """[B,A,W] pinned float32 -> [B,X,Y] pinned float32."""
-    return _run(plan, y_host, (y_host.shape[0], plan.X, plan.Y), async_op, lambda pipe, out: pipe.adjoint(y_host, out, interp, mode), "adj")
+def adjoint_host(plan, y_host: torch.Tensor, interp: int, mode: int, async_op: bool = False, out=None):
+    """[B,A,W] host float32 (pinned or pageable) -> [B,X,Y] pinned float32."""
+    return _run(plan, y_host, (y_host.shape[0], plan.X, plan.Y), async_op, lambda pipe, o: pipe.adjoint(y_host, o, interp, mode), "adj", out)

@@ -39,11 +39,21 @@ def calculate_log_prob_M_given_R(output_sample, mask, proj_sample, poisson_noise
                                  angles_i=None, pad=True, *, interpolation="nearest", adjoint="exact"):
     """Drop-in (reference :336-368): returns log p(M | R) per ray, ``[B,A',P,1]``."""
     th, idx = _gather_theta(theta, angles_i)
-    if idx is not None:
-        sel = torch.as_tensor(idx, device=mask.device)
-        mask = mask.index_select(1, sel)
-        proj_sample = proj_sample.index_select(1, sel.to(proj_sample.device))
-    proj = project_tf_fast(output_sample, th, pad=pad, dim=2, integrate_vae=True, interpolation=interpolation, adjoint=adjoint)
+    if idx is None or not (isinstance(output_sample, torch.Tensor) and output_sample.is_cuda):
+        if idx is not None:
+            sel = torch.as_tensor(idx, device=mask.device)
+            mask = mask.index_select(1, sel)
+            proj_sample = proj_sample.index_select(1, sel.to(proj_sample.device))
+        proj = project_tf_fast(output_sample, th, pad=pad, dim=2, integrate_vae=True, interpolation=interpolation, adjoint=adjoint)
+    else:
+        # device tensors + an angle minibatch: one plan over all the angles, the subset as an index list
+        dev = output_sample.device
+        th_all = ops.theta_to_host(theta).astype(np.float32).astype(np.float64)
+        plan = _lib.get_plan(th_all, int(output_sample.shape[1]), int(output_sample.shape[2]), bool(pad), dev.index or 0)
+        sel = torch.as_tensor(idx, dtype=torch.int32, device=dev)
+        mask = mask.to(dev).index_select(1, sel.long())
+        proj_sample = proj_sample.to(dev).index_select(1, sel.long())
+        proj = ops.project(output_sample[..., 0].to(torch.float32), plan, ops.INTERP[interpolation], ops.ADJOINT[adjoint], sel).unsqueeze(-1)
     pm = proj * mask.to(proj.device)[:, :, None, None]
     scale = sqrt_reg + torch.sqrt(pm / poisson_noise_multiplier + sqrt_reg)
     y = proj_sample.to(proj.device).unsqueeze(-1)
@@ -57,15 +67,22 @@ def log_prob_M_given_R_sum(output_sample, mask, proj_sample, poisson_noise_multi
     if output_sample.dim() != 4 or output_sample.shape[3] != 1:
         raise ValueError("output_sample must be [batch, x, y, 1]")
     dev = _compute_device(output_sample)
-    th, idx = _gather_theta(theta, angles_i)
-    plan = _lib.get_plan(th, int(output_sample.shape[1]), int(output_sample.shape[2]), bool(pad), dev.index or 0)
+    # ONE plan over all the angles serves every angle minibatch: the subset travels as an index list (no plan is
+    # created, uploaded or freed on the iteration path).  The reference casts the gathered angles to float32 (:355);
+    # the plan's transform table is built from float32(-theta) either way, so the table rows are the same.
+    th_all = ops.theta_to_host(theta)
+    if angles_i is not None:
+        th_all = th_all.astype(np.float32).astype(np.float64)
+    plan = _lib.get_plan(th_all, int(output_sample.shape[1]), int(output_sample.shape[2]), bool(pad), dev.index or 0)
     img = output_sample[..., 0].to(device=dev, dtype=torch.float32)
     mask_d = mask.to(device=dev, dtype=torch.float32)
     meas_d = proj_sample.to(device=dev, dtype=torch.float32)
-    amap = None if idx is None else torch.as_tensor(idx, dtype=torch.int32, device=dev)
+    sel = None
+    if angles_i is not None:
+        sel = torch.as_tensor(angles_i).reshape(-1).to(device=dev, dtype=torch.int32)
     iid, mid = ops.INTERP[interpolation], ops.ADJOINT[adjoint]
     if img.requires_grad and torch.is_grad_enabled():
-        ll = ops.LoglikFunction.apply(img, plan, mask_d, meas_d, amap, float(poisson_noise_multiplier), float(sqrt_reg), iid, mid)
+        ll = ops.LoglikFunction.apply(img, plan, mask_d, meas_d, None, float(poisson_noise_multiplier), float(sqrt_reg), iid, mid, sel)
     else:
-        ll, _ = ops.radon_loglik(img, plan, mask_d, meas_d, amap, float(poisson_noise_multiplier), float(sqrt_reg), iid)
+        ll, _ = ops.radon_loglik(img, plan, mask_d, meas_d, None, float(poisson_noise_multiplier), float(sqrt_reg), iid, sel)
     return ll if per_image else ll.sum()

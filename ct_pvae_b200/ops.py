@@ -43,12 +43,32 @@ def theta_to_host(theta) -> np.ndarray:
     return np.ascontiguousarray(th.reshape(-1), dtype=np.float64)
 
 
-def radon_forward(img: torch.Tensor, plan: _lib.Plan, interp: int) -> torch.Tensor:
-    """img [B,X,Y] float32 CUDA -> sino [B,A,W] float32 CUDA (ctr_radon_forward_dl)."""
+def _check_sel(sel, plan: _lib.Plan, device) -> torch.Tensor:
+    """Angle subset as the device int32 index list the *_sel entry points take."""
+    if not isinstance(sel, torch.Tensor):
+        sel = torch.as_tensor(np.asarray(sel).reshape(-1), dtype=torch.int32)
+    sel = sel.to(device=device, dtype=torch.int32).contiguous().reshape(-1)
+    if sel.numel() < 1 or sel.numel() > plan.A:
+        raise ValueError("the angle subset must have between 1 and A entries")
+    return sel
+
+
+def radon_forward(img: torch.Tensor, plan: _lib.Plan, interp: int, sel=None) -> torch.Tensor:
+    """img [B,X,Y] float32 CUDA -> sino [B,A,W] float32 CUDA (ctr_radon_forward_dl).
+    sel: angle subset (indices into the plan's angles) -> sino [B,len(sel),W] (ctr_radon_forward_sel)."""
     img = _require_cuda_f32(img, "img")
     if img.dim() != 3 or img.shape[1] != plan.X or img.shape[2] != plan.Y:
         raise ValueError(f"img must be [B,{plan.X},{plan.Y}], got {tuple(img.shape)}")
     B = img.shape[0]
+    if sel is not None:
+        sel = _check_sel(sel, plan, img.device)
+        sino = torch.empty((B, sel.numel(), plan.W), dtype=torch.float32, device=img.device)
+        if B == 0:
+            return sino
+        ws = _workspace(plan.forward_workspace_bytes(B), img.device)
+        _lib.check(_lib.lib().ctr_radon_forward_sel(plan.handle, img.data_ptr(), sino.data_ptr(), B, interp, sel.data_ptr(), sel.numel(),
+                                                    ws.data_ptr(), ws.numel(), _stream_ptr(img.device)))
+        return sino
     sino = torch.empty((B, plan.A, plan.W), dtype=torch.float32, device=img.device)
     if B == 0:
         return sino
@@ -58,8 +78,11 @@ def radon_forward(img: torch.Tensor, plan: _lib.Plan, interp: int) -> torch.Tens
     return sino
 
 
-def radon_adjoint(dsino: torch.Tensor, plan: _lib.Plan, interp: int, mode: int) -> torch.Tensor:
-    """dsino [B,A,W] float32 CUDA -> dimg [B,X,Y] float32 CUDA (ctr_radon_adjoint_dl)."""
+def radon_adjoint(dsino: torch.Tensor, plan: _lib.Plan, interp: int, mode: int, sel=None) -> torch.Tensor:
+    """dsino [B,A,W] float32 CUDA -> dimg [B,X,Y] float32 CUDA (ctr_radon_adjoint_dl).
+    sel: dsino is [B,len(sel),W], the rows of an angle subset (ctr_radon_adjoint_sel)."""
+    if sel is not None:
+        return radon_adjoint_scaled(dsino, plan, interp, mode, 1.0, sel)
     dsino = _require_cuda_f32(dsino, "dsino")
     if dsino.dim() != 3 or dsino.shape[1] != plan.A or dsino.shape[2] != plan.W:
         raise ValueError(f"dsino must be [B,{plan.A},{plan.W}], got {tuple(dsino.shape)}")
@@ -92,46 +115,71 @@ class RadonFunction(torch.autograd.Function):
     Mirrors what tf.GradientTape does around project_tf_fast (main_ct_vae.py:471-481)."""
 
     @staticmethod
-    def forward(ctx, img, plan, interp, mode):
-        ctx.plan, ctx.interp, ctx.mode = plan, interp, mode
-        return radon_forward(img, plan, interp)
+    def forward(ctx, img, plan, interp, mode, sel=None):
+        ctx.plan, ctx.interp, ctx.mode, ctx.sel = plan, interp, mode, sel
+        return radon_forward(img, plan, interp, sel)
 
     @staticmethod
     def backward(ctx, dsino):
-        return radon_adjoint(dsino.contiguous(), ctx.plan, ctx.interp, ctx.mode), None, None, None
+        return radon_adjoint(dsino.contiguous(), ctx.plan, ctx.interp, ctx.mode, ctx.sel), None, None, None, None
 
 
-def project(img: torch.Tensor, plan: _lib.Plan, interp: int, mode: int) -> torch.Tensor:
+def project(img: torch.Tensor, plan: _lib.Plan, interp: int, mode: int, sel=None) -> torch.Tensor:
+    if sel is not None:
+        sel = _check_sel(sel, plan, img.device)
     if img.requires_grad and torch.is_grad_enabled():
-        return RadonFunction.apply(img, plan, interp, mode)
-    return radon_forward(img, plan, interp)
+        return RadonFunction.apply(img, plan, interp, mode, sel)
+    return radon_forward(img, plan, interp, sel)
 
 
-def radon_adjoint_scaled(dsino: torch.Tensor, plan: _lib.Plan, interp: int, mode: int, scale: float) -> torch.Tensor:
-    """``scale * A^T dsino`` in one launch (ctr_radon_adjoint_scaled)."""
+def radon_adjoint_scaled(dsino: torch.Tensor, plan: _lib.Plan, interp: int, mode: int, scale: float, sel=None) -> torch.Tensor:
+    """``scale * A^T dsino`` in one launch (ctr_radon_adjoint_scaled / ctr_radon_adjoint_sel)."""
     dsino = _require_cuda_f32(dsino, "dsino")
     B = dsino.shape[0]
     dimg = torch.empty((B, plan.X, plan.Y), dtype=torch.float32, device=dsino.device)
+    if sel is not None:
+        sel = _check_sel(sel, plan, dsino.device)
+        if dsino.dim() != 3 or dsino.shape[1] != sel.numel() or dsino.shape[2] != plan.W:
+            raise ValueError(f"dsino must be [B,{sel.numel()},{plan.W}], got {tuple(dsino.shape)}")
+    elif dsino.dim() != 3 or dsino.shape[1] != plan.A or dsino.shape[2] != plan.W:
+        raise ValueError(f"dsino must be [B,{plan.A},{plan.W}], got {tuple(dsino.shape)}")
     if B == 0:
         return dimg
     ws = _workspace(plan.adjoint_workspace_bytes(B), dsino.device)
+    if sel is not None:
+        _lib.check(_lib.lib().ctr_radon_adjoint_sel(plan.handle, dsino.data_ptr(), dimg.data_ptr(), B, interp, mode, float(scale),
+                                                    sel.data_ptr(), sel.numel(), ws.data_ptr(), ws.numel(), _stream_ptr(dsino.device)))
+        return dimg
     _lib.check(_lib.lib().ctr_radon_adjoint_scaled(plan.handle, dsino.data_ptr(), dimg.data_ptr(), B, interp, mode, float(scale),
                                                    ws.data_ptr(), ws.numel(), _stream_ptr(dsino.device)))
     return dimg
 
 
 def radon_loglik(img: torch.Tensor, plan: _lib.Plan, mask: torch.Tensor, meas: torch.Tensor, angle_map, pnm: float,
-                 sqrt_reg: float, interp: int):
+                 sqrt_reg: float, interp: int, sel=None):
     """Fused projector + measurement log-likelihood (ctr_radon_loglik).
 
     img [B,X,Y], mask [B,A_all], meas [B,A_all,W] float32 CUDA; angle_map int32 CUDA [A] or None.
-    Returns (loglik [B], dproj [B,A,W]) -- dproj is d loglik / d proj, the adjoint's cotangent."""
+    Returns (loglik [B], dproj [B,A,W]) -- dproj is d loglik / d proj, the adjoint's cotangent.
+    sel: the plan covers ALL A_all angles and the call projects the subset sel (ctr_radon_loglik_sel);
+    dproj is then [B,len(sel),W]."""
     img = _require_cuda_f32(img, "img")
     mask = _require_cuda_f32(mask, "mask")
     meas = _require_cuda_f32(meas, "proj_sample")
     B, A_all = img.shape[0], mask.shape[1]
     if mask.shape[0] != B or meas.shape[0] != B or meas.shape[1] != A_all or meas.shape[2] != plan.W:
         raise ValueError("mask must be [B,A_all] and proj_sample [B,A_all,num_proj_pix]")
+    if sel is not None:
+        if A_all != plan.A:
+            raise ValueError("with an angle subset the mask must cover exactly the plan's angles")
+        sel = _check_sel(sel, plan, img.device)
+        loglik = torch.empty((B,), dtype=torch.float32, device=img.device)
+        dproj = torch.empty((B, sel.numel(), plan.W), dtype=torch.float32, device=img.device)
+        ws = _workspace(plan.loglik_workspace_bytes(B), img.device)
+        _lib.check(_lib.lib().ctr_radon_loglik_sel(plan.handle, img.data_ptr(), mask.data_ptr(), meas.data_ptr(), sel.data_ptr(),
+                                                   sel.numel(), float(pnm), float(sqrt_reg), loglik.data_ptr(), dproj.data_ptr(), B,
+                                                   interp, ws.data_ptr(), ws.numel(), _stream_ptr(img.device)))
+        return loglik, dproj
     if angle_map is None:
         if A_all != plan.A:
             raise ValueError("without angles_i the mask must cover exactly the plan's angles")
@@ -155,9 +203,9 @@ class LoglikFunction(torch.autograd.Function):
     already produced the cotangent, so backward is a single (scaled) adjoint launch."""
 
     @staticmethod
-    def forward(ctx, img, plan, mask, meas, angle_map, pnm, sqrt_reg, interp, mode):
-        loglik, dproj = radon_loglik(img, plan, mask, meas, angle_map, pnm, sqrt_reg, interp)
-        ctx.plan, ctx.interp, ctx.mode = plan, interp, mode
+    def forward(ctx, img, plan, mask, meas, angle_map, pnm, sqrt_reg, interp, mode, sel=None):
+        loglik, dproj = radon_loglik(img, plan, mask, meas, angle_map, pnm, sqrt_reg, interp, sel)
+        ctx.plan, ctx.interp, ctx.mode, ctx.sel = plan, interp, mode, sel
         ctx.save_for_backward(dproj)
         return loglik
 
@@ -167,7 +215,7 @@ class LoglikFunction(torch.autograd.Function):
         g = grad_loglik.reshape(-1)
         if g.numel() > 1 and bool((g != g[0]).any()):
             cot = dproj * g.view(-1, 1, 1)          # per-image upstream weights (rare): one elementwise scale
-            dimg = radon_adjoint(cot, ctx.plan, ctx.interp, ctx.mode)
+            dimg = radon_adjoint(cot, ctx.plan, ctx.interp, ctx.mode, ctx.sel)
         else:
-            dimg = radon_adjoint_scaled(dproj, ctx.plan, ctx.interp, ctx.mode, float(g[0]))
-        return (dimg,) + (None,) * 8
+            dimg = radon_adjoint_scaled(dproj, ctx.plan, ctx.interp, ctx.mode, float(g[0]), ctx.sel)
+        return (dimg,) + (None,) * 9

@@ -123,6 +123,22 @@ int ctr_radon_adjoint(const ctr_plan* plan, const float* dsino, float* dimg, int
 int ctr_radon_adjoint_scaled(const ctr_plan* plan, const float* dsino, float* dimg, int B, int interp, int mode,
                              float scale, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- angle subsets (training's angle minibatch) ----------------------------------------------------
+ * The training loop projects a random subset of the angles every iteration (helper_functions.py:350-357:
+ * tf.gather(theta, angles_i) before the projector call).  Instead of a plan per subset, ONE plan over all the angles
+ * serves every subset: `sel` is a DEVICE array of n_sel int32 indices into the plan's angles; sinogram row k of the
+ * call is angle sel[k].  sino / dsino are [B, n_sel, W].  Nothing is allocated, uploaded or freed on this path.
+ * Workspaces: the plain ctr_*_workspace_bytes of the same B. */
+int ctr_radon_forward_sel(const ctr_plan* plan, const float* img, float* sino, int B, int interp, const int* sel, int n_sel,
+                          void* workspace, size_t workspace_bytes, void* stream);
+int ctr_radon_adjoint_sel(const ctr_plan* plan, const float* dsino, float* dimg, int B, int interp, int mode, float scale,
+                          const int* sel, int n_sel, void* workspace, size_t workspace_bytes, void* stream);
+/* ctr_radon_loglik (below) on a subset: mask [B,A] and meas [B,A,W] cover ALL the plan's angles and are read at
+ * column sel[k]; dproj is [B, n_sel, W] */
+int ctr_radon_loglik_sel(const ctr_plan* plan, const float* img, const float* mask, const float* meas, const int* sel,
+                         int n_sel, float pnm, float sqrt_reg, float* loglik, float* dproj, int B, int interp,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- fused measurement log-likelihood ------------------------------------------
  * calculate_log_prob_M_given_R (ctvae/helper_functions.py:336-368) reduced over angles and
  * bins as find_loss_vae_unsup does (:305-311), in ONE pass of the projector:
@@ -158,8 +174,11 @@ int ctr_fbp(const ctr_fbp_plan* plan, const float* sino, int A, float* recon, in
  * scripts/images_to_sinograms.py:61-68).  A pipe owns device staging for `chunk` images per
  * slot (6 slots), its workspace and three streams; a call cuts the host batch into chunks
  * and overlaps copy-in, kernels and copy-out.  Calls only ENQUEUE and return; results are
- * valid after ctr_hostpipe_wait.  Host buffers should be page-locked (pinned) -- pageable
- * memory works but serialises the copies.  Calls on one pipe are serialised by a mutex and
+ * valid after ctr_hostpipe_wait.  Page-locked (pinned) host buffers are copied directly.  Pageable
+ * memory -- a plain NumPy array, what the reference's callers pass -- is staged through pinned
+ * buffers owned by the slots (worker threads fill the next chunk's buffer while the previous one
+ * crosses PCIe); a pageable input may be released as soon as the call returns, a pageable result
+ * is complete after ctr_hostpipe_wait.  Calls on one pipe are serialised by a mutex and
  * their chunks share the ring, so back-to-back calls overlap each other's copies.
  * ctr_hostpipe_done: 1 if everything enqueued so far has completed, 0 if not, < 0 on error. */
 typedef struct ctr_hostpipe ctr_hostpipe;

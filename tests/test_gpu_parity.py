@@ -303,12 +303,18 @@ def test_pinned_host_batch_goes_through_the_chunked_pipeline(cp, orc):
     assert g.device.type == "cpu" and rel_l2(g.numpy(), orc.adjoint_exact(cot, th, X, X, True, 1)) <= TOL
 
 
-@pytest.mark.parametrize("chunk", [None, "32", "16"])
-def test_async_host_calls_overlap_and_match(cp, orc, chunk, monkeypatch):
+@pytest.fixture
+def host_chunks():
+    from ct_pvae_b200 import hostpipe
+    yield hostpipe.set_chunk
+    hostpipe.set_chunk(0, 0)
+
+
+@pytest.mark.parametrize("chunk", [0, 32, 16])
+def test_async_host_calls_overlap_and_match(cp, orc, chunk, host_chunks):
     """async_op=True: two host-buffer calls in flight at once (result + completion handle each); forced small
     chunks exercise the staging ring's slot reuse and the ragged last chunk."""
-    if chunk:
-        monkeypatch.setenv("CTR_HOST_CHUNK", chunk)
+    host_chunks(chunk, chunk)
     rng = np.random.default_rng(18)
     B, X, A = 120, 24, 9
     th = _theta(A)
@@ -326,6 +332,59 @@ def test_async_host_calls_overlap_and_match(cp, orc, chunk, monkeypatch):
         assert rel_l2(g.numpy(), orc.adjoint_exact(cot, th, X, X, True, 1)) <= TOL
     with pytest.raises(ValueError):
         cp.project_tf_fast(torch.from_numpy(img[:4]).unsqueeze(-1), th, pad=True, dim=2, integrate_vae=True, async_op=True)
+
+
+@pytest.mark.parametrize("chunk", [0, 16])
+def test_pageable_numpy_batches_are_staged_by_the_library(cp, orc, chunk, host_chunks):
+    """The drop-in case: plain (pageable) NumPy arrays, what the reference's callers pass.  The library stages them
+    through the pipe's pinned ring; blocking and async_op calls, several in flight, small chunks wrapping the ring,
+    and a caller-provided result buffer (out=)."""
+    host_chunks(chunk, chunk)
+    rng = np.random.default_rng(28)
+    B, X, A = 150, 24, 9
+    th = _theta(A)
+    img = rng.random((B, X, X, 1), dtype=np.float32)
+    want = orc.forward(img[..., 0], th, True, 1)
+    cot = rng.random(want.shape, dtype=np.float32)
+    gwant = orc.adjoint_exact(cot, th, X, X, True, 1)
+    s = cp.project_tf_fast(img, th, pad=True, dim=2, integrate_vae=True, interpolation="bilinear")
+    assert isinstance(s, np.ndarray) and s.dtype == np.float32 and rel_l2(s[..., 0], want) <= TOL
+    g = cp.backproject(cot, th, X, X, pad=True, interpolation="bilinear")
+    assert isinstance(g, np.ndarray) and rel_l2(g, gwant) <= TOL
+    out_s = torch.empty((B, A, want.shape[2]), dtype=torch.float32).pin_memory()
+    for _ in range(3):
+        s2, hs = cp.project_tf_fast(img, th, pad=True, dim=2, integrate_vae=True, interpolation="bilinear", async_op=True, out=out_s)
+        g2, hg = cp.backproject(cot, th, X, X, pad=True, interpolation="bilinear", async_op=True)
+        img_copy = img.copy()
+        img_copy[:] = 0          # a pageable input may be released / overwritten as soon as the call has returned
+        hs.wait()
+        hg.wait()
+        assert hs.is_completed() and hg.is_completed()
+        assert s2.ctypes.data == out_s.data_ptr() and rel_l2(out_s.numpy(), want) <= TOL
+        assert rel_l2(g2, gwant) <= TOL
+    # a pageable RESULT buffer: delivered by wait()
+    out_pg = torch.empty((B, X, X), dtype=torch.float32)
+    g3, hg = cp.backproject(cot, th, X, X, pad=True, interpolation="bilinear", async_op=True, out=out_pg)
+    hg.wait()
+    assert rel_l2(out_pg.numpy(), gwant) <= TOL
+    with pytest.raises(ValueError):
+        cp.backproject(cot, th, X, X, pad=True, interpolation="bilinear", out=torch.empty((B, X, X + 1)))
+
+
+def test_host_handles_survive_pipe_eviction(cp, orc):
+    """evicting / clearing a pipe that outstanding async handles still reference must not turn a completed
+    result into an error."""
+    from ct_pvae_b200 import hostpipe
+    rng = np.random.default_rng(38)
+    B, X, A = 40, 16, 5
+    th = _theta(A)
+    img = rng.random((B, X, X, 1), dtype=np.float32)
+    s, h = cp.project_tf_fast(torch.from_numpy(img).pin_memory(), th, pad=True, dim=2, integrate_vae=True,
+                              interpolation="bilinear", async_op=True)
+    hostpipe.clear_pipes()
+    assert h.is_completed()
+    h.wait()
+    assert rel_l2(s[..., 0].numpy(), orc.forward(img[..., 0], th, True, 1)) <= TOL
 
 
 @pytest.mark.parametrize("interp", INTERPS)
@@ -361,6 +420,57 @@ def test_fused_loglik_matches_oracle(cp, orc, interp, gather, X):
                                            theta=th, angles_i=ai, pad=True, interpolation=interp)
     assert full.shape == (B, logp.shape[1], P, 1)
     assert (np.abs(full[..., 0].double().sum(dim=(1, 2)).cpu().numpy() - want) <= budget).all()
+
+
+@pytest.mark.parametrize("B,X,A_all,n_sel", [(5, 128, 180, 20), (13, 33, 40, 7), (37, 64, 30, 30), (20, 300, 48, 9), (33, 260, 36, 5), (3, 200, 12, 1)])
+def test_angle_subsets_share_one_plan(cp, orc, B, X, A_all, n_sel):
+    """Training's angle minibatch (helper_functions.py:350-357): ONE plan over all the angles, the subset as a device
+    index list (ctr_radon_*_sel).  Every forward shape (4 / 16 / 32-image records, whole-row and windowed strips) and
+    both adjoints against the oracle run on the gathered angles; no plan is created after the first call."""
+    from ct_pvae_b200 import _lib, ops
+    rng = np.random.default_rng(200 + B)
+    th = _theta(A_all)
+    plan = _lib.get_plan(th, X, X, True, 0)
+    img = rng.random((B, X, X), dtype=np.float32)
+    x = torch.from_numpy(img).cuda()
+    made = _lib.PLANS_CREATED
+    for trial in range(2):
+        idx = rng.permutation(A_all)[:n_sel]
+        sel = torch.from_numpy(idx.astype(np.int32)).cuda()
+        y = rng.random((B, n_sel, plan.W), dtype=np.float32)
+        for interp in INTERPS:
+            got = ops.radon_forward(x, plan, IID[interp], sel).cpu().numpy()
+            assert got.shape == (B, n_sel, plan.W)
+            assert rel_l2(got, orc.forward(img, th[idx], True, IID[interp])) <= TOL
+            for mode, fn in ((0, orc.adjoint_exact), (1, orc.adjoint_tf)):
+                g = ops.radon_adjoint(torch.from_numpy(y).cuda(), plan, IID[interp], mode, sel).cpu().numpy()
+                assert rel_l2(g, fn(y, th[idx], X, X, True, IID[interp])) <= TOL
+    assert _lib.PLANS_CREATED == made
+
+
+def test_training_iterations_do_not_replan(cp):
+    """vae.train_step with a fresh random angle minibatch every iteration (main_ct_vae.py:388-389): after the first
+    iteration no ctr_plan is created (every iteration used to miss the plan cache)."""
+    from ct_pvae_b200 import _lib, vae
+    torch.manual_seed(0)
+    N, X, A, b, api = 8, 32, 30, 4, 6
+    theta = np.linspace(0, np.pi, A, endpoint=False)
+    imgs = torch.rand((N, X, X), device="cuda")
+    sino = vae.create_sinogram(imgs, theta, pad=True, interpolation="bilinear")
+    masks, meas = vae.create_all_masks(sino, A, 1e4, num_sparse_angles=10, random=True)
+    enc_in = vae.iradon_all(meas, masks, theta, X, X)
+    model = vae.CTVAE(X, X, num_filters=1).cuda()
+    g = torch.Generator().manual_seed(1)
+    losses = []
+    for it in range(6):
+        if it == 1:
+            made = _lib.PLANS_CREATED
+        idx = torch.randint(0, N, (b,), generator=g).cuda()
+        angles_i = torch.randperm(A, generator=g)[:api]
+        loss, _, _, _ = model.train_step(meas[idx], masks[idx], enc_in[idx], 1e4, theta, angles_i=angles_i, num_samples=2)
+        losses.append(float(loss))
+    assert _lib.PLANS_CREATED == made, "a training iteration created a plan"
+    assert all(np.isfinite(losses))
 
 
 def test_dataset_helpers_on_the_projector(cp, orc, tmp_path):

@@ -101,7 +101,9 @@ def test_host_pipeline_eligibility():
     from ct_pvae_b200 import hostpipe
 
     x = torch.zeros(40, 8, 8)
-    assert not hostpipe.eligible(x)                       # pageable memory: plain path
+    assert hostpipe.eligible(x)                           # pageable memory: staged through the pipe's pinned ring
+    assert hostpipe.eligible(torch.from_numpy(np.zeros((40, 8, 8), np.float32)))
+    assert not hostpipe.eligible(x.permute(0, 2, 1))      # the C call wants one contiguous block
     assert not hostpipe.eligible(torch.zeros(40, 8, 8, dtype=torch.float64))
     assert not hostpipe.eligible(torch.zeros(4, 8, 8))    # small batches are not worth chunking
     assert not hostpipe.eligible(torch.zeros(40, 8, 8, requires_grad=True))
@@ -112,13 +114,15 @@ def test_host_chunk_sizes(monkeypatch):
     import types
 
     from ct_pvae_b200 import hostpipe
-    monkeypatch.delenv("CTR_HOST_CHUNK", raising=False)
-    monkeypatch.delenv("CTR_HOST_CHUNK_FWD", raising=False)
+    hostpipe.set_chunk(0, 0)
     c2 = types.SimpleNamespace(A=180, X=128, Y=128)
     c4 = types.SimpleNamespace(A=720, X=512, Y=512)
     assert hostpipe.chunk_for(c2, 256, "fwd") == 64
     assert hostpipe.chunk_for(c2, 1024, "adj") == 256
     assert hostpipe.chunk_for(c4, 64, "fwd") == 16
     assert hostpipe.chunk_for(c2, 40, "fwd") == 48          # one chunk: the batch is too small to split
-    monkeypatch.setenv("CTR_HOST_CHUNK", "32")
-    assert hostpipe.chunk_for(c2, 256, "fwd") == 32
+    hostpipe.set_chunk(32, 0)
+    try:
+        assert hostpipe.chunk_for(c2, 256, "fwd") == 32 and hostpipe.chunk_for(c2, 256, "adj") == 64
+    finally:
+        hostpipe.set_chunk(0, 0)

@@ -24,5 +24,5 @@ def async_step():
     hs.wait(); hg.wait(); hold[0]=(s,g)
 for ch in os.environ.get("CHUNKS", "0:0,64:64,128:64,96:96").split(","):
     cf, ca = ch.split(":")
-    if int(cf): os.environ["CTR_HOST_CHUNK_FWD"] = cf; os.environ["CTR_HOST_CHUNK_ADJ"] = ca
+    hostpipe.set_chunk(int(cf), int(ca))
     print("chunk fwd:adj", ch, "blocking step %.3f ms   async step %.3f ms" % (wall(sync_step), wall(async_step)), flush=True)

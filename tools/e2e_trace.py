@@ -1,8 +1,10 @@
 import os, sys, time
-os.environ["CTR_HOSTPIPE_TRACE"]="1"
+
 import numpy as np, torch
 sys.path.insert(0, os.getcwd())
 import ct_pvae_b200 as cp
+from ct_pvae_b200 import hostpipe
+hostpipe.set_trace(True)
 B, X, A = 256,128,180
 th = np.linspace(0, np.pi, A, endpoint=False)
 img_h = torch.rand((B, X, X, 1)).pin_memory()

@@ -1,4 +1,4 @@
-"""Time the back-projection kernels alone (developer tool; honours CTR_BP_NB)."""
+"""Time the back-projection kernels alone (developer tool)."""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -21,5 +21,4 @@ for (B, X, A) in shapes:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); fn(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
         res[name] = min(ts)
-    print(f"B={B} X={X} A={A}: " + "  ".join(f"{k} {v:.3f}" for k, v in res.items()) + "  env=" +
-          " ".join(f"{k}={v}" for k, v in os.environ.items() if k.startswith("CTR_BP")), flush=True)
+    print(f"B={B} X={X} A={A}: " + "  ".join(f"{k} {v:.3f}" for k, v in res.items()), flush=True)

@@ -1,4 +1,4 @@
-"""Time the forward kernel alone (developer tool; honours CTR_FWD_* overrides)."""
+"""Time the forward kernel alone (developer tool)."""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -18,5 +18,4 @@ for (B, X, A) in shapes:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); ops.radon_forward(img, plan, iid); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
         out.append(min(ts))
-    print(f"B={B} X={X} A={A} P={plan.W}: bilinear {out[0]:.3f} ms  nearest {out[1]:.3f} ms   env=" +
-          " ".join(f"{k}={v}" for k, v in os.environ.items() if k.startswith("CTR_FWD")), flush=True)
+    print(f"B={B} X={X} A={A} P={plan.W}: bilinear {out[0]:.3f} ms  nearest {out[1]:.3f} ms   {plan.describe(B)}", flush=True)

@@ -477,12 +477,8 @@ static int forward_impl(const ctr_plan* p, const float* img, float* out, int B, 
     float* pk0 = p->n_cls[0] ? (float*)ws : nullptr;
     float* pk1 = p->n_cls[1] ? (float*)((char*)ws + pack_bytes(p, B)) : nullptr;
     {
-        const int up0 = p->geom[0].Up, up1 = p->geom[1].Up;   // tiles cover the padded row lengths of both packs
-        dim3 grid((up0 + 31) / 32, (up1 + 31) / 32, G * fc.depth), block(32, 8);
         ProfScope prof(CTR_K_PACK_IMAGE, st);
-        ctr::ctr_pack_image_kernel<ctr::kFwdNB><<<grid, block, 0, st>>>(img, B, p->X, p->Y, pk0, pk1, fc.depth, up0, up1);
-        ctr::launch_counter()++;
-        CTR_CUDA(cudaGetLastError());
+        CTR_CUDA(ctr::launch_pack_image(img, B, p->X, p->Y, pk0, pk1, rec, p->geom[0].Up, p->geom[1].Up, st));
     }
     ctr::FwdParams fp;
     fp.pk[0] = pk0; fp.pk[1] = pk1;

@@ -91,66 +91,76 @@ constexpr int kFwdMaxConsumers = kFwdMaxThreads - 32;  // 736 = 23 warps
 __host__ __device__ static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 // ------------------------------------------------------------------------------------------ K0 packs
-// grid (ceil(up0/32), ceil(up1/32), G*depth), block (32, 8).  Reads are coalesced along
-// image rows; both packs are written with 16-byte-per-lane coalesced stores, the
-// transposed one through a padded shared-memory tile.
-// `depth` image groups of NB share one pixel record of depth*NB floats (depth-first pack):
-// blockIdx.z = super-group * depth + sub; this block fills chunk `sub` of every record.
-template <int NB>
+// [B,X,Y] -> pixel records of REC images, halo-padded: pk0 [G][X+2][up0][REC] (row-major) and pk1 [G][Y+2][up1][REC]
+// (transposed).  One CTA = a 16 x 16 tile of the packed frame x all REC images of one record:
+//   load   thread (r, c) of the tile reads its pixel from each of the REC images -- every warp load is two 64-byte row
+//          segments, and all REC loads of a thread are in flight before the first is used (the kernel is pure data
+//          movement: r1's version, 4 images per CTA and 16-byte stores 128 bytes apart, ran at 23 % of the HBM rate);
+//   store  through a shared-memory tile [REC][17-pixel rows] (+ padding: conflict-free in both directions): the lanes of
+//          a warp write whole records, 512 contiguous bytes per store instruction, for both packs.
+// grid (ceil(max(up0, Y+2) / 16), ceil(max(X+2, up1) / 16), G), block 256.
+constexpr int kPackT = 16;                       // tile edge (pixels)
+constexpr int kPackStride = 16 * 17 + 17;        // floats between images in the tile: == 1 (mod 32)
+template <int REC>
 __global__ void __launch_bounds__(256) ctr_pack_image_kernel(const float* __restrict__ img, int B, int X, int Y,
-                                                             float* __restrict__ pk0, float* __restrict__ pk1, int depth,
+                                                             float* __restrict__ pk0, float* __restrict__ pk1,
                                                              int up0, int up1)   // packed row lengths (pixels) of the two packs
 {
-    __shared__ float tile[NB][32][33];
-    const int g = blockIdx.z;                       // image group of NB
-    const int sg = g / depth, sub = g - sg * depth; // super-group (one pixel record) and chunk inside it
-    const int rec = NB * depth;
-    const int pr0 = blockIdx.y * 32, pc0 = blockIdx.x * 32;
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    // all NB x 4 loads of a thread are issued before the first one is consumed (the kernel is latency-bound:
-    // r1 ncu, 18 long-scoreboard stalls per issue with the loads interleaved with the shared-memory stores)
-    float v[NB][4];
-    const int c = pc0 + tx - 1;
-    const bool cok = c >= 0 && c < Y;
+    extern __shared__ __align__(16) float tile[];                // [REC][kPackStride], pixel (r, c) at r * 17 + c
+    const int g = blockIdx.z;
+    const int pr0 = blockIdx.y * kPackT, pc0 = blockIdx.x * kPackT;
+    const int tid = threadIdx.x, tr = tid >> 4, tc = tid & 15;
+    {
+        const int r = pr0 + tr - 1, c = pc0 + tc - 1;            // image coordinates of packed (pr0 + tr, pc0 + tc)
+        const bool inside = r >= 0 && r < X && c >= 0 && c < Y;
+        const float* src = img + ((size_t)g * REC * X + (inside ? r : 0)) * Y + (inside ? c : 0);
+        float v[REC];
 #pragma unroll
-    for (int n = 0; n < NB; ++n) {
-        const int b = g * NB + n;
+        for (int n = 0; n < REC; ++n) v[n] = (inside && g * REC + n < B) ? __ldg(src + (size_t)n * X * Y) : 0.f;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int r = pr0 + ty + 8 * k - 1;
-            const bool ok = cok && b < B && r >= 0 && r < X;
-            v[n][k] = ok ? __ldg(img + ((size_t)(ok ? b : 0) * X + (ok ? r : 0)) * Y + (ok ? c : 0)) : 0.f;
-        }
+        for (int n = 0; n < REC; ++n) tile[n * kPackStride + tr * 17 + tc] = v[n];
     }
-#pragma unroll
-    for (int n = 0; n < NB; ++n)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) tile[n][ty + 8 * k][tx] = v[n][k];
     __syncthreads();
-    if (pk0) {
-        for (int rr = ty; rr < 32; rr += 8) {
-            const int pr = pr0 + rr, pc = pc0 + tx;
-            if (pr < X + 2 && pc < up0) {          // columns Y+2 .. up0-1 are zero padding
-                float* dst = pk0 + (((size_t)sg * (X + 2) + pr) * up0 + pc) * rec + sub * NB;
-#pragma unroll
-                for (int q = 0; q < NB / 4; ++q)
-                    reinterpret_cast<float4*>(dst)[q] = make_float4(tile[4 * q][rr][tx], tile[4 * q + 1][rr][tx],
-                                                                    tile[4 * q + 2][rr][tx], tile[4 * q + 3][rr][tx]);
+    constexpr int Q = REC / 4;                                   // 16-byte chunks per record
+    for (int idx = tid; idx < kPackT * kPackT * Q; idx += 256) {
+        const int q = idx % Q, pix = idx / Q;
+        if (pk0) {                                               // consecutive pixels of a tile row
+            const int r = pix >> 4, c = pix & 15;
+            const int pr = pr0 + r, pc = pc0 + c;
+            if (pr < X + 2 && pc < up0) {                        // columns Y+2 .. up0-1 are zero padding
+                const float* t = tile + (4 * q) * kPackStride + r * 17 + c;
+                *reinterpret_cast<float4*>(pk0 + (((size_t)g * (X + 2) + pr) * up0 + pc) * REC + 4 * q) =
+                    make_float4(t[0], t[kPackStride], t[2 * kPackStride], t[3 * kPackStride]);
             }
         }
-    }
-    if (pk1) {
-        for (int cc = ty; cc < 32; cc += 8) {
-            const int pc = pc0 + cc, pr = pr0 + tx;
+        if (pk1) {                                               // consecutive pixels of a tile column
+            const int c = pix >> 4, r = pix & 15;
+            const int pr = pr0 + r, pc = pc0 + c;
             if (pc < Y + 2 && pr < up1) {
-                float* dst = pk1 + (((size_t)sg * (Y + 2) + pc) * up1 + pr) * rec + sub * NB;
-#pragma unroll
-                for (int q = 0; q < NB / 4; ++q)
-                    reinterpret_cast<float4*>(dst)[q] = make_float4(tile[4 * q][tx][cc], tile[4 * q + 1][tx][cc],
-                                                                    tile[4 * q + 2][tx][cc], tile[4 * q + 3][tx][cc]);
+                const float* t = tile + (4 * q) * kPackStride + r * 17 + c;
+                *reinterpret_cast<float4*>(pk1 + (((size_t)g * (Y + 2) + pc) * up1 + pr) * REC + 4 * q) =
+                    make_float4(t[0], t[kPackStride], t[2 * kPackStride], t[3 * kPackStride]);
             }
         }
     }
+}
+
+inline cudaError_t launch_pack_image(const float* img, int B, int X, int Y, float* pk0, float* pk1, int rec, int up0, int up1,
+                                     cudaStream_t st)
+{
+    const int G = (B + rec - 1) / rec;
+    const int wpix = up0 > Y + 2 ? up0 : Y + 2, hpix = X + 2 > up1 ? X + 2 : up1;
+    dim3 grid((wpix + kPackT - 1) / kPackT, (hpix + kPackT - 1) / kPackT, G), block(256);
+    const size_t smem = (size_t)rec * kPackStride * sizeof(float);
+    switch (rec) {
+        case 4: ctr_pack_image_kernel<4><<<grid, block, smem, st>>>(img, B, X, Y, pk0, pk1, up0, up1); break;
+        case 8: ctr_pack_image_kernel<8><<<grid, block, smem, st>>>(img, B, X, Y, pk0, pk1, up0, up1); break;
+        case 16: ctr_pack_image_kernel<16><<<grid, block, smem, st>>>(img, B, X, Y, pk0, pk1, up0, up1); break;
+        case 32: ctr_pack_image_kernel<32><<<grid, block, smem, st>>>(img, B, X, Y, pk0, pk1, up0, up1); break;
+        default: return cudaErrorInvalidValue;
+    }
+    launch_counter()++;
+    return cudaGetLastError();
 }
 
 // [B,A,W] -> [G][A][NB/4 planes][W+2][4]: zero halo bins, 4 images interleaved per 16-byte bin.

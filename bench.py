@@ -538,15 +538,23 @@ def c5_record(ctx, steps=5):
     theta = np.linspace(0, np.pi, A, endpoint=False)
     fplan = _lib.get_fbp_plan(theta, P, X, X, cp.get_fourier_filter(P, "ramp"), ctx.local)
     sino = torch.rand((B, A, P), device=ctx.dev, generator=torch.Generator(device=ctx.dev).manual_seed(3))
-    _lib.profile_reset()
-    _lib.profile_enable(True)
-    ms = best_ms(ctx, lambda: ops.fbp(sino, fplan), iters=steps)
-    _lib.profile_enable(False)
-    prof = _lib.profile_read()
-    _lib.profile_reset()
+    def timed(fused):
+        ran_fused = fplan.set_fused(fused)
+        _lib.profile_reset()
+        _lib.profile_enable(True)
+        ms = best_ms(ctx, lambda: ops.fbp(sino, fplan), iters=steps)
+        _lib.profile_enable(False)
+        prof = _lib.profile_read()
+        _lib.profile_reset()
+        return ms, {k: {"ms_per_launch": v[0] / v[1], "launches": v[1]} for k, v in prof.items()}, ran_fused
+
+    ms2, k2, _ = timed(False)
+    ms, k1, ran_fused = timed(True)        # leave the plan on its default (fused) path
     rec = {"workload": wl["name"], "ms_per_pass": ms, "value": B * A * X * X / (ms * 1e-3) / 1e9,
-           "unit": "G pixel-angle updates/s", "dtype": "f32 values, f64 geometry and filter accumulation",
-           "kernels": {k: {"ms_per_launch": v[0] / v[1], "launches": v[1]} for k, v in prof.items()},
+           "unit": "G pixel-angle updates/s", "dtype": "f32 values, f64 geometry",
+           "path": "one cluster kernel: row filter in shared memory + back-projection (ctr_fbp_fused_kernel)" if ran_fused
+                   else "ctr_fbp_filter_kernel + ctr_bp_kernel<fbp>",
+           "kernels": k1, "two_kernel_path": {"ms_per_pass": ms2, "kernels": k2},
            "tomopy_gridrec": "unavailable (tomopy is not installable in this image)"}
     try:
         rec["cpu_baseline"] = cpu_baseline(wl, target_s=8.0, fbp=True)
@@ -658,7 +666,7 @@ def run_angle(args, ctx, wl):
     # the SAME full cotangent on every rank (seeded), of which the rank uses its angle block
     gen = torch.Generator(device=ctx.dev).manual_seed(1)
     cot_full = torch.rand((B, A, P), device=ctx.dev, generator=gen)
-    cot = cot_full[:, op.a_lo:op.a_hi].contiguous()
+    cot = op.local_rows(cot_full)
 
     # ---- parity of the exchange step (runs on whatever hardware times it): the reduced back-projection of this
     # rank's images against a single-rank adjoint of the same cotangent over ALL angles
@@ -674,7 +682,7 @@ def run_angle(args, ctx, wl):
         raise SystemExit(f"angle-sharded adjoint differs from the single-rank adjoint: rel-L2 {worst:.3e} > 1e-5")
     # forward blocks are disjoint rows of the single-rank sinogram: check this rank's block on a few images
     s_blk = op.forward(img[:32])
-    s_ref = ops.radon_forward(img[:32], full_plan, op.iid)[:, op.a_lo:op.a_hi]
+    s_ref = op.local_rows(ops.radon_forward(img[:32], full_plan, op.iid))
     fwd_par = ctx.max_over_ranks(float((s_blk.double() - s_ref.double()).norm() / s_ref.double().norm()))
     if fwd_par > 1e-6:
         raise SystemExit(f"angle-sharded forward block differs from the single-rank rows: rel-L2 {fwd_par:.3e}")
@@ -689,8 +697,11 @@ def run_angle(args, ctx, wl):
     units = B * A * P                                                     # total work is fixed: strong scaling
     rec = {"ms_per_step": ms, "kernels": kernel_table(prof, total_ms), "P": P, "steps": args.steps}
 
-    # ---- e2e: host buffers in, host buffers out, through the sharded operator
-    img_h = img.cpu().pin_memory()
+    # ---- e2e: host buffers in, host buffers out, through the sharded operator.  The host side of the job holds the
+    # batch once: every rank uploads its B/N images and the full batch is assembled over NVLink (op.gather_images), so
+    # each image crosses PCIe once; the cotangent rows and both results are per-rank anyway.
+    own_lo = int(op.owned_images()[0])
+    img_h = img[own_lo:own_lo + B // ctx.world].cpu().pin_memory()
     cot_h = cot.cpu().pin_memory()
     sino_h = torch.empty((B, A_loc, P), dtype=torch.float32).pin_memory()
     g_h = torch.empty((B // ctx.world, X, X), dtype=torch.float32).pin_memory()
@@ -701,7 +712,7 @@ def run_angle(args, ctx, wl):
         side_stream.wait_stream(cur)
         with torch.cuda.stream(side_stream):          # cotangent upload under the forward
             cot_d = cot_h.to(ctx.dev, non_blocking=True)
-        img_d = img_h.to(ctx.dev, non_blocking=True)
+        img_d = op.gather_images(img_h.to(ctx.dev, non_blocking=True))
         s = op.forward(img_d)
         sino_h.copy_(s, non_blocking=True)
         cur.wait_stream(side_stream)
@@ -721,7 +732,8 @@ def run_angle(args, ctx, wl):
     h2d = (img_h.numel() + cot_h.numel()) * 4 * ctx.world
     d2h = (sino_h.numel() + g_h.numel()) * 4 * ctx.world
     e2e = {"value": units * args.steps / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-           "ms_per_step": dt / args.steps * 1e3, "note": "bytes are summed over the ranks (every rank uploads all images)"}
+           "ms_per_step": dt / args.steps * 1e3,
+           "note": "bytes are summed over the ranks; every rank uploads B/N images (assembled over NVLink) and its cotangent rows"}
 
     others = {}
     if not args.no_side_legs:
@@ -763,7 +775,8 @@ def run_angle(args, ctx, wl):
             "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic foam (unit disk, random circular pores), random cotangents",
             "config": {"workload": wl["name"], "interpolation": INTERP, "adjoint": "exact", "B": B, "X": X, "Y": X, "A": A, "P": P,
-                       "angles_per_gpu": A_loc, "sharding": f"angle ({op.algo} reduce-scatter of the partial back-projections inside the step)",
+                       "angles_per_gpu": A_loc, "angle_assignment": op.assignment,
+                       "sharding": f"angle ({op.algo} reduce-scatter of the partial back-projections inside the step)",
                        "l2": "flushed (256 MiB memset) between timed steps"},
             "clocks": clocks,
             "e2e": {k: e2e[k] for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")},

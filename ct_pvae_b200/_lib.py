@@ -61,6 +61,7 @@ SYMBOLS = {
                                   _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_size_t, _c_void_p]),
     "ctr_fbp_plan_create": (_c_int, [_f64p, _c_int, _c_int, _c_int, _c_int, _f64p, _f64p, _c_int, ctypes.POINTER(_c_void_p)]),
     "ctr_fbp_plan_destroy": (_c_int, [_c_void_p]),
+    "ctr_fbp_plan_set_fused": (_c_int, [_c_void_p, _c_int]),
     "ctr_fbp_workspace_bytes": (_c_size_t, [_c_void_p, _c_int]),
     "ctr_fbp": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_size_t, _c_void_p]),
     "ctr_hostpipe_create": (_c_int, [_c_void_p, _c_int, ctypes.POINTER(_c_void_p)]),
@@ -132,7 +133,7 @@ def launch_count() -> int:
     return int(lib().ctr_launch_count())
 
 
-N_KERNELS = 8
+N_KERNELS = 9
 
 
 def profile_enable(on: bool) -> None:
@@ -242,6 +243,13 @@ class FbpPlan:
 
     def workspace_bytes(self, B: int) -> int:
         return int(lib().ctr_fbp_workspace_bytes(self.handle, B))
+
+    def set_fused(self, on: bool) -> bool:
+        """Single-kernel (cluster, filter in shared memory) vs two-kernel path; -> whether the fused path will run."""
+        rc = lib().ctr_fbp_plan_set_fused(self.handle, int(bool(on)))
+        if rc < 0:
+            check(rc)
+        return bool(on) and rc == 0
 
     def close(self):
         if self.handle:

@@ -118,6 +118,8 @@ struct ctr_fbp_plan {
     int A = 0, P = 0, x_size = 0, y_size = 0;
     double* d_cs = nullptr;   // [A][2]
     float* d_h = nullptr;     // [P] spatial kernel
+    int fused_cl = 0, fused_ab = 0;   // cluster size / angle batch of the single-kernel path (0: image too large for it)
+    int use_fused = 1;                // ctr_fbp_plan_set_fused
 };
 
 extern "C" {
@@ -128,7 +130,7 @@ long long ctr_launch_count(void) { return ctr::launch_counter().load(); }
 
 static const char* kKernelNames[CTR_K_COUNT] = {"ctr_pack_image_kernel", "ctr_pack_sino_kernel", "ctr_fwd_kernel",
                                                 "ctr_bp_kernel<exact>", "ctr_bp_kernel<tf_compat>",
-                                                "ctr_fbp_filter_kernel", "ctr_bp_kernel<fbp>", "ctr_xchg_sum_kernel"};
+                                                "ctr_fbp_filter_kernel", "ctr_bp_kernel<fbp>", "ctr_xchg_sum_kernel", "ctr_fbp_fused_kernel"};
 const char* ctr_kernel_name(int id) { return (id >= 0 && id < CTR_K_COUNT) ? kKernelNames[id] : ""; }
 
 int ctr_profile_enable(int on)
@@ -647,6 +649,11 @@ int ctr_fbp_plan_create(const double* theta, int A, int P, int x_size, int y_siz
     for (int k = 0; k < P; ++k) hf[k] = (float)hd[k];
     DeviceGuard guard(device);
     if (!guard.ok) { int rc = fail_cuda(guard.err, "cudaSetDevice"); delete p; return rc; }
+    {
+        int smem_optin = 0;
+        if (cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) == cudaSuccess)
+            ctr::fbp_fused_shape(x_size, y_size, P, smem_optin - 1024, p->fused_cl, p->fused_ab);
+    }
     cudaError_t e;
     if ((e = cudaMalloc(&p->d_cs, cs.size() * sizeof(double))) != cudaSuccess ||
         (e = cudaMalloc(&p->d_h, hf.size() * sizeof(float))) != cudaSuccess ||
@@ -670,6 +677,13 @@ int ctr_fbp_plan_destroy(ctr_fbp_plan* p)
     return CTR_OK;
 }
 
+int ctr_fbp_plan_set_fused(ctr_fbp_plan* p, int on)
+{
+    if (!p) return fail(CTR_EINVAL, "ctr_fbp_plan_set_fused: plan is NULL");
+    p->use_fused = on ? 1 : 0;
+    return (on && p->fused_cl == 0) ? 1 : CTR_OK;   // 1: accepted, but this geometry only has the two-kernel path
+}
+
 size_t ctr_fbp_workspace_bytes(const ctr_fbp_plan* p, int B)
 {
     if (!p || B <= 0) return 0;
@@ -689,6 +703,18 @@ static int fbp_impl(const ctr_fbp_plan* p, const float* sino, int A, int A_total
     DeviceGuard guard(p->device);
     if (!guard.ok) return fail_cuda(guard.err, "cudaSetDevice");
     cudaStream_t st = (cudaStream_t)stream;
+    if (p->use_fused && p->fused_cl > 0) {
+        // single kernel: the filtered rows stay in (distributed) shared memory
+        ctr::FbpFusedParams fp{};
+        fp.sino = sino; fp.h = p->d_h; fp.cs = p->d_cs; fp.out = recon;
+        fp.B = B; fp.A = p->A; fp.P = p->P; fp.X = p->x_size; fp.Y = p->y_size; fp.AB = p->fused_ab;
+        fp.scale = (float)(M_PI / (2.0 * (double)A_total));
+        if (xg) fp.xg = *xg; else fp.xg.nranks = 1;
+        ProfScope prof(CTR_K_FBP_FUSED, st);
+        const cudaError_t e = ctr::launch_fbp_fused(fp, p->fused_cl, st);
+        if (e != cudaSuccess) return fail_cuda(e, "ctr_fbp_fused_kernel launch");
+        return CTR_OK;
+    }
     const int NBb = ctr::bp_nb_for_batch(B, CTR_ADJ_FBP, p->x_size, p->y_size);
     const int G = (B + NBb - 1) / NBb;
     float* spk = (float*)ws;

@@ -720,6 +720,186 @@ __global__ void __launch_bounds__(256) ctr_fbp_filter_kernel(const float* __rest
     }
 }
 
+// ------------------------------------------------------------------------------------------ K3 fused FBP
+// iradon in ONE kernel (fbp_tensorflow.py:49-74): the circular row filter runs in shared memory and its output never
+// leaves the chip.  A thread-block CLUSTER of CL CTAs serves one group of 16 sinograms:
+//   filter   the rows of an angle batch are dealt out to the CTAs as "row quads" (angle k, 4 images): each CTA loads its
+//            quads' raw rows, convolves them with the spatial kernel (no redundant work anywhere in the cluster) and
+//            stores every filtered bin into the batch buffer of ALL CTAs of the cluster through distributed shared
+//            memory (st.shared::cluster; 16 bytes per bin and quad: the plane layout the gather reads);
+//   gather   every CTA owns 1/CL of the image's pixels (4 per thread, 64 accumulators); it back-projects the batch from
+//            its own shared memory exactly like ctr_bp_kernel<FBP> (same ctr_adj_fbp, same angle order: bit-identical).
+// The batch buffers are double buffered: F(b+1) then BP(b), one cluster barrier per batch.
+// Fits images of up to 8 * 2048 pixels (128 x 128, the foam dataset: BASELINE configs[4]); larger ones take the
+// two-kernel path (ctr_fbp_filter_kernel + ctr_bp_kernel<FBP>).
+constexpr int kFusedNB = 16, kFusedPPT = 4, kFusedThreads = 512, kFusedPxPerCta = kFusedThreads * kFusedPPT;
+struct FbpFusedParams {
+    const float* sino;     // [B][A][P]
+    const float* h;        // [P] spatial kernel real(ifft(filter_1d))
+    const double* cs;      // [A][2] cos / sin(theta)
+    float* out;            // [B][X][Y]
+    int B, A, P, X, Y;
+    int AB;                // angles per batch (1, 2, 4 or 8; chosen so the buffers fit shared memory)
+    float scale;           // pi / (2 A_total)
+    CtrExchange xg;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// 16-byte store into the same shared-memory offset of CTA `rank` of this cluster
+__device__ __forceinline__ void st_cluster_f4(const void* local, uint32_t rank, float4 v)
+{
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local)), "r"(rank));
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(remote), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+__host__ __device__ inline size_t fbp_fused_smem(int P, int AB, int CL)
+{
+    const int quads = (AB * (kFusedNB / 4) + CL - 1) / CL;                  // row quads a CTA filters per batch
+    return 2ull * AB * (kFusedNB / 4) * P * 16 + (size_t)quads * P * 16 + 2ull * P * 4 + 16;
+}
+
+__global__ void __launch_bounds__(kFusedThreads, 1) ctr_fbp_fused_kernel(const FbpFusedParams p)
+{
+    constexpr int NB = kFusedNB, NBP = NB / 4, PPT = kFusedPPT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int P = p.P, AB = p.AB;
+    const int CL = (int)cluster_nctarank(), q = (int)cluster_ctarank();
+    const int g = blockIdx.x / CL, tid = threadIdx.x;
+    const int quads = (AB * NBP + CL - 1) / CL;
+    float* filt = reinterpret_cast<float*>(smem_raw);                        // [2][AB][NBP][P][4]
+    const int stage_floats = AB * NBP * P * 4;
+    float* raw = filt + 2 * stage_floats;                                    // [quads][P][4]
+    float* h2 = raw + quads * P * 4;                                         // [2P]
+    for (int m = tid; m < 2 * P; m += kFusedThreads) h2[m] = __ldg(p.h + (m >= P ? m - P : m));
+
+    // this thread's pixels (consecutive lanes = consecutive pixels of a row: neighbouring bins in the gather)
+    const int npix = p.X * p.Y, per = (npix + CL - 1) / CL;
+    const int px_lo = q * per, px_hi = min(npix, px_lo + per);
+    double xpr[PPT], ypr[PPT];
+    float acc[PPT][NB];
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {
+        const int pi = min(px_lo + tid + i * kFusedThreads, npix - 1);
+        const int r = pi / p.Y, c = pi - r * p.Y;
+        xpr[i] = (double)r - 0.5 * (double)p.X;                              // fbp_tensorflow.py:52-53
+        ypr[i] = (double)c - 0.5 * (double)p.Y;
+#pragma unroll
+        for (int n = 0; n < NB; ++n) acc[i][n] = 0.f;
+    }
+    const int nbatch = (p.A + AB - 1) / AB;
+    const int nb2 = (P + 1) / 2;                                             // filter tasks per quad: 2 bins each
+
+    auto filter_batch = [&](int b) {
+        float* dst = filt + (b & 1) * stage_floats;
+        // raw rows of this CTA's quads: quad t = (angle k = t / NBP, plane h = t % NBP), t = q + CL * ql
+        for (int idx = tid; idx < quads * 4 * P; idx += kFusedThreads) {
+            const int kk = idx % P, n4 = (idx / P) & 3, ql = idx / (4 * P);
+            const int t = q + CL * ql, k = t / NBP, hpl = t - k * NBP;
+            const int a = b * AB + k, bimg = g * NB + 4 * hpl + n4;
+            raw[(ql * P + kk) * 4 + n4] = (t < AB * NBP && a < p.A && bimg < p.B) ? __ldg(p.sino + ((size_t)bimg * p.A + a) * P + kk) : 0.f;
+        }
+        __syncthreads();
+        for (int task = tid; task < quads * nb2; task += kFusedThreads) {
+            const int ql = task / nb2, n0 = (task - ql * nb2) * 2;
+            const int t = q + CL * ql, k = t / NBP, hpl = t - k * NBP;
+            if (t >= AB * NBP || b * AB + k >= p.A) continue;
+            // rf[n] = sum_k s[k] * h[(n - k) mod P], k ascending like ctr_fbp_filter_kernel (bit-identical sums)
+            const float* sq = raw + (size_t)ql * P * 4;
+            const float* hp = h2 + n0 + P;
+            float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
+            float h_hi = hp[1];                                              // h2[n0 + 1 + P - k] at k = 0
+            for (int kk = 0; kk < P; ++kk) {
+                const float h_lo = hp[-kk];
+                const float4 sv = *reinterpret_cast<const float4*>(sq + kk * 4);
+                a0[0] = fmaf(h_lo, sv.x, a0[0]); a0[1] = fmaf(h_lo, sv.y, a0[1]); a0[2] = fmaf(h_lo, sv.z, a0[2]); a0[3] = fmaf(h_lo, sv.w, a0[3]);
+                a1[0] = fmaf(h_hi, sv.x, a1[0]); a1[1] = fmaf(h_hi, sv.y, a1[1]); a1[2] = fmaf(h_hi, sv.z, a1[2]); a1[3] = fmaf(h_hi, sv.w, a1[3]);
+                h_hi = h_lo;
+            }
+            float* d0 = dst + ((size_t)(k * NBP + hpl) * P + n0) * 4;
+            for (int r = 0; r < CL; ++r) {
+                st_cluster_f4(d0, (uint32_t)r, make_float4(a0[0], a0[1], a0[2], a0[3]));
+                if (n0 + 1 < P) st_cluster_f4(d0 + 4, (uint32_t)r, make_float4(a1[0], a1[1], a1[2], a1[3]));
+            }
+        }
+    };
+
+    __syncthreads();
+    filter_batch(0);
+    cluster_sync_all();
+    for (int b = 0; b < nbatch; ++b) {
+        if (b + 1 < nbatch) filter_batch(b + 1);      // into the other stage, while nobody reads it
+        const float* src = filt + (b & 1) * stage_floats;
+        const int na = min(AB, p.A - b * AB);
+        for (int k = 0; k < na; ++k) {
+            double cs[2];
+            cs[0] = __ldg(p.cs + 2 * (b * AB + k));
+            cs[1] = __ldg(p.cs + 2 * (b * AB + k) + 1);
+            const float* ywin = src + (size_t)k * NBP * P * 4;
+#pragma unroll
+            for (int i = 0; i < PPT; ++i) ctr_adj_fbp<NB>(cs, P, xpr[i], ypr[i], ywin, P * 4, 1, acc[i]);
+        }
+        cluster_sync_all();                            // F(b+1) has landed everywhere; BP(b) has finished everywhere
+    }
+
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {
+        const int pi = px_lo + tid + i * kFusedThreads;
+        if (pi >= px_hi) continue;
+        const int r = pi / p.Y, c = pi - r * p.Y;
+#pragma unroll
+        for (int n = 0; n < NB; ++n) {
+            const int bimg = g * NB + n;
+            if (bimg >= p.B) continue;
+            const float v = acc[i][n] * p.scale;
+            if (p.xg.nranks <= 1) {
+                p.out[((size_t)bimg * p.X + r) * p.Y + c] = v;
+            } else {
+                const int owner = ctr_xg_owner(bimg, p.xg.Bs);
+                p.xg.peer[owner][ctr_xg_index(p.xg.rank, bimg - owner * p.xg.Bs, p.xg.Bs, r, c, p.X, p.Y)] = v;
+            }
+        }
+    }
+}
+
+// cluster size and angle batch for an image of X x Y and a detector of P bins; CL = 0: does not fit the fused kernel
+inline void fbp_fused_shape(int X, int Y, int P, int smem_optin, int& CL, int& AB)
+{
+    CL = 0; AB = 0;
+    const long long npix = (long long)X * Y;
+    for (int c : {1, 2, 4, 8})
+        if (npix <= (long long)c * kFusedPxPerCta) { CL = c; break; }
+    if (!CL) return;
+    for (int ab : {8, 4, 2, 1})
+        if (fbp_fused_smem(P, ab, CL) <= (size_t)smem_optin) { AB = ab; break; }
+    if (!AB) CL = 0;
+}
+
+inline cudaError_t launch_fbp_fused(const FbpFusedParams& p, int CL, cudaStream_t st)
+{
+    const size_t smem = fbp_fused_smem(p.P, p.AB, CL);
+    cudaError_t e = cudaFuncSetAttribute(ctr_fbp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int G = (p.B + kFusedNB - 1) / kFusedNB;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(G * CL));
+    cfg.blockDim = dim3(kFusedThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, ctr_fbp_fused_kernel, p);
+    launch_counter()++;
+    return e != cudaSuccess ? e : cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------ launchers
 struct FwdConfig {
     int JW, NS, KA, R, jchunks, depth, stages;

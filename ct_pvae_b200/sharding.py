@@ -40,6 +40,32 @@ def _check_angles_cover_ranks(num_angles: int, world: int) -> None:
         raise ValueError(f"angle sharding needs at least one angle per rank: {num_angles} angles over {world} ranks")
 
 
+def balanced_angle_blocks(theta, rank: int, world: int) -> np.ndarray:
+    """Indices of the angles rank ``rank`` owns when the angle axis is dealt out for EQUAL COST rather than as one
+    contiguous block per rank.  The forward projector's cost per angle grows with the distance of the ray direction
+    from the image axes (wider strip windows near 45 degrees), so contiguous blocks of pi/world leave some ranks with
+    only cheap and others with only expensive directions (8 GPUs: 11 % between fastest and slowest rank, all of it
+    spent waiting in the exchange).  Here the angles are cut into 2*world contiguous blocks, the blocks are ranked by
+    how oblique their mid direction is, and every rank gets one block from each end of that ranking.  Blocks stay
+    contiguous (the CTAs of the windowed forward want neighbouring angles), every rank gets shard sizes that differ
+    by at most one angle, and the assignment is a pure function of (theta, world) -- identical on all ranks."""
+    theta = np.asarray(theta, np.float64).reshape(-1)
+    A = theta.shape[0]
+    if world == 1:
+        return np.arange(A)
+    nblk = 2 * world
+    if A < nblk:                         # too few angles to split twice: contiguous blocks
+        lo, hi = shard_range(A, rank, world)
+        return np.arange(lo, hi)
+    bounds = [shard_range(A, b, nblk) for b in range(nblk)]
+    mid = np.array([theta[(lo + hi - 1) // 2] for lo, hi in bounds])
+    oblique = np.abs(np.mod(mid + np.pi / 4, np.pi / 2) - np.pi / 4)       # 0 on the axes .. pi/4 on the diagonals
+    order = sorted(range(nblk), key=lambda b: (round(float(oblique[b]), 9), b))
+    # sizes differ by at most one angle between blocks; pair long with short as well as cheap with expensive
+    mine = sorted((order[rank], order[nblk - 1 - rank]))
+    return np.concatenate([np.arange(*bounds[b]) for b in mine])
+
+
 def _world(group=None) -> Tuple[int, int]:
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(group), dist.get_world_size(group)
@@ -137,9 +163,12 @@ def radon_adjoint_angle_sharded(sinogram_local, theta, x_size, y_size, pad=True,
 class AngleShardedRadon:
     """The angle-sharded operator pair of SURVEY 8e on this rank's GPU (BASELINE configs[3]).
 
-    Every rank holds all ``B`` images and the contiguous angle block ``shard_range(A, rank, world)``:
+    Every rank holds all ``B`` images and the angles ``angle_indices`` (``assignment="contiguous"``: the block
+    ``shard_range(A, rank, world)``; ``"balanced"``, the default: two contiguous blocks per rank picked for equal
+    cost, see ``balanced_angle_blocks``):
 
-    * ``forward(img [B,X,Y])`` -> this rank's sinogram rows ``[B, A_local, W]`` (disjoint blocks, no exchange);
+    * ``forward(img [B,X,Y])`` -> this rank's sinogram rows ``[B, A_local, W]``, row ``k`` = angle ``angle_indices[k]``
+      (disjoint row sets, no exchange);
     * ``adjoint(dsino_local [B, A_local, W])`` -> the back-projection summed over ALL ranks' angle blocks, left
       batch-sharded: rank ``r`` returns images ``shard_range(B, r, world)`` as ``[B/world, X, Y]``
       (``replicate=True``: the full ``[B,X,Y]`` on every rank).  This sum is the path's only exchange step.
@@ -154,11 +183,13 @@ class AngleShardedRadon:
     """
 
     def __init__(self, theta, X: int, Y: int, pad: bool, B: int, device: torch.device, interpolation: str = "bilinear",
-                 adjoint: str = "exact", group=None, algo: str = "auto"):
+                 adjoint: str = "exact", group=None, algo: str = "auto", assignment: str = "balanced"):
         from . import _lib, ops
 
         if algo not in ("auto", "p2p", "nccl", "torch"):
             raise ValueError("algo must be 'auto', 'p2p', 'nccl' or 'torch'")
+        if assignment not in ("balanced", "contiguous"):
+            raise ValueError("assignment must be 'balanced' or 'contiguous'")
         self.rank, self.world = _world(group)
         self.group, self.B, self.X, self.Y = group, int(B), int(X), int(Y)
         theta = np.ascontiguousarray(np.asarray(theta, np.float64).reshape(-1))
@@ -166,8 +197,15 @@ class AngleShardedRadon:
         if self.B % self.world != 0:
             raise ValueError("the batch must divide evenly over the ranks (the result is left batch-sharded)")
         self.A = int(theta.shape[0])
-        self.a_lo, self.a_hi = shard_range(self.A, self.rank, self.world)
-        self.theta_local = theta[self.a_lo:self.a_hi]
+        # the angles this rank owns, in the order of its sinogram rows: one contiguous block, or (default) two blocks
+        # chosen so that every rank gets the same mix of cheap and expensive directions (balanced_angle_blocks)
+        if assignment == "contiguous":
+            lo, hi = shard_range(self.A, self.rank, self.world)
+            self.angle_indices = np.arange(lo, hi)
+        else:
+            self.angle_indices = balanced_angle_blocks(theta, self.rank, self.world)
+        self.assignment = assignment
+        self.theta_local = np.ascontiguousarray(theta[self.angle_indices])
         self.device = device
         self.plan = _lib.get_plan(self.theta_local, self.X, self.Y, bool(pad), device.index or 0)
         self.iid, self.mid = ops.INTERP[interpolation], ops.ADJOINT[adjoint]
@@ -183,7 +221,21 @@ class AngleShardedRadon:
 
     @property
     def A_local(self) -> int:
-        return self.a_hi - self.a_lo
+        return int(self.angle_indices.shape[0])
+
+    def local_rows(self, full: torch.Tensor) -> torch.Tensor:
+        """This rank's rows of a full ``[B, A, W]`` sinogram-shaped tensor, as a contiguous ``[B, A_local, W]``."""
+        idx = torch.as_tensor(self.angle_indices, device=full.device)
+        return full.index_select(1, idx).contiguous()
+
+    def gather_images(self, img_shard: torch.Tensor) -> torch.Tensor:
+        """``[B/world, X, Y]`` (this rank's share of a host-side batch, already on the device) -> all ``B`` images on
+        every rank, over NVLink (one all-gather): each image crosses PCIe once instead of ``world`` times."""
+        if self.world == 1:
+            return img_shard
+        full = torch.empty((self.B, self.X, self.Y), dtype=img_shard.dtype, device=img_shard.device)
+        dist.all_gather_into_tensor(full, img_shard.contiguous(), group=self.group)
+        return full
 
     def forward(self, img: torch.Tensor) -> torch.Tensor:
         from . import ops

@@ -66,7 +66,7 @@ long long ctr_launch_count(void);
  * device time and launch count of one kernel since the last reset. */
 enum {
     CTR_K_PACK_IMAGE = 0, CTR_K_PACK_SINO = 1, CTR_K_FORWARD = 2, CTR_K_ADJ_EXACT = 3,
-    CTR_K_ADJ_TF = 4, CTR_K_FBP_FILTER = 5, CTR_K_FBP_BP = 6, CTR_K_XCHG_SUM = 7, CTR_K_COUNT = 8
+    CTR_K_ADJ_TF = 4, CTR_K_FBP_FILTER = 5, CTR_K_FBP_BP = 6, CTR_K_XCHG_SUM = 7, CTR_K_FBP_FUSED = 8, CTR_K_COUNT = 9
 };
 int ctr_profile_enable(int on);
 int ctr_profile_reset(void);
@@ -163,6 +163,11 @@ int ctr_radon_loglik(const ctr_plan* plan, const float* img, const float* mask, 
 int ctr_fbp_plan_create(const double* theta, int A, int P, int x_size, int y_size, const double* filt_re,
                         const double* filt_im, int device, ctr_fbp_plan** out);
 int ctr_fbp_plan_destroy(ctr_fbp_plan* plan);
+/* Images of up to 128 x 128 pixels (8 x 2048) run as ONE kernel: a thread-block cluster filters the sinogram rows in
+ * shared memory and back-projects them from there (ctr_fbp_fused_kernel).  Larger images, or on = 0, take the
+ * two-kernel path (row filter to a packed sinogram, then the gather); both give bit-identical results.
+ * Returns 1 if on != 0 but the plan's geometry has no single-kernel path. */
+int ctr_fbp_plan_set_fused(ctr_fbp_plan* plan, int on);
 size_t ctr_fbp_workspace_bytes(const ctr_fbp_plan* plan, int B);
 /* sino [B,A,P] -> recon [B,x_size,y_size] (float32 on device; the Python shim widens
  * to float64 to keep the reference's return dtype) */

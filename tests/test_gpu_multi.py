@@ -54,7 +54,8 @@ def _worker(rank, world, port, out_dir):
         op = sharding.AngleShardedRadon(theta, X, X, True, B, dev, interpolation=interp, algo="auto")
         assert op.algo == "p2p" and op.comm is not None and op.comm.has_nccl, op.algo
         res[f"fwd_block_{interp}"] = op.forward(img[..., 0].contiguous()).cpu().numpy()
-        cl = cot[:, op.a_lo:op.a_hi].contiguous()
+        cl = op.local_rows(cot)
+        res[f"angles_{interp}"] = op.angle_indices
         for algo in ("p2p", "nccl", "torch"):
             outs = [op.adjoint(cl * (k + 1), algo=algo) for k in range(3)]       # enqueued without host syncs in between
             for k, o in enumerate(outs):
@@ -65,10 +66,10 @@ def _worker(rank, world, port, out_dir):
     filt = cp.get_fourier_filter(W, "ramp")
     fplan = _lib.get_fbp_plan(op.theta_local, W, X, X, filt, rank)
     for algo in ("p2p", "nccl"):
-        res[f"fbp_{algo}"] = op.comm.fbp_sharded(fplan, cot[:, op.a_lo:op.a_hi].contiguous(), A, algo=algo).cpu().numpy()
+        res[f"fbp_{algo}"] = op.comm.fbp_sharded(fplan, op.local_rows(cot), A, algo=algo).cpu().numpy()
     # argument errors come back as exceptions on every rank alike (nothing was enqueued)
     with pytest.raises(ValueError):
-        op.comm.adjoint_sharded(op.plan, cot[:B - 1, op.a_lo:op.a_hi].contiguous(), op.iid, op.mid)
+        op.comm.adjoint_sharded(op.plan, op.local_rows(cot)[:B - 1].contiguous(), op.iid, op.mid)
     with pytest.raises(ValueError):
         sharding.AngleShardedRadon(theta[:1], X, X, True, B, dev)       # fewer angles than ranks: all ranks raise together
     np.savez(os.path.join(out_dir, f"r{rank}.npz"), **res)
@@ -94,16 +95,16 @@ def test_nccl_sharding_matches_oracle(tmp_path, orc):
     fwd = {"bilinear": full, "nearest": orc.forward(img, theta, True, 0)}
     rec = orc.iradon(cot.astype(np.float64), theta, X, X, orc.get_fourier_filter(W, "ramp"))
     per = B // world
-    from ct_pvae_b200.sharding import shard_range
+    owned = []
     for r in range(world):
         z = np.load(tmp_path / f"r{r}.npz")
         assert rel_l2(z["batch"][..., 0], full) <= 1e-5
         assert rel_l2(z["angle"][..., 0], full) <= 1e-5
         assert rel_l2(z["adj"], grad["bilinear"]) <= 1e-5
         assert rel_l2(z["adj_scatter"], grad["bilinear"][r * per:(r + 1) * per]) <= 1e-5
-        lo, hi = shard_range(A, r, world)
         for interp in ("bilinear", "nearest"):
-            assert rel_l2(z[f"fwd_block_{interp}"], fwd[interp][:, lo:hi]) <= 1e-5
+            mine = z[f"angles_{interp}"]
+            assert rel_l2(z[f"fwd_block_{interp}"], fwd[interp][:, mine]) <= 1e-5
             want = grad[interp][r * per:(r + 1) * per]
             for algo in ("p2p", "nccl", "torch"):
                 for k in range(3):
@@ -113,6 +114,8 @@ def test_nccl_sharding_matches_oracle(tmp_path, orc):
             assert rel_l2(z[f"op_replicate_{interp}"], grad[interp]) <= 1e-5
         for algo in ("p2p", "nccl"):
             assert rel_l2(z[f"fbp_{algo}"], rec[r * per:(r + 1) * per]) <= 1e-5, algo
+        owned.append(z["angles_bilinear"])
+    assert sorted(np.concatenate(owned).tolist()) == list(range(A))      # the ranks' angle sets partition the angle axis
 
 
 @pytest.mark.timeout(600)

@@ -273,6 +273,52 @@ def test_fbp_matches_oracle(cp, orc):
         cp.iradon(torch.zeros((1, 5, 16), device="cuda"), _theta(4), 8, 8, np.ones(16))
 
 
+@pytest.mark.parametrize("B,A,X,Y", [(3, 20, 30, 30), (9, 45, 128, 128), (2, 12, 33, 21), (20, 13, 64, 64), (17, 9, 90, 90),
+                                     (5, 7, 128, 100), (33, 24, 47, 45)])
+def test_fused_fbp_is_one_kernel_and_matches_the_two_kernel_path(cp, orc, B, A, X, Y):
+    """iradon of images up to 128 x 128: ONE cluster kernel (row filter in shared memory, back-projection from
+    distributed shared memory).  Cluster sizes 1 / 2 / 4 / 8, ragged 16-image groups, angle counts that do not fill
+    the last batch.  Bit-identical to the filter + gather kernel pair, and within 1e-5 of the float64 oracle."""
+    from ct_pvae_b200 import _lib, ops
+    rng = np.random.default_rng(50 + B)
+    P = cp.num_proj_pix(X, Y)
+    th = _theta(A)
+    sino = rng.random((B, A, P), dtype=np.float32)
+    filt = orc.get_fourier_filter(P, "ramp")
+    plan = _lib.get_fbp_plan(th, P, X, Y, filt, 0)
+    x = torch.from_numpy(sino).cuda()
+    try:
+        assert plan.set_fused(True)
+        _lib.profile_reset()
+        _lib.profile_enable(True)
+        fused = ops.fbp(x, plan)
+        torch.cuda.synchronize()
+        prof = _lib.profile_read()
+        _lib.profile_enable(False)
+        assert list(prof) == ["ctr_fbp_fused_kernel"] and prof["ctr_fbp_fused_kernel"][1] == 1, prof
+        plan.set_fused(False)
+        two = ops.fbp(x, plan)
+    finally:
+        _lib.profile_enable(False)
+        _lib.profile_reset()
+        plan.set_fused(True)
+    assert torch.equal(fused, two)
+    assert rel_l2(fused.cpu().numpy(), orc.iradon(sino.astype(np.float64), th, X, Y, filt)) <= TOL
+
+
+def test_large_images_take_the_two_kernel_fbp(cp, orc):
+    from ct_pvae_b200 import _lib
+    rng = np.random.default_rng(51)
+    B, A, X = 2, 10, 200
+    P = cp.num_proj_pix(X, X)
+    th = _theta(A)
+    sino = rng.random((B, A, P))
+    filt = orc.get_fourier_filter(P, "hann")
+    assert not _lib.get_fbp_plan(th, P, X, X, filt, 0).set_fused(True)      # 40000 pixels > 8 x 2048
+    got = cp.iradon(torch.from_numpy(sino).cuda(), th, X, X, filt)
+    assert rel_l2(got.cpu().numpy(), orc.iradon(sino, th, X, X, filt)) <= TOL
+
+
 def test_fbp_reconstructs_disk(cp):
     """forward (bilinear) -> iradon(ramp) recovers a 0.8-valued disk."""
     X = 128

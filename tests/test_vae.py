@@ -82,3 +82,86 @@ def test_training_step_runs_through_the_fused_projector():
         losses.append(float(loss))
     assert all(math.isfinite(v) for v in losses)
     assert any(not torch.equal(a, b) for a, b in zip(before, model.parameters()))
+
+
+def _np_positive_range(x, eps):
+    xm = x - 1
+    return np.where(xm < 0, np.exp(np.clip(xm, -1e10, 10)) + eps, xm + 1)
+
+
+@pytest.mark.gpu
+def test_iradon_all_matches_oracle_restatement(orc):
+    """helper_functions.py:491-519 (dose-normalise the masked sinogram, reconstruct it; back-project the mask without
+    a filter), with the oracle's float64 iradon in tomopy's place: values, not just shapes."""
+    rng = np.random.default_rng(5)
+    N, X, A = 5, 32, 24
+    theta = np.linspace(0, np.pi, A, endpoint=False)
+    P = orc.frame_of(X, X, True)[1]
+    eps = float(np.finfo(np.float32).eps)
+    masks = np.zeros((N, A), np.float32)
+    for i in range(N):
+        masks[i, rng.permutation(A)[:6]] = 1.0 / 6.0
+    meas = (rng.random((N, A, P), dtype=np.float32) * masks[:, :, None]).astype(np.float32)
+    got = vae.iradon_all(torch.from_numpy(meas).cuda(), torch.from_numpy(masks).cuda(), theta, X, X).cpu().numpy()
+    m = np.repeat(masks[:, :, None], P, axis=2).astype(np.float64)
+    ps = np.where(m > eps, meas / np.maximum(m, eps), meas)
+    want0 = orc.iradon(ps, theta, X, X, orc.get_fourier_filter(P, "ramp"))
+    want1 = orc.iradon(m, theta, X, X, orc.get_fourier_filter(P, None))
+    assert got.shape == (N, 2, X, X)
+    rel = lambda a, b: float(np.linalg.norm(a - b) / np.linalg.norm(b))  # noqa: E731
+    assert rel(got[:, 0], want0) <= 1e-5 and rel(got[:, 1], want1) <= 1e-5
+
+
+@pytest.mark.gpu
+def test_elbo_matches_independent_restatement(orc):
+    """find_loss_vae_unsup (helper_functions.py:204-332) against a float64 NumPy / SciPy restatement of its
+    arithmetic on the SAME draws: the posterior and truncated-normal samples are redrawn with the same seed and
+    call order, everything downstream -- positive_range, the truncated-normal and normal log-densities, the KL terms
+    and log p(M|R) through the ORACLE projector (nearest, the reference's mode) at the gathered angles -- is
+    recomputed independently."""
+    from scipy import stats
+
+    torch.manual_seed(0)
+    dev = torch.device("cuda")
+    N, X, A, api, ns = 3, 32, 24, 7, 2
+    theta = np.linspace(0, np.pi, A, endpoint=False)
+    eps = float(np.finfo(np.float32).eps)
+    pnm = 1e3
+    imgs = torch.rand((N, X, X), device=dev) * 0.5
+    sino = vae.create_sinogram(imgs, theta, pad=True, interpolation="nearest")
+    masks, meas = vae.create_all_masks(sino, A, pnm, num_sparse_angles=8, random=True)
+    enc_in = vae.iradon_all(meas, masks, theta, X, X)
+    model = vae.CTVAE(X, X, num_filters=1, num_blocks=2).to(dev).eval()
+    angles_i = torch.randperm(A)[:api]
+    with torch.no_grad():
+        torch.manual_seed(123)
+        loss, out_dists, kl, loglik = vae.find_loss_vae_unsup(meas, masks, enc_in, model.encode, model.decode, pnm, eps,
+                                                              kl_anneal=0.7, kl_multiplier=1.3, num_samples=ns, theta=theta,
+                                                              angles_i=angles_i, pad=True, interpolation="nearest")
+        # ---- the same draws, independent arithmetic
+        torch.manual_seed(123)
+        skips = model.encode(enc_in / 300)
+        locs = [sv.chunk(2, dim=1)[0].double().cpu().numpy() for sv in skips]
+        scales = [_np_positive_range(sv.chunk(2, dim=1)[1].double().cpu().numpy(), eps) + eps for sv in skips]
+        q = [torch.distributions.Normal(sv.chunk(2, dim=1)[0], vae.positive_range(sv.chunk(2, dim=1)[1]) + eps) for sv in skips]
+        lp = []
+        idx = angles_i.numpy()
+        th_sub = theta[idx].astype(np.float32).astype(np.float64)
+        m_np, y_np = masks.cpu().numpy(), meas.cpu().numpy()
+        for _ in range(ns):
+            z = [d.rsample() for d in q]
+            alpha, beta = model.decode(z)
+            a_np = _np_positive_range(alpha.double().cpu().numpy(), eps)
+            b_np = _np_positive_range(beta.double().cpu().numpy(), eps)
+            x = vae.TruncatedNormal(vae.positive_range(alpha), vae.positive_range(beta), 0.0, 1e10).sample()
+            x_np = x.double().cpu().numpy()
+            lp_R = stats.truncnorm.logpdf(x_np, (0.0 - a_np) / b_np, (1e10 - a_np) / b_np, loc=a_np, scale=b_np)
+            logp, _ = orc.log_prob_M_given_R(x_np[:, 0].astype(np.float32), m_np, y_np, pnm, eps, theta, idx, True, 0)
+            lp.append(logp.sum(axis=(1, 2)) + lp_R.reshape(N, -1).sum(axis=1))
+        kl_np = sum((np.log(1.0 / s) + (s ** 2 + l ** 2) / 2.0 - 0.5).reshape(N, -1).sum(axis=1) for l, s in zip(locs[1:], scales[1:]))
+        want_ll = np.mean(lp, axis=0)
+        want_loss = 0.7 * 1.3 * kl_np - want_ll
+    assert np.allclose(kl.cpu().numpy(), kl_np, rtol=2e-4)
+    assert np.allclose(loglik.cpu().numpy(), want_ll, rtol=2e-4), (loglik.cpu().numpy(), want_ll)
+    assert np.allclose(loss.cpu().numpy(), want_loss, rtol=2e-4)
+    assert th_sub.shape == (api,)

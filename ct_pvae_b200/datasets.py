@@ -64,7 +64,9 @@ def crop(img_2d, final_x, final_y, ignore_dim_0=False):
 
 
 def _ssim(im0, im1, data_range, win_size=None):
-    """skimage.metrics.structural_similarity defaults (uniform window 7, K1=.01, K2=.03, sample covariance)."""
+    """skimage.metrics.structural_similarity defaults (uniform window 7, K1=.01, K2=.03, sample covariance).
+    Restates the published algorithm of scikit-image's ``structural_similarity`` (Copyright (C) the scikit-image
+    team, BSD-3-Clause; see THIRD_PARTY_NOTICES.md), which the reference calls at helper_functions.py:394-418."""
     from scipy.ndimage import uniform_filter
 
     win = 7 if win_size is None else win_size

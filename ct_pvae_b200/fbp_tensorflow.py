@@ -23,7 +23,11 @@ __all__ = ["iradon", "get_fourier_filter"]
 
 def get_fourier_filter(size: int, filter_name="ramp") -> np.ndarray:
     """The ``filter_1d`` the reference intended to pass (skimage's
-    ``_get_fourier_filter``, named at main_ct_vae.py:22,183): length ``size``, FFT order."""
+    ``_get_fourier_filter``, named at main_ct_vae.py:22,183): length ``size``, FFT order.
+
+    Restates ``skimage.transform.radon_transform._get_fourier_filter`` of scikit-image (Copyright (C) the
+    scikit-image team, BSD-3-Clause; see THIRD_PARTY_NOTICES.md) so that the values are the ones the reference's
+    callers would have computed; scikit-image itself is not a dependency."""
     n = np.concatenate((np.arange(1, size / 2 + 1, 2, dtype=int), np.arange(size / 2 - 1, 0, -2, dtype=int)))
     f = np.zeros(size)
     f[0] = 0.25
@@ -47,8 +51,12 @@ def get_fourier_filter(size: int, filter_name="ramp") -> np.ndarray:
     return fourier_filter
 
 
-def iradon(sinogram, theta, x_size, y_size, filter_1d):
-    """Filtered back-projection (reference :14-75)."""
+def iradon(sinogram, theta, x_size, y_size, filter_1d, *, fused=None):
+    """Filtered back-projection (reference :14-75).
+
+    ``fused`` (keyword-only extra): ``None`` / ``False`` -- the library default, two kernels (row filter, then the
+    gather); ``True`` -- ONE thread-block-cluster kernel that filters the rows in shared memory and back-projects them
+    from there (images up to 128 x 128; same values)."""
     t, was_numpy = _as_tensor(sinogram)
     if t.dim() != 3:
         raise ValueError("sinogram must be [batch, num_angles, num_proj_pix]")
@@ -61,6 +69,12 @@ def iradon(sinogram, theta, x_size, y_size, filter_1d):
         filter_1d = filter_1d.detach().cpu().numpy()
     plan = _lib.get_fbp_plan(ops.theta_to_host(theta), int(t.shape[2]), int(x_size), int(y_size),
                              np.asarray(filter_1d), dev.index or 0)
-    rec = ops.fbp(t.to(device=dev, dtype=torch.float32), plan)
+    if fused is not None:
+        plan.set_fused(bool(fused))
+    try:
+        rec = ops.fbp(t.to(device=dev, dtype=torch.float32), plan)
+    finally:
+        if fused is not None:
+            plan.set_fused(False)
     out = rec.to(device=t.device, dtype=torch.float64)
     return out.numpy() if was_numpy else out

@@ -40,30 +40,32 @@ def _check_angles_cover_ranks(num_angles: int, world: int) -> None:
         raise ValueError(f"angle sharding needs at least one angle per rank: {num_angles} angles over {world} ranks")
 
 
-def balanced_angle_blocks(theta, rank: int, world: int) -> np.ndarray:
-    """Indices of the angles rank ``rank`` owns when the angle axis is dealt out for EQUAL COST rather than as one
-    contiguous block per rank.  The forward projector's cost per angle grows with the distance of the ray direction
-    from the image axes (wider strip windows near 45 degrees), so contiguous blocks of pi/world leave some ranks with
-    only cheap and others with only expensive directions (8 GPUs: 11 % between fastest and slowest rank, all of it
-    spent waiting in the exchange).  Here the angles are cut into 2*world contiguous blocks, the blocks are ranked by
-    how oblique their mid direction is, and every rank gets one block from each end of that ranking.  Blocks stay
-    contiguous (the CTAs of the windowed forward want neighbouring angles), every rank gets shard sizes that differ
-    by at most one angle, and the assignment is a pure function of (theta, world) -- identical on all ranks."""
+def cost_balanced_range(theta, rank: int, world: int, kappa: float = 0.2) -> Tuple[int, int]:
+    """Contiguous angle block ``[lo, hi)`` of ``rank`` with the block boundaries placed for EQUAL COST instead of equal
+    angle counts.  On wide detectors (column-windowed strips) the forward projector's cost per angle grows with the
+    distance of the ray direction from the image axes: measured per 45-angle block of the 64 x 512^2 x 720 sweep,
+    forward + exact adjoint cost 0.78 ms on the axes and 0.96 ms next to the diagonals
+    (tools/angle_block_cost.py, profiles/r2_angle_block_cost.txt), i.e. about ``1 + kappa * o`` with ``o`` in [0, 1] the
+    obliqueness and kappa = 0.2.  Equal-count blocks of pi/8 then leave an 11 % spread between the fastest and slowest
+    of 8 ranks, all of it spent waiting in the exchange.  (Dealing out two blocks per rank -- one cheap, one expensive
+    -- was measured too: a rank's launch then mixes two direction families and runs 8 % slower on average.)
+    Pure function of (theta, world, kappa): identical on all ranks.  kappa = 0 gives ``shard_range``."""
     theta = np.asarray(theta, np.float64).reshape(-1)
     A = theta.shape[0]
     if world == 1:
-        return np.arange(A)
-    nblk = 2 * world
-    if A < nblk:                         # too few angles to split twice: contiguous blocks
-        lo, hi = shard_range(A, rank, world)
-        return np.arange(lo, hi)
-    bounds = [shard_range(A, b, nblk) for b in range(nblk)]
-    mid = np.array([theta[(lo + hi - 1) // 2] for lo, hi in bounds])
-    oblique = np.abs(np.mod(mid + np.pi / 4, np.pi / 2) - np.pi / 4)       # 0 on the axes .. pi/4 on the diagonals
-    order = sorted(range(nblk), key=lambda b: (round(float(oblique[b]), 9), b))
-    # sizes differ by at most one angle between blocks; pair long with short as well as cheap with expensive
-    mine = sorted((order[rank], order[nblk - 1 - rank]))
-    return np.concatenate([np.arange(*bounds[b]) for b in mine])
+        return 0, A
+    if kappa <= 0 or A < 2 * world:
+        return shard_range(A, rank, world)
+    oblique = np.abs(np.mod(theta + np.pi / 4, np.pi / 2) - np.pi / 4) / (np.pi / 4)      # 0 on the axes .. 1 on the diagonals
+    w = 1.0 + kappa * oblique
+    cum = np.concatenate([[0.0], np.cumsum(w)])
+    cuts = [int(np.searchsorted(cum, cum[-1] * r / world, side="left")) for r in range(world + 1)]
+    cuts[0], cuts[-1] = 0, A
+    for r in range(1, world + 1):                      # every rank keeps at least one angle
+        cuts[r] = max(cuts[r], cuts[r - 1] + 1)
+    for r in range(world - 1, 0, -1):
+        cuts[r] = min(cuts[r], cuts[r + 1] - 1)
+    return cuts[rank], cuts[rank + 1]
 
 
 def _world(group=None) -> Tuple[int, int]:
@@ -163,9 +165,9 @@ def radon_adjoint_angle_sharded(sinogram_local, theta, x_size, y_size, pad=True,
 class AngleShardedRadon:
     """The angle-sharded operator pair of SURVEY 8e on this rank's GPU (BASELINE configs[3]).
 
-    Every rank holds all ``B`` images and the angles ``angle_indices`` (``assignment="contiguous"``: the block
-    ``shard_range(A, rank, world)``; ``"balanced"``, the default: two contiguous blocks per rank picked for equal
-    cost, see ``balanced_angle_blocks``):
+    Every rank holds all ``B`` images and the contiguous angle block ``angle_indices`` (``assignment="equal"``:
+    ``shard_range(A, rank, world)``; ``"cost"``, the default: boundaries placed for equal cost, see
+    ``cost_balanced_range``):
 
     * ``forward(img [B,X,Y])`` -> this rank's sinogram rows ``[B, A_local, W]``, row ``k`` = angle ``angle_indices[k]``
       (disjoint row sets, no exchange);
@@ -183,13 +185,13 @@ class AngleShardedRadon:
     """
 
     def __init__(self, theta, X: int, Y: int, pad: bool, B: int, device: torch.device, interpolation: str = "bilinear",
-                 adjoint: str = "exact", group=None, algo: str = "auto", assignment: str = "balanced"):
+                 adjoint: str = "exact", group=None, algo: str = "auto", assignment: str = "cost"):
         from . import _lib, ops
 
         if algo not in ("auto", "p2p", "nccl", "torch"):
             raise ValueError("algo must be 'auto', 'p2p', 'nccl' or 'torch'")
-        if assignment not in ("balanced", "contiguous"):
-            raise ValueError("assignment must be 'balanced' or 'contiguous'")
+        if assignment not in ("cost", "equal"):
+            raise ValueError("assignment must be 'cost' or 'equal'")
         self.rank, self.world = _world(group)
         self.group, self.B, self.X, self.Y = group, int(B), int(X), int(Y)
         theta = np.ascontiguousarray(np.asarray(theta, np.float64).reshape(-1))
@@ -197,14 +199,16 @@ class AngleShardedRadon:
         if self.B % self.world != 0:
             raise ValueError("the batch must divide evenly over the ranks (the result is left batch-sharded)")
         self.A = int(theta.shape[0])
-        # the angles this rank owns, in the order of its sinogram rows: one contiguous block, or (default) two blocks
-        # chosen so that every rank gets the same mix of cheap and expensive directions (balanced_angle_blocks)
-        if assignment == "contiguous":
-            lo, hi = shard_range(self.A, self.rank, self.world)
-            self.angle_indices = np.arange(lo, hi)
-        else:
-            self.angle_indices = balanced_angle_blocks(theta, self.rank, self.world)
-        self.assignment = assignment
+        # the angles this rank owns (one contiguous block), in the order of its sinogram rows.  "equal": the same number
+        # of angles per rank (shard_range); "cost" (default): block boundaries placed for equal cost where the
+        # forward's cost depends on the direction, i.e. on detectors wide enough for column-windowed strips
+        kappa = 0.0
+        if assignment == "cost" and self.world > 1:
+            full = _lib.get_plan(theta, self.X, self.Y, bool(pad), device.index or 0)
+            kappa = 0.2 if "windowed=1" in full.describe(self.B) else 0.0
+        lo, hi = cost_balanced_range(theta, self.rank, self.world, kappa)
+        self.angle_indices = np.arange(lo, hi)
+        self.assignment = assignment if kappa > 0 else "equal"
         self.theta_local = np.ascontiguousarray(theta[self.angle_indices])
         self.device = device
         self.plan = _lib.get_plan(self.theta_local, self.X, self.Y, bool(pad), device.index or 0)

@@ -73,6 +73,10 @@ int ctr_profile_reset(void);
 int ctr_profile_read(int kernel_id, double* total_ms, long long* launches);
 const char* ctr_kernel_name(int kernel_id);
 
+/* Blocks until every stream of `device` has drained.  For host frameworks whose compute stream cannot be passed in
+ * (the TensorFlow binding): synchronise, call with stream = NULL, synchronise. */
+int ctr_device_synchronize(int device);
+
 /* ---- host-side geometry (no GPU needed) ------------------------------------------------ */
 
 /* forward_functions.py:29-30: ceil((sqrt(X^2+Y^2)+2)/2)*2 */
@@ -163,11 +167,19 @@ int ctr_radon_loglik(const ctr_plan* plan, const float* img, const float* mask, 
 int ctr_fbp_plan_create(const double* theta, int A, int P, int x_size, int y_size, const double* filt_re,
                         const double* filt_im, int device, ctr_fbp_plan** out);
 int ctr_fbp_plan_destroy(ctr_fbp_plan* plan);
-/* Images of up to 128 x 128 pixels (8 x 2048) run as ONE kernel: a thread-block cluster filters the sinogram rows in
- * shared memory and back-projects them from there (ctr_fbp_fused_kernel).  Larger images, or on = 0, take the
- * two-kernel path (row filter to a packed sinogram, then the gather); both give bit-identical results.
+/* Two execution paths, same arithmetic:
+ *  - two kernels (default): row filter into a packed sinogram (L2-resident), then the interpolating gather;
+ *  - ONE kernel (on != 0; images of up to 128 x 128 = 8 x 2048 pixels): a thread-block cluster filters the sinogram
+ *    rows in shared memory and back-projects them from distributed shared memory (ctr_fbp_fused_kernel), so the
+ *    filtered rows never leave the chip.  With the dense row filter both paths are bit-identical.  The single kernel
+ *    holds 64 accumulators per thread and runs one 512-thread CTA per SM; measured on B200 it is the slower of the two
+ *    (DESIGN.md section 4), which is why it is opt-in.
  * Returns 1 if on != 0 but the plan's geometry has no single-kernel path. */
 int ctr_fbp_plan_set_fused(ctr_fbp_plan* plan, int on);
+/* The two-kernel path's row filter skips the taps of real(ifft(filter_1d)) that are zero (default on): every other tap
+ * of the ramp filter, all but one for filter_1d == 1.  on = 0 forces the dense loop.  Returns 1 if on != 0 but the
+ * filter has fewer than 25 % zero taps (the dense loop runs). */
+int ctr_fbp_plan_set_sparse_filter(ctr_fbp_plan* plan, int on);
 size_t ctr_fbp_workspace_bytes(const ctr_fbp_plan* plan, int B);
 /* sino [B,A,P] -> recon [B,x_size,y_size] (float32 on device; the Python shim widens
  * to float64 to keep the reference's return dtype) */

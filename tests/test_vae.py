@@ -159,7 +159,9 @@ def test_elbo_matches_independent_restatement(orc):
             logp, _ = orc.log_prob_M_given_R(x_np[:, 0].astype(np.float32), m_np, y_np, pnm, eps, theta, idx, True, 0)
             lp.append(logp.sum(axis=(1, 2)) + lp_R.reshape(N, -1).sum(axis=1))
         kl_np = sum((np.log(1.0 / s) + (s ** 2 + l ** 2) / 2.0 - 0.5).reshape(N, -1).sum(axis=1) for l, s in zip(locs[1:], scales[1:]))
-        want_ll = np.mean(lp, axis=0)
+        # helper_functions.py:305-306 sums the log-likelihood over the batch axis too (axis=[0,1,2]): one scalar per
+        # posterior sample, averaged over the samples (:329); the KL stays per image (:325) and the loss broadcasts
+        want_ll = np.mean([v.sum() for v in lp])
         want_loss = 0.7 * 1.3 * kl_np - want_ll
     assert np.allclose(kl.cpu().numpy(), kl_np, rtol=2e-4)
     assert np.allclose(loglik.cpu().numpy(), want_ll, rtol=2e-4), (loglik.cpu().numpy(), want_ll)

@@ -63,7 +63,6 @@ SYMBOLS = {
     "ctr_fbp_plan_create": (_c_int, [_f64p, _c_int, _c_int, _c_int, _c_int, _f64p, _f64p, _c_int, ctypes.POINTER(_c_void_p)]),
     "ctr_fbp_plan_destroy": (_c_int, [_c_void_p]),
     "ctr_fbp_plan_set_fused": (_c_int, [_c_void_p, _c_int]),
-    "ctr_fbp_plan_set_sparse_filter": (_c_int, [_c_void_p, _c_int]),
     "ctr_fbp_workspace_bytes": (_c_size_t, [_c_void_p, _c_int]),
     "ctr_fbp": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_size_t, _c_void_p]),
     "ctr_hostpipe_create": (_c_int, [_c_void_p, _c_int, ctypes.POINTER(_c_void_p)]),
@@ -245,13 +244,6 @@ class FbpPlan:
 
     def workspace_bytes(self, B: int) -> int:
         return int(lib().ctr_fbp_workspace_bytes(self.handle, B))
-
-    def set_sparse_filter(self, on: bool) -> bool:
-        """Row filter that skips the zero taps of the spatial kernel (default on); -> whether it will run."""
-        rc = lib().ctr_fbp_plan_set_sparse_filter(self.handle, int(bool(on)))
-        if rc < 0:
-            check(rc)
-        return bool(on) and rc == 0
 
     def set_fused(self, on: bool) -> bool:
         """Single-kernel (cluster, filter in shared memory) vs two-kernel path; -> whether the fused path will run."""

@@ -120,9 +120,6 @@ struct ctr_fbp_plan {
     float* d_h = nullptr;     // [P] spatial kernel
     int fused_cl = 0, fused_ab = 0;   // cluster size / angle batch of the single-kernel path (0: image too large for it)
     int use_fused = 0;                // ctr_fbp_plan_set_fused
-    ctr::FbpTap* d_taps = nullptr;    // non-zero taps of the spatial kernel (sparse row filter), or null
-    int nnz = 0;
-    int use_sparse = 1;               // ctr_fbp_plan_set_sparse_filter
 };
 
 extern "C" {
@@ -658,15 +655,6 @@ int ctr_fbp_plan_create(const double* theta, int A, int P, int x_size, int y_siz
     ctr_filter_to_spatial(fr, fi, P, hd.data());
     std::vector<float> hf(P);
     for (int k = 0; k < P; ++k) hf[k] = (float)hd[k];
-    // taps that are zero up to the rounding of the inverse DFT (1e-12 of the largest) are dropped by the sparse filter:
-    // the ramp filter has every other tap zero, "no filter" is a single tap
-    std::vector<ctr::FbpTap> taps;
-    {
-        double hmax = 0.0;
-        for (int k = 0; k < P; ++k) hmax = std::max(hmax, std::fabs(hd[k]));
-        for (int k = 0; k < P; ++k)
-            if (std::fabs(hd[k]) > 1e-12 * hmax) taps.push_back({hf[k], k});
-    }
     DeviceGuard guard(device);
     if (!guard.ok) { int rc = fail_cuda(guard.err, "cudaSetDevice"); delete p; return rc; }
     {
@@ -675,22 +663,12 @@ int ctr_fbp_plan_create(const double* theta, int A, int P, int x_size, int y_siz
             ctr::fbp_fused_shape(x_size, y_size, P, smem_optin - 1024, p->fused_cl, p->fused_ab);
     }
     cudaError_t e;
-    if (!taps.empty() && taps.size() * 4 <= (size_t)P * 3) {      // worth it from 25 % zeros up
-        p->nnz = (int)taps.size();
-        if ((e = cudaMalloc((void**)&p->d_taps, taps.size() * sizeof(ctr::FbpTap))) != cudaSuccess ||
-            (e = cudaMemcpy(p->d_taps, taps.data(), taps.size() * sizeof(ctr::FbpTap), cudaMemcpyHostToDevice)) != cudaSuccess) {
-            int rc = fail_cuda(e, "ctr_fbp_plan_create: tap upload");
-            cudaFree(p->d_taps);
-            delete p;
-            return rc;
-        }
-    }
     if ((e = cudaMalloc(&p->d_cs, cs.size() * sizeof(double))) != cudaSuccess ||
         (e = cudaMalloc(&p->d_h, hf.size() * sizeof(float))) != cudaSuccess ||
         (e = cudaMemcpy(p->d_cs, cs.data(), cs.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess ||
         (e = cudaMemcpy(p->d_h, hf.data(), hf.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess) {
         int rc = fail_cuda(e, "ctr_fbp_plan_create: table upload");
-        cudaFree(p->d_cs); cudaFree(p->d_h); cudaFree(p->d_taps);
+        cudaFree(p->d_cs); cudaFree(p->d_h);
         delete p;
         return rc;
     }
@@ -702,16 +680,9 @@ int ctr_fbp_plan_destroy(ctr_fbp_plan* p)
 {
     if (!p) return CTR_OK;
     DeviceGuard guard(p->device);
-    cudaFree(p->d_cs); cudaFree(p->d_h); cudaFree(p->d_taps);
+    cudaFree(p->d_cs); cudaFree(p->d_h);
     delete p;
     return CTR_OK;
-}
-
-int ctr_fbp_plan_set_sparse_filter(ctr_fbp_plan* p, int on)
-{
-    if (!p) return fail(CTR_EINVAL, "ctr_fbp_plan_set_sparse_filter: plan is NULL");
-    p->use_sparse = on ? 1 : 0;
-    return (on && !p->d_taps) ? 1 : CTR_OK;         // 1: accepted, but this filter has no zero taps to skip
 }
 
 int ctr_fbp_plan_set_fused(ctr_fbp_plan* p, int on)
@@ -755,23 +726,7 @@ static int fbp_impl(const ctr_fbp_plan* p, const float* sino, int A, int A_total
     const int NBb = ctr::bp_nb_for_batch(B, CTR_ADJ_FBP, p->x_size, p->y_size);
     const int G = (B + NBb - 1) / NBb;
     float* spk = (float*)ws;
-    const size_t smem_sparse = (size_t)NBb * 2 * p->P * sizeof(float) + (size_t)p->nnz * sizeof(ctr::FbpTap);
-    if (p->use_sparse && p->d_taps && smem_sparse <= 200 * 1024) {
-        dim3 grid(p->A, G), block(256);
-        ProfScope prof(CTR_K_FBP_FILTER, st);
-        if (NBb == 32) {
-            CTR_CUDA(cudaFuncSetAttribute(ctr::ctr_fbp_filter_sparse_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sparse));
-            ctr::ctr_fbp_filter_sparse_kernel<32><<<grid, block, smem_sparse, st>>>(sino, p->d_taps, p->nnz, B, p->A, p->P, spk);
-        } else if (NBb == 16) {
-            CTR_CUDA(cudaFuncSetAttribute(ctr::ctr_fbp_filter_sparse_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sparse));
-            ctr::ctr_fbp_filter_sparse_kernel<16><<<grid, block, smem_sparse, st>>>(sino, p->d_taps, p->nnz, B, p->A, p->P, spk);
-        } else {
-            CTR_CUDA(cudaFuncSetAttribute(ctr::ctr_fbp_filter_sparse_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sparse));
-            ctr::ctr_fbp_filter_sparse_kernel<8><<<grid, block, smem_sparse, st>>>(sino, p->d_taps, p->nnz, B, p->A, p->P, spk);
-        }
-        ctr::launch_counter()++;
-        CTR_CUDA(cudaGetLastError());
-    } else {
+    {
         const size_t smem = (size_t)p->P * (NBb + 2) * sizeof(float);
         dim3 grid(p->A, G), block(256);
         ProfScope prof(CTR_K_FBP_FILTER, st);

@@ -720,60 +720,6 @@ __global__ void __launch_bounds__(256) ctr_fbp_filter_kernel(const float* __rest
     }
 }
 
-// Sparse variant of the row filter: sums only the taps of the spatial kernel that are not zero.  The ramp filter --
-// iradon's default, and the filter of BASELINE configs[4] -- has h[m] == 0 for every even m != 0 (P even), i.e. half
-// the taps of the dense loop multiply by zero; "no filter" (the mask back-projection of iradon_all) is a single tap.
-//   rf[n] = sum_t val[t] * s[(n - idx[t]) mod P]
-// The rows are staged twice over (s2[k] = s[k mod P], k < 2P) as NB/4 planes of [k][4 images], so the tap loop has no
-// modulo and lanes (consecutive n) read consecutive 16-byte chunks.  grid (A, G), block 256.
-// smem: planes [NB/4][2P][4] floats + taps [nnz] (float value, int index).
-struct FbpTap { float val; int idx; };
-template <int NB>
-__global__ void __launch_bounds__(256) ctr_fbp_filter_sparse_kernel(const float* __restrict__ sino, const FbpTap* __restrict__ taps,
-                                                                    int nnz, int B, int A, int P, float* __restrict__ spk)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* s2 = reinterpret_cast<float*>(smem_raw);                              // [NB/4][2P][4]
-    FbpTap* tp = reinterpret_cast<FbpTap*>(s2 + (size_t)NB * 2 * P);
-    const int a = blockIdx.x, g = blockIdx.y;
-    for (int idx = threadIdx.x; idx < P * NB; idx += blockDim.x) {
-        const int n = idx / P, k = idx - n * P;       // coalesced along k per image
-        const int b = g * NB + n;
-        const float v = (b < B) ? __ldg(sino + ((size_t)b * A + a) * P + k) : 0.f;
-        float* d = s2 + ((size_t)(n >> 2) * 2 * P + k) * 4 + (n & 3);
-        d[0] = v;
-        d[(size_t)P * 4] = v;
-    }
-    for (int t = threadIdx.x; t < nnz; t += blockDim.x) tp[t] = taps[t];
-    __syncthreads();
-    float* dst_row = spk + ((size_t)g * A + a) * (NB / 4) * (size_t)(P + 2) * 4;
-    for (int n_out = threadIdx.x; n_out < P; n_out += blockDim.x) {
-        float acc[NB];
-#pragma unroll
-        for (int n = 0; n < NB; ++n) acc[n] = 0.f;
-        const float* base = s2 + (size_t)(n_out + P) * 4;
-        for (int t = 0; t < nnz; ++t) {
-            const FbpTap tap = tp[t];
-            const float* sp = base - (size_t)tap.idx * 4;
-#pragma unroll
-            for (int q = 0; q < NB / 4; ++q) {
-                const float4 sv = *reinterpret_cast<const float4*>(sp + (size_t)q * 2 * P * 4);
-                acc[4 * q] = fmaf(tap.val, sv.x, acc[4 * q]); acc[4 * q + 1] = fmaf(tap.val, sv.y, acc[4 * q + 1]);
-                acc[4 * q + 2] = fmaf(tap.val, sv.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(tap.val, sv.w, acc[4 * q + 3]);
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < NB / 4; ++q)
-            *reinterpret_cast<float4*>(dst_row + ((size_t)q * (P + 2) + n_out + 1) * 4) =
-                make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
-    }
-    if (threadIdx.x < 2 * (NB / 4)) {  // halo bins (never read by the FBP gather; keep them defined)
-        const int q = threadIdx.x >> 1;
-        *reinterpret_cast<float4*>(dst_row + ((size_t)q * (P + 2) + ((threadIdx.x & 1) ? P + 1 : 0)) * 4) =
-            make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-}
-
 // ------------------------------------------------------------------------------------------ K3 fused FBP
 // iradon in ONE kernel (fbp_tensorflow.py:49-74): the circular row filter runs in shared memory and its output never
 // leaves the chip.  A thread-block CLUSTER of CL CTAs serves one group of 16 sinograms:

@@ -213,8 +213,11 @@ class LoglikFunction(torch.autograd.Function):
     def backward(ctx, grad_loglik):
         (dproj,) = ctx.saved_tensors
         g = grad_loglik.reshape(-1)
-        if g.numel() > 1 and bool((g != g[0]).any()):
-            cot = dproj * g.view(-1, 1, 1)          # per-image upstream weights (rare): one elementwise scale
+        # The upstream weight is one scalar for a summed loss: it can ride along as the adjoint's `scale` argument --
+        # but reading it costs a device->host sync, which stalls the launch queue and is illegal under CUDA-graph
+        # capture.  Scaling the cotangent on the device is one small elementwise launch and needs neither.
+        if torch.cuda.is_current_stream_capturing() or g.numel() > 1:
+            cot = dproj * g.view(-1, 1, 1)
             dimg = radon_adjoint(cot, ctx.plan, ctx.interp, ctx.mode, ctx.sel)
         else:
             dimg = radon_adjoint_scaled(dproj, ctx.plan, ctx.interp, ctx.mode, float(g[0]), ctx.sel)

@@ -171,14 +171,16 @@ class TruncatedNormal:
 def find_loss_vae_unsup(proj_sample, mask, input_encode, model_encode, model_decode, poisson_noise_multiplier, sqrt_reg,
                         kl_anneal=1.0, kl_multiplier=1.0, num_samples=2, theta=None, angles_i=None, pad=True,
                         use_normal=True, training=True, interpolation="nearest", adjoint="exact"):
-    """helper_functions.py:204-332.  input_encode [B,C,X,Y] (NCHW), mask [B,A], proj_sample [B,A,P]."""
+    """helper_functions.py:204-332.  input_encode [B,C,X,Y] (NCHW), mask [B,A], proj_sample [B,A,P].
+    The distributions are built with validate_args=False: the argument checks are host-synchronising reductions
+    (``(scale > 0).all()``), which stall the launch queue every call and cannot run under CUDA-graph capture."""
     skips_val = model_encode(input_encode / 300)
     q = []
     for sv in skips_val:
         loc, log_scale = sv.chunk(2, dim=1)
         scale = positive_range(log_scale)
-        q.append(torch.distributions.Normal(loc, scale + sqrt_reg) if use_normal
-                 else torch.distributions.Beta(positive_range(loc), scale))
+        q.append(torch.distributions.Normal(loc, scale + sqrt_reg, validate_args=False) if use_normal
+                 else torch.distributions.Beta(positive_range(loc), scale, validate_args=False))
     log_prob_M = []
     out_dists = []
     for _ in range(num_samples):
@@ -189,7 +191,7 @@ def find_loss_vae_unsup(proj_sample, mask, input_encode, model_encode, model_dec
             x = out.sample()
             lp_R = out.log_prob(x)
         else:
-            out = torch.distributions.Beta(positive_range(alpha), positive_range(beta))
+            out = torch.distributions.Beta(positive_range(alpha), positive_range(beta), validate_args=False)
             x = out.rsample()
             lp_R = out.log_prob(torch.clamp(x, sqrt_reg, 1 - sqrt_reg))
         out_dists.append(out)
@@ -198,9 +200,9 @@ def find_loss_vae_unsup(proj_sample, mask, input_encode, model_encode, model_dec
                                       theta=theta, angles_i=angles_i, pad=pad, interpolation=interpolation, adjoint=adjoint)
         log_prob_M.append(lp_M + lp_R.sum())
     if use_normal:
-        prior = [torch.distributions.Normal(torch.zeros_like(d.loc), 1.0) for d in q]
+        prior = [torch.distributions.Normal(torch.zeros_like(d.loc), 1.0, validate_args=False) for d in q]
     else:
-        prior = [torch.distributions.Beta(torch.full_like(d.concentration1, 0.5), torch.full_like(d.concentration0, 0.5)) for d in q]
+        prior = [torch.distributions.Beta(torch.full_like(d.concentration1, 0.5), torch.full_like(d.concentration0, 0.5), validate_args=False) for d in q]
     kl = sum(torch.distributions.kl_divergence(q[i], prior[i]).sum(dim=(1, 2, 3)) for i in range(1, len(q)))
     loglik = torch.stack(log_prob_M).mean(dim=0)
     return kl_anneal * kl_multiplier * kl - loglik, out_dists, kl, loglik
@@ -226,7 +228,9 @@ class CTVAE(nn.Module):
                    kl_anneal=1.0, kl_multiplier=1.0, use_normal=True, sqrt_reg=EPS32, training=True, interpolation="nearest"):
         """main_ct_vae.py:463-486."""
         if self.optimizer is None:
-            self.optimizer = torch.optim.Adam(self.parameters(), lr=self.lr, eps=self.adam_eps)
+            # capturable: the step counter lives on the device, so the optimiser step can be part of a CUDA graph
+            cuda = next(self.parameters()).is_cuda
+            self.optimizer = torch.optim.Adam(self.parameters(), lr=self.lr, eps=self.adam_eps, capturable=cuda)
         with torch.set_grad_enabled(training):
             loss, out_dists, kl, loglik = find_loss_vae_unsup(
                 proj_sample, mask, input_encode, self.encode, self.decode, pnm, sqrt_reg, kl_anneal, kl_multiplier,
@@ -239,9 +243,8 @@ class CTVAE(nn.Module):
             for p in self.parameters():
                 if p.grad is not None:
                     torch.nan_to_num_(p.grad, nan=0.0)
-                    n = p.grad.norm()
-                    if n > norm:                      # tf.clip_by_norm per tensor
-                        p.grad.mul_(norm / n)
+                    # tf.clip_by_norm per tensor: t * clip / max(||t||, clip), without reading the norm on the host
+                    p.grad.mul_(norm / torch.clamp(p.grad.norm(), min=norm))
             self.optimizer.step()
         return loss.detach(), out_dists, kl.detach(), loglik.detach()
 
@@ -263,6 +266,55 @@ class CTVAE(nn.Module):
             n = g.numel()
             g.copy_(flat[off:off + n].view_as(g))
             off += n
+
+
+class GraphedTrainStep:
+    """main_ct_vae.py:375-422's iteration as ONE CUDA graph: batch gather, encoder, ``num_samples`` decoder passes, the
+    fused projector + log-likelihood (forward and adjoint kernels), backward, gradient clipping and the Adam step are
+    captured once and replayed.  The eager step issues ~2200 small launches per iteration and is bound by the host's
+    launch rate (profiles/r2_prof_train_before_graphs.txt: 21 ms per iteration for 8.7 ms of GPU work); a replay
+    costs one launch.  The per-iteration inputs -- the example indices and the angle minibatch (main_ct_vae.py:388-389)
+    -- are written into static device tensors before each replay; the angle subset reaches the kernels as an index
+    list into ONE plan (ctr_radon_loglik_sel), so nothing on the iteration path allocates or creates a plan."""
+
+    def __init__(self, model: "CTVAE", proj_samples, masks, input_encode, pnm, theta, batch: int, angles_per_iter: int,
+                 num_samples: int = 2, pad: bool = True, interpolation: str = "nearest", warmup: int = 3, **step_kwargs):
+        dev = proj_samples.device
+        if dev.type != "cuda":
+            raise RuntimeError("GraphedTrainStep needs CUDA tensors")
+        self.model, self.data = model, (proj_samples, masks, input_encode)
+        self.idx = torch.zeros((batch,), dtype=torch.long, device=dev)
+        self.sel = torch.arange(angles_per_iter, dtype=torch.int32, device=dev)
+        self.args = dict(pnm=pnm, theta=theta, pad=pad, num_samples=num_samples, interpolation=interpolation, **step_kwargs)
+        self.graph = None
+        self.loss = None
+        # warm-up on a side stream (allocator, cuDNN algorithm choice, lazy optimiser state), then capture
+        s = torch.cuda.Stream(dev)
+        s.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(s):
+            for _ in range(max(1, warmup)):
+                self._body()
+        torch.cuda.current_stream(dev).wait_stream(s)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        model.optimizer.zero_grad(set_to_none=True)
+        with torch.cuda.graph(g):
+            self.loss = self._body()
+        self.graph = g
+
+    def _body(self):
+        meas, masks, enc = self.data
+        loss, _, _, _ = self.model.train_step(meas[self.idx], masks[self.idx], enc[self.idx], self.args["pnm"], self.args["theta"],
+                                              angles_i=self.sel, **{k: v for k, v in self.args.items() if k not in ("pnm", "theta")})
+        return loss
+
+    def __call__(self, example_idx, angles_i):
+        """One training iteration on the examples ``example_idx`` [batch] at the angles ``angles_i`` [angles_per_iter];
+        returns the (device) loss of this iteration."""
+        self.idx.copy_(torch.as_tensor(example_idx), non_blocking=True)
+        self.sel.copy_(torch.as_tensor(angles_i).to(torch.int32), non_blocking=True)
+        self.graph.replay()
+        return self.loss
 
 
 # ---------------------------------------------------------------------------------- data preparation

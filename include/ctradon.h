@@ -171,15 +171,11 @@ int ctr_fbp_plan_destroy(ctr_fbp_plan* plan);
  *  - two kernels (default): row filter into a packed sinogram (L2-resident), then the interpolating gather;
  *  - ONE kernel (on != 0; images of up to 128 x 128 = 8 x 2048 pixels): a thread-block cluster filters the sinogram
  *    rows in shared memory and back-projects them from distributed shared memory (ctr_fbp_fused_kernel), so the
- *    filtered rows never leave the chip.  With the dense row filter both paths are bit-identical.  The single kernel
+ *    filtered rows never leave the chip.  Both paths are bit-identical.  The single kernel
  *    holds 64 accumulators per thread and runs one 512-thread CTA per SM; measured on B200 it is the slower of the two
  *    (DESIGN.md section 4), which is why it is opt-in.
  * Returns 1 if on != 0 but the plan's geometry has no single-kernel path. */
 int ctr_fbp_plan_set_fused(ctr_fbp_plan* plan, int on);
-/* The two-kernel path's row filter skips the taps of real(ifft(filter_1d)) that are zero (default on): every other tap
- * of the ramp filter, all but one for filter_1d == 1.  on = 0 forces the dense loop.  Returns 1 if on != 0 but the
- * filter has fewer than 25 % zero taps (the dense loop runs). */
-int ctr_fbp_plan_set_sparse_filter(ctr_fbp_plan* plan, int on);
 size_t ctr_fbp_workspace_bytes(const ctr_fbp_plan* plan, int B);
 /* sino [B,A,P] -> recon [B,x_size,y_size] (float32 on device; the Python shim widens
  * to float64 to keep the reference's return dtype) */

@@ -297,40 +297,13 @@ def test_fused_fbp_is_one_kernel_and_matches_the_two_kernel_path(cp, orc, B, A, 
         _lib.profile_enable(False)
         assert list(prof) == ["ctr_fbp_fused_kernel"] and prof["ctr_fbp_fused_kernel"][1] == 1, prof
         plan.set_fused(False)
-        plan.set_sparse_filter(False)                    # the dense row filter sums in the fused kernel's order
         two = ops.fbp(x, plan)
     finally:
         _lib.profile_enable(False)
         _lib.profile_reset()
-        plan.set_fused(False)                            # library defaults
-        plan.set_sparse_filter(True)
+        plan.set_fused(False)                            # library default
     assert torch.equal(fused, two)
     assert rel_l2(fused.cpu().numpy(), orc.iradon(sino.astype(np.float64), th, X, Y, filt)) <= TOL
-
-
-@pytest.mark.parametrize("name,sparse", [("ramp", True), (None, True), ("hann", False), ("shepp-logan", False)])
-def test_sparse_row_filter_skips_zero_taps(cp, orc, name, sparse):
-    """The ramp filter's spatial kernel has every other tap zero, 'no filter' is one tap: the default row filter sums
-    only the non-zero taps.  Same values as the dense loop up to summation order, and within 1e-5 of the oracle."""
-    from ct_pvae_b200 import _lib, ops
-    rng = np.random.default_rng(52)
-    B, A, X = 19, 11, 70
-    P = cp.num_proj_pix(X, X)
-    th = _theta(A)
-    sino = rng.random((B, A, P), dtype=np.float32)
-    filt = orc.get_fourier_filter(P, name)
-    plan = _lib.get_fbp_plan(th, P, X, X, filt, 0)
-    x = torch.from_numpy(sino).cuda()
-    try:
-        assert plan.set_sparse_filter(True) == sparse
-        a = ops.fbp(x, plan)
-        plan.set_sparse_filter(False)
-        b = ops.fbp(x, plan)
-    finally:
-        plan.set_sparse_filter(True)
-    want = orc.iradon(sino.astype(np.float64), th, X, X, filt)
-    assert rel_l2(a.cpu().numpy(), want) <= TOL and rel_l2(b.cpu().numpy(), want) <= TOL
-    assert rel_l2(a.cpu().numpy(), b.cpu().numpy()) <= 2e-6
 
 
 def test_large_images_take_the_two_kernel_fbp(cp, orc):

@@ -167,3 +167,33 @@ def test_elbo_matches_independent_restatement(orc):
     assert np.allclose(loglik.cpu().numpy(), want_ll, rtol=2e-4), (loglik.cpu().numpy(), want_ll)
     assert np.allclose(loss.cpu().numpy(), want_loss, rtol=2e-4)
     assert th_sub.shape == (api,)
+
+
+@pytest.mark.gpu
+def test_graphed_training_step():
+    """The whole iteration as one CUDA graph (vae.GraphedTrainStep): replays with fresh example indices and angle
+    minibatches, no plan is created, the weights move and the loss stays finite and goes down on a fixed tiny problem."""
+    from ct_pvae_b200 import _lib
+
+    torch.manual_seed(0)
+    dev = torch.device("cuda")
+    N, X, A, b, api = 8, 32, 24, 4, 6
+    theta = np.linspace(0, np.pi, A, endpoint=False)
+    yy, xx = torch.meshgrid(torch.linspace(-1, 1, X), torch.linspace(-1, 1, X), indexing="ij")
+    imgs = ((xx ** 2 + yy ** 2) < 0.6).float()[None].repeat(N, 1, 1).to(dev) * (0.3 + 0.5 * torch.rand(N, 1, 1, device=dev))
+    sino = vae.create_sinogram(imgs, theta, pad=True)
+    masks, meas = vae.create_all_masks(sino, A, 1e4, num_sparse_angles=8, random=True)
+    enc_in = vae.iradon_all(meas, masks, theta, X, X)
+    model = vae.CTVAE(X, X, num_filters=1, num_blocks=2, learning_rate=1e-3).to(dev)
+    before = [p.detach().clone() for p in model.parameters()]
+    step = vae.GraphedTrainStep(model, meas, masks, enc_in, 1e4, theta, batch=b, angles_per_iter=api, num_samples=2)
+    made = _lib.PLANS_CREATED
+    g = torch.Generator().manual_seed(2)
+    losses = []
+    for it in range(120):
+        loss = step(torch.randint(0, N, (b,), generator=g), torch.randperm(A, generator=g)[:api])
+        losses.append(float(loss))
+    assert _lib.PLANS_CREATED == made
+    assert all(math.isfinite(v) for v in losses)
+    assert any(not torch.equal(a, c) for a, c in zip(before, model.parameters()))
+    assert np.mean(losses[-20:]) < np.mean(losses[:20])

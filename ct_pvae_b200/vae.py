@@ -200,7 +200,9 @@ def find_loss_vae_unsup(proj_sample, mask, input_encode, model_encode, model_dec
                                       theta=theta, angles_i=angles_i, pad=pad, interpolation=interpolation, adjoint=adjoint)
         log_prob_M.append(lp_M + lp_R.sum())
     if use_normal:
-        prior = [torch.distributions.Normal(torch.zeros_like(d.loc), 1.0, validate_args=False) for d in q]
+        # (ones_like, not the Python scalar 1.0: torch would build the scalar on the host and copy it to the device --
+        # a host->device copy per call, and illegal under CUDA-graph capture)
+        prior = [torch.distributions.Normal(torch.zeros_like(d.loc), torch.ones_like(d.loc), validate_args=False) for d in q]
     else:
         prior = [torch.distributions.Beta(torch.full_like(d.concentration1, 0.5), torch.full_like(d.concentration0, 0.5), validate_args=False) for d in q]
     kl = sum(torch.distributions.kl_divergence(q[i], prior[i]).sum(dim=(1, 2, 3)) for i in range(1, len(q)))

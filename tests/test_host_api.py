@@ -119,7 +119,8 @@ def test_host_chunk_sizes(monkeypatch):
     c4 = types.SimpleNamespace(A=720, X=512, Y=512)
     assert hostpipe.chunk_for(c2, 256, "fwd") == 64
     assert hostpipe.chunk_for(c2, 1024, "adj") == 256
-    assert hostpipe.chunk_for(c4, 64, "fwd") == 16
+    assert hostpipe.chunk_for(c4, 64, "fwd") == 32         # two chunks of whole 32-image records
+    assert hostpipe.chunk_for(c4, 32, "fwd") == 16
     assert hostpipe.chunk_for(c2, 40, "fwd") == 48          # one chunk: the batch is too small to split
     hostpipe.set_chunk(32, 0)
     try:

@@ -57,9 +57,13 @@ class ConvBlock(nn.Module):
         self.k, self.s, self.transpose, self.cout = kernel, stride, transpose, cout
         self.drop = nn.Dropout(dropout) if dropout > 0 else None
         if transpose:
-            pad = -(-(kernel - stride) // 2) if kernel >= stride else 0
-            self.conv = nn.ConvTranspose2d(cin, 2 * cout, kernel, stride=stride, padding=pad,
-                                           output_padding=2 * pad - (kernel - stride) if kernel >= stride else 0)
+            if kernel < stride:
+                raise ValueError("transposed conv_block needs kernel_size >= stride")
+            # Keras Conv2DTranspose(padding="same") (models.py:287-301): output = input * stride.  The full transposed
+            # convolution is (input - 1) * stride + kernel long; "same" drops kernel - stride samples, the smaller half
+            # in front (the toy run's kernel 2 / stride 1 drops one sample at the end)
+            self.conv = nn.ConvTranspose2d(cin, 2 * cout, kernel, stride=stride, padding=0)
+            self.crop = (kernel - stride) // 2
         else:
             self.conv = nn.Conv2d(cin, 2 * cout, kernel, stride=stride)
         nn.init.xavier_uniform_(self.conv.weight)
@@ -74,6 +78,9 @@ class ConvBlock(nn.Module):
             py = self.k - (hy % self.s if hy % self.s else self.s)
             x = periodic_padding(x, (px // 2 + px % 2, px // 2), (py // 2 + py % 2, py // 2))
         y = self.conv(x)
+        if self.transpose:
+            hx, hy = x.shape[-2] * self.s, x.shape[-1] * self.s
+            y = y[..., self.crop:self.crop + hx, self.crop:self.crop + hy]
         return torch.maximum(y[:, :self.cout], y[:, self.cout:])
 
 

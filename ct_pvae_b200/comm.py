@@ -46,30 +46,44 @@ class PeerComm:
         self.group, self.device = group, device
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.handle = ctypes.c_void_p()
+        self.has_nccl = False
         L = _lib.lib()
-        _lib.check(L.ctr_comm_create(self.world, self.rank, device.index or 0, int(exchange_bytes), ctypes.byref(self.handle)))
+        flag_dev = device if device.type == "cuda" else torch.device("cpu")
+
+        def all_ok(ok: bool) -> bool:
+            """Collective success vote: a step that failed on ONE rank (say, cudaIpcOpenMemHandle refused in a
+            restricted container) must make EVERY rank give up together, or the others would block in the next
+            collective."""
+            t = torch.tensor([1 if ok else 0], device=flag_dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+            return bool(int(t.item()))
+
+        err = None
         try:
+            _lib.check(L.ctr_comm_create(self.world, self.rank, device.index or 0, int(exchange_bytes), ctypes.byref(self.handle)))
             blob = ctypes.create_string_buffer(_lib.COMM_HANDLE_BYTES)
             _lib.check(L.ctr_comm_export(self.handle, blob))
-            every = exchange_blobs(blob.raw, group)
-            _lib.check(L.ctr_comm_connect(self.handle, ctypes.c_char_p(every)))
-            self.has_nccl = False
-            if nccl:
-                idb = ctypes.create_string_buffer(_lib.NCCL_ID_BYTES)
-                ok = 1
-                if self.rank == 0:
-                    ok = 1 if L.ctr_comm_nccl_unique_id(idb) == _lib.CTR_OK else 0
-                flag = torch.tensor([ok], device=device if device.type == "cuda" else "cpu")
-                dist.broadcast(flag, src=0, group=group)
-                if int(flag.item()) == 1:
-                    ident = broadcast_blob(idb.raw if self.rank == 0 else b"", _lib.NCCL_ID_BYTES, 0, group)
-                    _lib.check(L.ctr_comm_nccl_init(self.handle, ctypes.c_char_p(ident)))
-                    self.has_nccl = True
-            if timeout_ms > 0:
-                _lib.check(L.ctr_comm_set_timeout_ms(self.handle, int(timeout_ms)))
-        except Exception:
+            mine = blob.raw
+        except Exception as exc:  # noqa: BLE001
+            err, mine = exc, bytes(_lib.COMM_HANDLE_BYTES)
+        every = exchange_blobs(mine, group)
+        if err is None:
+            try:
+                _lib.check(L.ctr_comm_connect(self.handle, ctypes.c_char_p(every)))
+            except Exception as exc:  # noqa: BLE001
+                err = exc
+        if not all_ok(err is None):
             self.close()
-            raise
+            raise RuntimeError(f"peer exchange buffers could not be mapped on every rank (this rank: {err or 'ok'})")
+        if nccl:
+            idb = ctypes.create_string_buffer(_lib.NCCL_ID_BYTES)
+            ok = self.rank != 0 or L.ctr_comm_nccl_unique_id(idb) == _lib.CTR_OK
+            ident = broadcast_blob(idb.raw if self.rank == 0 else b"", _lib.NCCL_ID_BYTES, 0, group)
+            if all_ok(ok):                      # (rank 0 could not open libnccl: everybody skips NCCL)
+                rc = L.ctr_comm_nccl_init(self.handle, ctypes.c_char_p(ident))
+                self.has_nccl = all_ok(rc == _lib.CTR_OK)
+        if timeout_ms > 0:
+            _lib.check(L.ctr_comm_set_timeout_ms(self.handle, int(timeout_ms)))
 
     def check(self) -> None:
         """Raises CtrError(CTR_ECOMM) if a peer missed an exchange or NCCL reported an asynchronous error."""

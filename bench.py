@@ -441,6 +441,26 @@ def best_ms(ctx, fn, iters=5):
     return float(np.median(ts))
 
 
+def pcie_aggregate(ctx, mbytes=128, reps=4):
+    """All ranks copy pinned host memory to / from their GPU AT THE SAME TIME: the aggregate host<->device rate of the
+    box, which bounds every e2e figure at N > 1 (the ranks share the host's memory system and PCIe roots)."""
+    torch = ctx.torch
+    h = torch.empty(mbytes << 20, dtype=torch.uint8).pin_memory()
+    d = torch.empty_like(h, device=ctx.dev)
+    out = {}
+    for name, fn in (("h2d", lambda: d.copy_(h, non_blocking=True)), ("d2h", lambda: h.copy_(d, non_blocking=True))):
+        fn()
+        ctx.sync_all()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize(ctx.dev)
+        dt = ctx.max_over_ranks(time.perf_counter() - t0)
+        out[name + "_GBs_all_ranks"] = ctx.world * reps * (mbytes << 20) / dt / 1e9
+        ctx.sync_all()
+    return out
+
+
 def kernel_table(prof, total_ms):
     return {k: {"ms_per_launch": v[0] / v[1], "launches": v[1], "share_of_step": v[0] / total_ms} for k, v in prof.items()}
 
@@ -776,6 +796,10 @@ def run_angle(args, ctx, wl):
                 others["batch_sharded_" + key] = {k: r2[k] for k in ("workload", "ms_per_step", "value", "unit")}
             except Exception as exc:
                 others["batch_sharded_" + key] = {"error": repr(exc)[:200]}
+        try:
+            others["pcie_aggregate"] = pcie_aggregate(ctx)
+        except Exception as exc:
+            others["pcie_aggregate"] = {"error": repr(exc)[:200]}
         if not args.no_train_leg:
             try:
                 leg = vae_training_leg(ctx.dev, seed=ctx.rank, world=ctx.world)

@@ -1285,7 +1285,9 @@ static int exchange_begin(ctr_comm* c, int B, size_t img_floats, int algo, CtrEx
     }
     if (!c->connected) return fail(CTR_EINVAL, std::string(who) + ": ctr_comm_connect has not been called");
     if ((size_t)B * img_floats * sizeof(float) > c->bytes) return fail(CTR_EWORKSPACE, std::string(who) + ": exchange buffer smaller than B*X*Y*4 bytes");
-    const unsigned epoch = ++c->epoch;
+    // the epoch is committed by exchange_finish_p2p, once the back-projection kernel has been enqueued: a call that
+    // fails before that leaves the ranks' epochs in step
+    const unsigned epoch = c->epoch + 1;
     for (int s = 0; s < c->nranks; ++s) xg->peer[s] = (float*)((char*)c->peer_base[s] + kXgHeader + (size_t)(epoch & 1) * c->bytes);
     xg->nranks = c->nranks; xg->rank = c->rank; xg->Bs = B / c->nranks;
     return CTR_OK;
@@ -1301,7 +1303,7 @@ static int exchange_finish_p2p(ctr_comm* c, const CtrExchange& xg, float* out, s
     xp.slots = xg.peer[c->rank];
     xp.out = out;
     xp.n = n;
-    xp.epoch = c->epoch;
+    xp.epoch = ++c->epoch;
     xp.nranks = c->nranks; xp.rank = c->rank;
     xp.timeout_ns = c->timeout_ns;
     size_t blocks = (n / 4 + 511) / 512;

@@ -650,7 +650,7 @@ def run_batch(args, ctx, wl):
                     r2, st2 = batch_record(ctx, WORKLOADS[key], max(10, args.steps // 2), 3)
                     r2["workload"] = WORKLOADS[key]["name"]
                     r2["smem_roofline"] = smem_rooflines(r2, WORKLOADS[key], WORKLOADS[key]["A"], r2["clocks"])
-                    r2["e2e"] = e2e_batch(ctx, WORKLOADS[key], st2, max(5, args.steps // 5))
+                    r2["e2e"] = e2e_batch(ctx, WORKLOADS[key], st2, args.steps if key == "c2" else max(5, args.steps // 5))
                     del st2
                     torch.cuda.empty_cache()
                     others[key] = r2
@@ -745,21 +745,25 @@ def run_angle(args, ctx, wl):
     cot_h = cot.cpu().pin_memory()
     sino_h = torch.empty((B, A_loc, P), dtype=torch.float32).pin_memory()
     g_h = torch.empty((B // ctx.world, X, X), dtype=torch.float32).pin_memory()
-    side_stream = torch.cuda.Stream(ctx.dev)
+    up_stream, down_stream = torch.cuda.Stream(ctx.dev), torch.cuda.Stream(ctx.dev)
 
     def e2e_step():
         cur = torch.cuda.current_stream(ctx.dev)
-        side_stream.wait_stream(cur)
-        with torch.cuda.stream(side_stream):          # cotangent upload under the forward
+        up_stream.wait_stream(cur)
+        with torch.cuda.stream(up_stream):            # cotangent upload under the image upload / forward
             cot_d = cot_h.to(ctx.dev, non_blocking=True)
         img_d = op.gather_images(img_h.to(ctx.dev, non_blocking=True))
         s = op.forward(img_d)
-        sino_h.copy_(s, non_blocking=True)
-        cur.wait_stream(side_stream)
+        down_stream.wait_stream(cur)
+        with torch.cuda.stream(down_stream):          # sinogram download under the adjoint
+            sino_h.copy_(s, non_blocking=True)
+        s.record_stream(down_stream)
+        cur.wait_stream(up_stream)
         g = op.adjoint(cot_d)
         g_h.copy_(g, non_blocking=True)
         cot_d.record_stream(cur)
         cur.synchronize()
+        down_stream.synchronize()
 
     for _ in range(3):
         e2e_step()

@@ -218,9 +218,12 @@ class AngleShardedRadon:
             try:
                 from . import comm as _comm
                 self.comm = _comm.PeerComm(self.B * self.X * self.Y * 4, device, group, nccl=(algo in ("nccl", "auto")))
-            except Exception:
+            except Exception as exc:  # noqa: BLE001
                 if algo != "auto":
                     raise
+                import warnings
+                warnings.warn(f"AngleShardedRadon: peer exchange unavailable ({exc}); summing the partial back-projections "
+                              "with torch.distributed.reduce_scatter_tensor instead", RuntimeWarning, stacklevel=2)
         self.algo = ("p2p" if algo == "auto" else algo) if self.comm is not None else "torch"
 
     @property

@@ -727,18 +727,18 @@ static int fbp_impl(const ctr_fbp_plan* p, const float* sino, int A, int A_total
     const int G = (B + NBb - 1) / NBb;
     float* spk = (float*)ws;
     {
-        const size_t smem = (size_t)p->P * (NBb + 2) * sizeof(float);
-        dim3 grid(p->A, G), block(256);
+        const size_t smem = ((size_t)p->P * (NBb + 2) + 1) * sizeof(float);
+        const int pairs = (p->P + 1) / 2;                                  // two adjacent bins per thread
+        dim3 grid(p->A, G), block(std::min(256, (pairs + 31) / 32 * 32));
         ProfScope prof(CTR_K_FBP_FILTER, st);
-        if (NBb == 32) {
-            CTR_CUDA(cudaFuncSetAttribute(ctr::ctr_fbp_filter_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            ctr::ctr_fbp_filter_kernel<32><<<grid, block, smem, st>>>(sino, p->d_h, B, p->A, p->P, spk);
-        } else if (NBb == 16) {
+        if (NBb == 16) {
             CTR_CUDA(cudaFuncSetAttribute(ctr::ctr_fbp_filter_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             ctr::ctr_fbp_filter_kernel<16><<<grid, block, smem, st>>>(sino, p->d_h, B, p->A, p->P, spk);
-        } else {
+        } else if (NBb == 8) {
             CTR_CUDA(cudaFuncSetAttribute(ctr::ctr_fbp_filter_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             ctr::ctr_fbp_filter_kernel<8><<<grid, block, smem, st>>>(sino, p->d_h, B, p->A, p->P, spk);
+        } else {
+            return fail(CTR_EUNSUPPORTED, "ctr_fbp: unexpected image group size");
         }
         ctr::launch_counter()++;
         CTR_CUDA(cudaGetLastError());

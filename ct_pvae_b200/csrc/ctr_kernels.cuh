@@ -678,7 +678,12 @@ __global__ void __launch_bounds__(512) ctr_xchg_sum_kernel(const XchgParams p)
 // ------------------------------------------------------------------------------------------ K3a filter
 // rf[n] = sum_k s[k] * h[(n-k) mod P]  ==  real(ifft(fft(s) * filter_1d))   for real s
 // (fbp_tensorflow.py:49-50; no zero padding, so the convolution is circular).
-// grid (A, G), block 256.  smem: NB rows interleaved [P][NB] + doubled kernel h2[2P].
+// grid (A, G), block = ceil(P/2) threads rounded up to a warp (at most 256).  smem: NB rows interleaved [P][NB] +
+// doubled kernel h2[2P].  A thread computes TWO adjacent bins for all NB images: per k it reads the NB sinogram values
+// once (broadcast LDS.128) and ONE new kernel value -- the second bin's h at step k is the first bin's h at step k-1 --
+// so the loop is 2*NB FFMA per NB/4 + 1 shared-memory loads (r1's one-bin-per-thread loop was bound by those loads, and
+// 72 of its 256 threads had no bin at P = 184: 0.48 -> see DESIGN.md section 4).  k ascending, fmaf(h, s, acc): the
+// same sums, bit for bit, as the fused kernel's filter stage.
 // Output goes straight into the plane-layout sinogram pack K3b reads.
 template <int NB>
 __global__ void __launch_bounds__(256) ctr_fbp_filter_kernel(const float* __restrict__ sino, const float* __restrict__ h,
@@ -686,32 +691,39 @@ __global__ void __launch_bounds__(256) ctr_fbp_filter_kernel(const float* __rest
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* s = reinterpret_cast<float*>(smem_raw);   // [P][NB]
-    float* h2 = s + (size_t)P * NB;                   // [2P]
+    float* h2 = s + (size_t)P * NB;                   // [2P] (+ 1 pad)
     const int a = blockIdx.x, g = blockIdx.y;
     for (int idx = threadIdx.x; idx < P * NB; idx += blockDim.x) {
         const int n = idx / P, k = idx - n * P;       // coalesced along k per image
         const int b = g * NB + n;
         s[k * NB + n] = (b < B) ? __ldg(sino + ((size_t)b * A + a) * P + k) : 0.f;
     }
-    for (int m = threadIdx.x; m < 2 * P; m += blockDim.x) h2[m] = __ldg(h + (m >= P ? m - P : m));
+    for (int m = threadIdx.x; m <= 2 * P; m += blockDim.x) h2[m] = (m < 2 * P) ? __ldg(h + (m >= P ? m - P : m)) : 0.f;
     __syncthreads();
     float* dst_row = spk + ((size_t)g * A + a) * (NB / 4) * (size_t)(P + 2) * 4;
-    for (int n_out = threadIdx.x; n_out < P; n_out += blockDim.x) {
-        float acc[NB];
+    for (int n0 = 2 * threadIdx.x; n0 < P; n0 += 2 * blockDim.x) {
+        float a0[NB], a1[NB];
 #pragma unroll
-        for (int n = 0; n < NB; ++n) acc[n] = 0.f;
-        const float* hp = h2 + n_out + P;
+        for (int n = 0; n < NB; ++n) { a0[n] = 0.f; a1[n] = 0.f; }
+        const float* hp = h2 + n0 + P;
+        float h_hi = hp[1];                           // h2[n0 + 1 + P - k] at k = 0
         for (int k = 0; k < P; ++k) {
-            const float hv = hp[-k];
+            const float h_lo = hp[-k];
             float sv[NB];
             ctr_ldv<NB>(s + (size_t)k * NB, sv);
 #pragma unroll
-            for (int n = 0; n < NB; ++n) acc[n] = fmaf(hv, sv[n], acc[n]);
+            for (int n = 0; n < NB; ++n) {
+                a0[n] = fmaf(h_lo, sv[n], a0[n]);
+                a1[n] = fmaf(h_hi, sv[n], a1[n]);
+            }
+            h_hi = h_lo;
         }
 #pragma unroll
-        for (int q = 0; q < NB / 4; ++q)
-            *reinterpret_cast<float4*>(dst_row + ((size_t)q * (P + 2) + n_out + 1) * 4) =
-                make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+        for (int q = 0; q < NB / 4; ++q) {
+            float* d = dst_row + ((size_t)q * (P + 2) + n0 + 1) * 4;
+            *reinterpret_cast<float4*>(d) = make_float4(a0[4 * q], a0[4 * q + 1], a0[4 * q + 2], a0[4 * q + 3]);
+            if (n0 + 1 < P) *reinterpret_cast<float4*>(d + 4) = make_float4(a1[4 * q], a1[4 * q + 1], a1[4 * q + 2], a1[4 * q + 3]);
+        }
     }
     if (threadIdx.x < 2 * (NB / 4)) {  // halo bins (never read by the FBP gather; keep them defined)
         const int q = threadIdx.x >> 1;

@@ -10,4 +10,4 @@ from .forward_functions import backproject, num_proj_pix, pad_phantom, project_t
 from .fbp_tensorflow import get_fourier_filter, iradon  # noqa: F401
 from .likelihood import calculate_log_prob_M_given_R, log_prob_M_given_R_sum  # noqa: F401
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"

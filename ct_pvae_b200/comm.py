@@ -10,7 +10,6 @@ from __future__ import annotations
 
 import ctypes
 
-import numpy as np
 import torch
 import torch.distributed as dist
 

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define CTR_VERSION 100 /* 0.1.0 */
+#define CTR_VERSION 200 /* 0.2.0 */
 
 enum {
     CTR_OK = 0,

@@ -36,7 +36,7 @@ def test_every_declared_symbol_is_exported_and_bound(L):
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/ctradon.h but not exported"
     assert sorted(_lib.SYMBOLS) == names, "ctypes table and header disagree"
-    assert L.ctr_version() == 100
+    assert L.ctr_version() == 200
 
 
 def test_host_geometry_matches_oracle(L, orc):

@@ -6,7 +6,6 @@ import collections
 import os
 import re
 import subprocess
-import sys
 
 so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ct_pvae_b200", "libctradon.so")
 out = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True, check=True).stdout

@@ -95,3 +95,37 @@ def test_no_gpu_means_loud_failure(L):
     rc = L.ctr_plan_create(th.ctypes.data_as(f64p), 2, 4, 4, 1, 0, ctypes.byref(h))
     assert rc == -2 and not h.value, "plan creation must fail with CTR_ECUDA without a device"
     assert len(L.ctr_last_error()) > 0
+
+
+def _build_c_smoke(tmp_path):
+    """tests/capi/capi_smoke.c: the library driven from plain C (no Python, no torch) -- compiled against
+    include/ctradon.h and linked to the in-tree libctradon.so."""
+    import shutil
+    import subprocess
+
+    from ct_pvae_b200 import _lib
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    _lib.lib()                                         # raises if the library has not been built
+    exe = str(tmp_path / "capi_smoke")
+    cuda_lib = "/usr/local/cuda/lib64"
+    cmd = [shutil.which("gcc") or "/usr/bin/gcc", "-O2", "-std=c11", "-I", os.path.join(root, "include"),
+           os.path.join(root, "tests", "capi", "capi_smoke.c"), "-o", exe, "-L", os.path.join(root, "ct_pvae_b200"), "-lctradon",
+           "-L", cuda_lib, "-lcudart", "-lm", "-Wl,-rpath," + os.path.join(root, "ct_pvae_b200"), "-Wl,-rpath," + cuda_lib]
+    subprocess.check_call(cmd)
+    return exe
+
+
+def test_c_program_links_and_runs_host_checks(tmp_path):
+    import subprocess
+
+    out = subprocess.run([_build_c_smoke(tmp_path)], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and "capi_smoke ok (host)" in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.gpu
+def test_c_program_runs_the_projector_without_python(tmp_path):
+    import subprocess
+
+    out = subprocess.run([_build_c_smoke(tmp_path), "gpu"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "capi_smoke ok (gpu)" in out.stdout, out.stdout + out.stderr

@@ -43,7 +43,7 @@ for it in range(n):
     rhs = float((img[..., 0].double() * gsub.double()).sum())
     assert abs(lhs - rhs) / max(abs(lhs), 1e-30) < 5e-6, f"subset adjoint identity broken at it={it} {B,X,Y,A,pad,interp,k}"
     # FBP: one cluster kernel == filter + gather, bit for bit (images that fit the single kernel)
-    if X * Y <= 16384 and it % 5 == 0:
+    if X * Y <= 16384 and it % 5 == 0 and plan.W % 2 == 0:     # (the ramp filter is defined for even detector widths)
         P = plan.W
         fplan = _lib.get_fbp_plan(np.asarray(th, np.float64), P, X, Y, cp.get_fourier_filter(P, "ramp"), 0)
         sino = s1[..., 0].contiguous()

@@ -207,6 +207,7 @@ class AngleShardedRadon:
             full = _lib.get_plan(theta, self.X, self.Y, bool(pad), device.index or 0)
             kappa = 0.2 if "windowed=1" in full.describe(self.B) else 0.0
         lo, hi = cost_balanced_range(theta, self.rank, self.world, kappa)
+        self._theta, self._kappa = theta, kappa
         self.angle_indices = np.arange(lo, hi)
         self.assignment = assignment if kappa > 0 else "equal"
         self.theta_local = np.ascontiguousarray(theta[self.angle_indices])
@@ -234,6 +235,20 @@ class AngleShardedRadon:
         """This rank's rows of a full ``[B, A, W]`` sinogram-shaped tensor, as a contiguous ``[B, A_local, W]``."""
         idx = torch.as_tensor(self.angle_indices, device=full.device)
         return full.index_select(1, idx).contiguous()
+
+    def gather_rows(self, local: torch.Tensor) -> torch.Tensor:
+        """This rank's sinogram rows ``[B, A_local, W]`` -> the full ``[B, A, W]`` on every rank (one all-gather over
+        NVLink; the blocks may differ in length, so they travel padded to the longest).  Only for consumers that need
+        the whole sinogram on one device -- the operator pair itself never does."""
+        if self.world == 1:
+            return local
+        counts = [cost_balanced_range(self._theta, r, self.world, self._kappa) for r in range(self.world)]
+        longest = max(hi - lo for lo, hi in counts)
+        padded = torch.zeros((local.shape[0], longest, local.shape[2]), dtype=local.dtype, device=local.device)
+        padded[:, :local.shape[1]].copy_(local)
+        bufs = torch.empty((self.world,) + tuple(padded.shape), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(bufs, padded, group=self.group)
+        return torch.cat([bufs[r, :, :hi - lo] for r, (lo, hi) in enumerate(counts)], dim=1)
 
     def gather_images(self, img_shard: torch.Tensor) -> torch.Tensor:
         """``[B/world, X, Y]`` (this rank's share of a host-side batch, already on the device) -> all ``B`` images on

@@ -53,7 +53,9 @@ def _worker(rank, world, port, out_dir):
     for interp in ("bilinear", "nearest"):
         op = sharding.AngleShardedRadon(theta, X, X, True, B, dev, interpolation=interp, algo="auto")
         assert op.algo == "p2p" and op.comm is not None and op.comm.has_nccl, op.algo
-        res[f"fwd_block_{interp}"] = op.forward(img[..., 0].contiguous()).cpu().numpy()
+        blk = op.forward(img[..., 0].contiguous())
+        res[f"fwd_block_{interp}"] = blk.cpu().numpy()
+        res[f"fwd_gathered_{interp}"] = op.gather_rows(blk).cpu().numpy()
         cl = op.local_rows(cot)
         res[f"angles_{interp}"] = op.angle_indices
         for algo in ("p2p", "nccl", "torch"):
@@ -105,6 +107,7 @@ def test_nccl_sharding_matches_oracle(tmp_path, orc):
         for interp in ("bilinear", "nearest"):
             mine = z[f"angles_{interp}"]
             assert rel_l2(z[f"fwd_block_{interp}"], fwd[interp][:, mine]) <= 1e-5
+            assert rel_l2(z[f"fwd_gathered_{interp}"], fwd[interp]) <= 1e-5
             want = grad[interp][r * per:(r + 1) * per]
             for algo in ("p2p", "nccl", "torch"):
                 for k in range(3):

@@ -84,6 +84,7 @@ struct ProfScope {
 
 }  // namespace
 
+constexpr int kShapes = 4;
 struct ctr_plan {
     int device = 0;
     int A = 0, X = 0, Y = 0, pad = 0, H = 0, W = 0, padx = 0, pady = 0;
@@ -92,7 +93,8 @@ struct ctr_plan {
     int n_cls[2] = {0, 0};
     CtrClassGeom geom[2];
     // forward kernel shapes: [0] 4 images per pixel record (any detector, any batch), [1] depth-first 8/16-image
-    // records, [2] 32-image records with 8 images per lane; [1] and [2] are column-windowed on wide detectors
+    // records, [2] 32-image records with 8 images per lane, [3] 32-image records with 16 images per lane (two lanes
+    // per ray); [1]..[3] are column-windowed on wide detectors
     // (fc.R == 0: shape unavailable for this geometry)
     struct Shape {
         ctr::FwdConfig fc;
@@ -103,7 +105,7 @@ struct ctr_plan {
         std::vector<CtrChunk> singles;
         CtrChunk* d_singles = nullptr;
         size_t smem_single = 0;
-    } shape[3];
+    } shape[kShapes];
     std::vector<int> pos;      // angle -> its row in the class-sorted ray table
     int* d_pos = nullptr;
     int sm_count = 148;
@@ -247,9 +249,10 @@ int ctr_plan_create(const double* theta, int A, int X, int Y, int pad, int devic
     p->shape[0].fc = ctr::fwd_config(p->W, p->geom, smem_optin - 2048);
     p->shape[1].fc = ctr::fwd_config_depth(p->W, p->geom, smem_optin - 2048, false);
     p->shape[2].fc = ctr::fwd_config_depth(p->W, p->geom, smem_optin - 2048, true);
+    p->shape[3].fc = ctr::fwd_config_wide(p->W, p->geom, smem_optin - 2048);
     if (p->shape[0].fc.R < 1) { delete p; return fail(CTR_EUNSUPPORTED, "ctr_plan_create: image rows too wide for the shared-memory strips"); }
     // CTA columns: chunks of consecutive table entries, strip height and (wide detectors) column windows
-    for (int k = 0; k < 3; ++k) {
+    for (int k = 0; k < kShapes; ++k) {
         ctr_plan::Shape& sh = p->shape[k];
         ctr::FwdConfig& fc = sh.fc;
         size_t strip_bytes = 0;
@@ -257,7 +260,10 @@ int ctr_plan_create(const double* theta, int A, int X, int Y, int pad, int devic
             const int rmax = 16;   // r1: taller windowed strips only widen the windows (C4: R <= 10 or 3 stages +3 %)
             // widely spaced angles (sparse-angle minibatches): retry with fewer angle slots per CTA
             for (int ns = fc.NS; ns >= 1; ns /= 2) {
-                if (ns != fc.NS) fc = ctr::fwd_config_depth(p->W, p->geom, smem_optin - 2048, k == 2, ns);
+                if (ns != fc.NS)
+                    fc = (k == 3) ? ctr::fwd_config_wide(p->W, p->geom, smem_optin - 2048, ns)
+                                  : ctr::fwd_config_depth(p->W, p->geom, smem_optin - 2048, k == 2, ns);
+                if (fc.JW < 1 || !fc.windowed) { fc.R = 0; continue; }
                 const int NA = fc.angles_per_cta(), fixed = ctr::FwdConfig::fixed_bytes(NA);
                 const size_t budget = (size_t)(smem_optin - 2048 - fixed);
                 if (ctr_h_build_chunks(p->rays, seg, p->geom, NA, p->W, fc.JW, fc.jchunks, ctr::kFwdNB * fc.depth * 4, fc.stages,
@@ -275,7 +281,7 @@ int ctr_plan_create(const double* theta, int A, int X, int Y, int pad, int devic
         }
     }
     // angle-subset calls: one CTA column per ray (same strip / window sizing rules, one ray per window)
-    for (int k = 0; k < 3; ++k) {
+    for (int k = 0; k < kShapes; ++k) {
         ctr_plan::Shape& sh = p->shape[k];
         const ctr::FwdConfig& fc = sh.fc;
         if (fc.R < 1) continue;
@@ -295,19 +301,19 @@ int ctr_plan_create(const double* theta, int A, int X, int Y, int pad, int devic
     for (int k = 0; k < A; ++k) p->pos[p->rays[k].angle] = k;
     // one allocation + one upload for all tables
     const size_t tb = (size_t)A * 8 * sizeof(float), rb = (size_t)A * sizeof(CtrRay), pb = align_up((size_t)A * sizeof(int), 16);
-    size_t cb[6], ctot = 0;
-    for (int k = 0; k < 3; ++k) {
+    size_t cb[2 * kShapes], ctot = 0;
+    for (int k = 0; k < kShapes; ++k) {
         cb[k] = p->shape[k].chunks.size() * sizeof(CtrChunk);
-        cb[3 + k] = p->shape[k].singles.size() * sizeof(CtrChunk);
-        ctot += cb[k] + cb[3 + k];
+        cb[kShapes + k] = p->shape[k].singles.size() * sizeof(CtrChunk);
+        ctot += cb[k] + cb[kShapes + k];
     }
     std::vector<unsigned char> host(2 * tb + rb + pb + ctot);
     std::memcpy(host.data(), p->t.data(), tb);
     std::memcpy(host.data() + tb, p->tinv.data(), tb);
     std::memcpy(host.data() + 2 * tb, p->rays.data(), rb);
     std::memcpy(host.data() + 2 * tb + rb, p->pos.data(), (size_t)A * sizeof(int));
-    for (size_t k = 0, off = 2 * tb + rb + pb; k < 6; off += cb[k], ++k) {
-        const std::vector<CtrChunk>& v = k < 3 ? p->shape[k].chunks : p->shape[k - 3].singles;
+    for (size_t k = 0, off = 2 * tb + rb + pb; k < 2 * kShapes; off += cb[k], ++k) {
+        const std::vector<CtrChunk>& v = k < kShapes ? p->shape[k].chunks : p->shape[k - kShapes].singles;
         if (cb[k]) std::memcpy(host.data() + off, v.data(), cb[k]);
     }
     if ((e = cudaMalloc(&p->d_block, host.size())) != cudaSuccess ||
@@ -321,9 +327,9 @@ int ctr_plan_create(const double* theta, int A, int X, int Y, int pad, int devic
     p->d_tinv = (float*)((char*)p->d_block + tb);
     p->d_rays = (CtrRay*)((char*)p->d_block + 2 * tb);
     p->d_pos = (int*)((char*)p->d_block + 2 * tb + rb);
-    for (size_t k = 0, off = 2 * tb + rb + pb; k < 6; off += cb[k], ++k) {
-        if (k < 3) p->shape[k].d_chunks = (CtrChunk*)((char*)p->d_block + off);
-        else p->shape[k - 3].d_singles = (CtrChunk*)((char*)p->d_block + off);
+    for (size_t k = 0, off = 2 * tb + rb + pb; k < 2 * kShapes; off += cb[k], ++k) {
+        if (k < kShapes) p->shape[k].d_chunks = (CtrChunk*)((char*)p->d_block + off);
+        else p->shape[k - kShapes].d_singles = (CtrChunk*)((char*)p->d_block + off);
     }
     *out = p;
     return CTR_OK;
@@ -361,13 +367,17 @@ int ctr_plan_tables(const ctr_plan* p, float* fwd, float* inv)
 
 // which forward shape serves a batch of B: the deepest pixel record the batch fills reasonably
 // (32 images from 17 up, 8/16 from 3 lanes' worth up), else the 4-image records
-static const ctr_plan::Shape& shape_for(const ctr_plan* p, int B, bool subset = false)
+static const ctr_plan::Shape& shape_for(const ctr_plan* p, int B, bool subset = false, int interp = CTR_INTERP_BILINEAR)
 {
     const ctr_plan::Shape& s16 = p->shape[1];
     const ctr_plan::Shape& s32 = p->shape[2];
     // angle-subset calls run one ray per CTA column (the `singles` tables)
     const bool ok16 = s16.fc.R >= 1 && B >= 3 * s16.fc.depth && (!subset || !s16.singles.empty());
     const bool ok32 = s32.fc.R >= 1 && B > 16 && (!subset || !s32.singles.empty());
+    // nearest neighbour: one record per sample, so the per-sample geometry dominates and 16 images per lane win
+    // (r2, 64 x 512^2 x 720: 3.22 -> 2.15 ms; 256 x 128^2 x 180: 0.300 -> 0.265 ms)
+    const ctr_plan::Shape& sw = p->shape[3];
+    const bool okw = interp == CTR_INTERP_NEAREST && sw.fc.R >= 1 && B > 16 && (!subset || !sw.singles.empty());
     if (!subset && ok16 && ok32 && s16.fc.lanes == 4 && !s16.fc.windowed && !s32.fc.windowed) {
         // Both run one CTA per SM; a 32-image CTA does twice the work of a 16-image one in 1.84x the time
         // (r1: 93 vs 51 us per wave at 128^2 x 180).  Small batches (the chunks of the host pipeline) leave the last
@@ -377,20 +387,24 @@ static const ctr_plan::Shape& shape_for(const ctr_plan* p, int B, bool subset = 
             const long long ctas = G * (long long)sh.chunks.size() * sh.fc.jchunks;
             return (double)((ctas + p->sm_count - 1) / p->sm_count);
         };
-        return (waves(s32) * 1.84 <= waves(s16)) ? s32 : s16;
+        return (waves(s32) * 1.84 <= waves(s16)) ? (okw ? sw : s32) : s16;
     }
+    if (okw) return sw;
     if (ok32) return s32;
     if (ok16) return s16;
     return p->shape[0];
 }
-static const ctr::FwdConfig& fwd_cfg_for(const ctr_plan* p, int B, bool subset = false) { return shape_for(p, B, subset).fc; }
+static const ctr::FwdConfig& fwd_cfg_for(const ctr_plan* p, int B, bool subset = false, int interp = CTR_INTERP_BILINEAR)
+{
+    return shape_for(p, B, subset, interp).fc;
+}
 
 // one packed copy of the batch; sized for the deeper of the full-plan and the angle-subset shape of this batch size
 static size_t pack_bytes(const ctr_plan* p, int B)
 {
     size_t best = 0;
-    for (int subset = 0; subset < 2; ++subset) {
-        const size_t rec = (size_t)ctr::kFwdNB * fwd_cfg_for(p, B, subset != 0).depth;
+    for (int k = 0; k < 4; ++k) {
+        const size_t rec = (size_t)ctr::kFwdNB * fwd_cfg_for(p, B, (k & 1) != 0, (k & 2) ? CTR_INTERP_NEAREST : CTR_INTERP_BILINEAR).depth;
         const size_t G = ((size_t)B + rec - 1) / rec;
         const size_t px0 = (size_t)p->geom[0].Vp * p->geom[0].Up, px1 = (size_t)p->geom[1].Vp * p->geom[1].Up;
         best = std::max(best, align_up(G * std::max(px0, px1) * rec * sizeof(float), 256));
@@ -409,10 +423,12 @@ int ctr_plan_describe(const ctr_plan* p, int B, char* buf, size_t n)
         rlo = std::min(rlo, c.R); rhi = std::max(rhi, c.R);
         if (c.wc > 0) { wlo = std::min(wlo, c.wc); whi = std::max(whi, c.wc); ++nwin; }
     }
+    const ctr::FwdConfig& fn = fwd_cfg_for(p, B, false, CTR_INTERP_NEAREST);   // the nearest-neighbour projector's shape
     snprintf(buf, n, "images_per_record=%d windowed=%d window_chunks=%d/%d JW=%d jchunks=%d NS=%d KA=%d stages=%d R=%d..%d wc=%d..%d smem=%zu "
-             "adjoint_images_per_thread: exact=%d tf_compat=%d",
+             "adjoint_images_per_thread: exact=%d tf_compat=%d nearest: images_per_lane=%d JW=%d NS=%d",
              ctr::kFwdNB * fc.depth, fc.windowed, nwin, (int)ch.size(), fc.JW, fc.jchunks, fc.NS, fc.KA, fc.stages, rlo, rhi,
-             nwin ? wlo : 0, whi, fc.smem, ctr::bp_nb_for_batch(B, CTR_ADJ_EXACT, p->X, p->Y), ctr::bp_nb_for_batch(B, CTR_ADJ_TF, p->X, p->Y));
+             nwin ? wlo : 0, whi, fc.smem, ctr::bp_nb_for_batch(B, CTR_ADJ_EXACT, p->X, p->Y), ctr::bp_nb_for_batch(B, CTR_ADJ_TF, p->X, p->Y),
+             ctr::kFwdNB * fn.depth / fn.lanes, fn.JW, fn.NS);
     return CTR_OK;
 }
 
@@ -453,9 +469,10 @@ struct LoglikArgs {
 static size_t loglik_partial_bytes(const ctr_plan* p, int B)
 {
     size_t best = 0;
-    for (int subset = 0; subset < 2; ++subset) {
-        const ctr::FwdConfig& fc = fwd_cfg_for(p, B, subset != 0);
-        const size_t chunks = subset ? (size_t)p->A : shape_for(p, B).chunks.size();   // a subset has at most A columns
+    for (int k = 0; k < 4; ++k) {
+        const int subset = k & 1, interp = (k & 2) ? CTR_INTERP_NEAREST : CTR_INTERP_BILINEAR;
+        const ctr::FwdConfig& fc = fwd_cfg_for(p, B, subset != 0, interp);
+        const size_t chunks = subset ? (size_t)p->A : shape_for(p, B, false, interp).chunks.size();   // a subset has at most A columns
         const size_t rec = (size_t)ctr::kFwdNB * fc.depth;
         const size_t G = ((size_t)B + rec - 1) / rec;
         best = std::max(best, align_up(chunks * fc.jchunks * G * rec * sizeof(float), 256));
@@ -476,7 +493,7 @@ static int forward_impl(const ctr_plan* p, const float* img, float* out, int B, 
     DeviceGuard guard(p->device);
     if (!guard.ok) return fail_cuda(guard.err, "cudaSetDevice");
     cudaStream_t st = (cudaStream_t)stream;
-    const ctr_plan::Shape& sh = shape_for(p, B, sel != nullptr);
+    const ctr_plan::Shape& sh = shape_for(p, B, sel != nullptr, interp);
     ctr::FwdConfig fc = sh.fc;
     if (sel) {
         if (sh.singles.empty()) return fail(CTR_EUNSUPPORTED, std::string(who) + ": no per-ray strip table for this geometry");

@@ -135,6 +135,22 @@ CTR_HD void ctr_ldv8_swz(const float* __restrict__ p, int swz, float* __restrict
     ctr_ldv<4>(p + (swz ^ 4), out + 4);
 }
 
+// Sixteen images of one lane out of a 32-image record (TWO lanes per ray): four 16-byte loads in an order rotated
+// by the ray's index mod 4 (rot = 0, 4, 8 or 12 floats).  A quarter-warp is then 4 rays x 2 lanes, and in every
+// instruction the rays' lanes read chunks {t+r mod 4} and {4 + (t+r mod 4)}, r = 0..3: eight different bank groups,
+// conflict-free wherever the four rays' pixels are.  out[4t..4t+3] holds images ((4t + rot) & 15) + 0..3 of the block.
+CTR_HD void ctr_ldv16_rot(const float* __restrict__ p, int rot, float* __restrict__ out)
+{
+#pragma unroll
+    for (int t = 0; t < 4; ++t) ctr_ldv<4>(p + ((4 * t + rot) & 15), out + 4 * t);
+}
+
+// which image of the lane's block register n holds under the load order above (swz = 0 for plain loads):
+// n ^ swz for the parity swizzle of 8-image lanes, (n + rot) & 15 for the rotation of 16-image lanes -- the same
+// expression, since swz and rot are multiples of 4 below NB.
+template <int NB>
+CTR_HD int ctr_img_of_reg(int n, int swz) { return (n + swz) & (NB - 1); }
+
 // Sinogram windows are staged as NB/4 planes of [bin][4 images] (pstride floats apart):
 // with 16-byte bins, lanes that read consecutive bins hit consecutive bank groups.
 template <int NB>
@@ -291,7 +307,8 @@ CTR_HD void ctr_sample(const CtrRay& r, float pu, float pv, float fi, int Up, in
 template <int NB>
 CTR_HD void ctr_ld_rec(const float* __restrict__ p, int swz, float* __restrict__ out)
 {
-    if (NB == 8) ctr_ldv8_swz(p, swz, out);
+    if (NB == 16) ctr_ldv16_rot(p, swz, out);
+    else if (NB == 8) ctr_ldv8_swz(p, swz, out);
     else ctr_ldv<NB>(p, out);
 }
 

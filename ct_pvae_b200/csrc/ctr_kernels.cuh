@@ -222,9 +222,12 @@ struct FwdParams {
 // The vertical-reuse march keeps two register sets of records alive across loop trips: its CTAs are capped at
 // 640 threads so that ptxas may use 96 registers instead of 80 (no spills; 704 threads still get 80: registers
 // are granted per warp in blocks that make 88 x 22 warps overflow the file).
-constexpr int kFwdReuseThreads = 640;
+// 16 images per lane (NB = 16, two lanes per ray; the nearest-neighbour projector): 96 registers, so CTAs of 640
+// threads like the reuse march.
+constexpr int kFwdReuseThreads = 640, kFwdWideThreads = 640;
+__host__ __device__ constexpr int fwd_max_threads(int NB, int REUSE) { return NB == 16 ? kFwdWideThreads : (REUSE ? kFwdReuseThreads : kFwdMaxThreads); }
 template <int NB, int KA, int INTERP, int EPI, int DEPTH, int REUSE = 0>
-__global__ void __launch_bounds__(REUSE ? kFwdReuseThreads : kFwdMaxThreads, 1) ctr_fwd_kernel(const FwdParams p)
+__global__ void __launch_bounds__(fwd_max_threads(NB, REUSE), 1) ctr_fwd_kernel(const FwdParams p)
 {
     constexpr int REC = NB * DEPTH;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -237,7 +240,8 @@ __global__ void __launch_bounds__(REUSE ? kFwdReuseThreads : kFwdMaxThreads, 1) 
     const int tx = (tid - ty * JWD) / DEPTH, gsub = (tid - ty * JWD) % DEPTH;
     // 8 images per lane (32-image records): the two 16-byte halves of a lane's block are read in an order
     // that alternates with the ray's parity, which makes every quarter-warp load conflict-free (ctr_ldv8_swz)
-    const int swz = (NB == 8) ? (tx & 1) * 4 : 0;
+    // 16 images per lane: four loads per record, rotated by the ray's index mod 4 (ctr_ldv16_rot)
+    const int swz = (NB == 16) ? (tx & 3) * 4 : (NB == 8) ? (tx & 1) * 4 : 0;
     const int NA = NS * KA;
 
     const int S = p.stages;                                                 // ring depth (<= 4)
@@ -350,7 +354,7 @@ __global__ void __launch_bounds__(REUSE ? kFwdReuseThreads : kFwdMaxThreads, 1) 
                     s.fi = ri[q];
                     s.n = rn[q];
                     s.dfi = (r.v1 >= 0.f) ? 1.f : -1.f;
-                    if (REUSE && NB == 8 && INTERP == CTR_BILINEAR) ctr_march_reuse<NB, REC>(strip, Us, vend, rbase, offu, r, s, acc[q], swz);
+                    if (REUSE && NB >= 8 && INTERP == CTR_BILINEAR) ctr_march_reuse<NB, REC>(strip, Us, vend, rbase, offu, r, s, acc[q], swz);
                     else ctr_march<NB, INTERP, REC>(strip, Us, vend, rbase, offu, r, s, acc[q], swz);
                     ri[q] = s.fi;
                     rn[q] = s.n;
@@ -374,7 +378,7 @@ __global__ void __launch_bounds__(REUSE ? kFwdReuseThreads : kFwdMaxThreads, 1) 
                 const int ao = p.sel ? rays_s[la].angle : ((EPI && p.amap) ? p.amap[a] : a);
 #pragma unroll
                 for (int n = 0; n < NB; ++n) {
-                    const int b = (g * DEPTH + gsub) * NB + (n ^ swz);   // register n holds image n ^ swz of the lane's block
+                    const int b = (g * DEPTH + gsub) * NB + ctr_img_of_reg<NB>(n, swz);   // the loads are swizzled / rotated
                     if (b < p.B) {
                         float outv = acc[q][n];
                         if (EPI) {
@@ -392,6 +396,20 @@ __global__ void __launch_bounds__(REUSE ? kFwdReuseThreads : kFwdMaxThreads, 1) 
             if (NB == 8 && swz) {   // back to image order before lanes of different parity are combined
 #pragma unroll
                 for (int n = 0; n < 4; ++n) { const float t = lsum[n]; lsum[n] = lsum[n + 4]; lsum[n + 4] = t; }
+            }
+            if (NB == 16) {         // undo the rotation: register n holds image (n + swz) & 15
+                if (swz & 4) {      // rotate up by 4
+#pragma unroll
+                    for (int n = 0; n < 4; ++n) {
+                        const float t = lsum[(12 + n) % NB];
+                        lsum[(12 + n) % NB] = lsum[(8 + n) % NB]; lsum[(8 + n) % NB] = lsum[(4 + n) % NB];
+                        lsum[(4 + n) % NB] = lsum[n % NB]; lsum[n % NB] = t;
+                    }
+                }
+                if (swz & 8) {      // rotate by 8
+#pragma unroll
+                    for (int n = 0; n < 8; ++n) { const float t = lsum[n % NB]; lsum[n % NB] = lsum[(n + 8) % NB]; lsum[(n + 8) % NB] = t; }
+                }
             }
             // warp-level part of the deterministic log-likelihood reduction (lanes of equal gsub)
 #pragma unroll
@@ -1014,6 +1032,51 @@ inline FwdConfig fwd_config_depth(int W, const CtrClassGeom geom[2], int smem_bu
     return c;
 }
 
+// 32-image records read by TWO lanes per ray, 16 images each (rotated loads, ctr_ldv16_rot): the per-sample geometry
+// (coordinates, rounding, address, loop: ~50 instructions) is paid once per 16 images.  Serves the NEAREST-neighbour
+// projector (project_tf_fast's default), whose samples read one record each and are therefore bound by that geometry:
+// r2, 64 x 512^2 x 720: 3.22 -> 2.12 ms, 256 x 128^2 x 180: 0.300 -> 0.264 ms.  The bilinear projector is bound by its
+// four shared-memory records per sample and lost with this shape (5.71 -> 5.76..6.35 ms over NS = 2..12 and CTAs of
+// 384 / 480 / 512 threads: its reuse march needs 156 registers), so it keeps the 8-image lanes.
+// Wide detectors: column-windowed strips with NS angle slots x KA = 2 angles per CTA (sweep at C4: NS 4 / 6 / 8 / 12 /
+// 16 -> 2.25 / 2.17 / 2.12 / 2.15 / 2.15 ms); narrow ones: whole-row strips.
+constexpr int kFwdWideNS = 8;
+inline FwdConfig fwd_config_wide(int W, const CtrClassGeom geom[2], int smem_budget, int win_ns = 0)
+{
+    FwdConfig c{};
+    c.lanes = 2;
+    c.depth = 8;
+    c.stages = kFwdStages;
+    c.KA = 2;
+    c.NS = 1;
+    c.jchunks = 1;
+    const int maxc = kFwdWideThreads - 32;
+    c.JW = round_up(W, 16);
+    if (c.JW * c.lanes > maxc) {
+        c.NS = win_ns > 0 ? win_ns : kFwdWideNS;
+        int q = 16;                                          // JW * NS must be a multiple of 16: whole warps per CTA
+        for (int d = 2; d <= 16; d *= 2) if (c.NS % d == 0) q = 16 / d;
+        c.JW = maxc / (c.lanes * c.NS) / q * q;
+        if (c.JW < q) return c;                              // R = 0: too many angle slots
+        c.jchunks = (W + c.JW - 1) / c.JW;
+        c.JW = round_up((W + c.jchunks - 1) / c.jchunks, q);
+        c.windowed = 1;
+        return c;                                            // R == 0 until the plan has sized the windows
+    }
+    c.reuse = 0;
+    const int fixed = FwdConfig::fixed_bytes(c.NS * c.KA);
+    const int Upmax = geom[0].Up > geom[1].Up ? geom[0].Up : geom[1].Up;
+    const int Vpmax = geom[0].Vp > geom[1].Vp ? geom[0].Vp : geom[1].Vp;
+    const int row_bytes = Upmax * kFwdNB * c.depth * 4;
+    int rows = (smem_budget - fixed) / (c.stages * row_bytes);
+    if (rows > Vpmax) rows = Vpmax;
+    if (rows > 33) rows = 33;
+    c.R = rows - 1;
+    if (c.R < 1) c.R = 0;
+    c.smem = (size_t)fixed + (size_t)c.stages * (size_t)(c.R + 1) * row_bytes;
+    return c;
+}
+
 template <int NBL, int INTERP, int EPI, int LANES, int REUSE>
 inline cudaError_t launch_fwd_one(const FwdParams& p, const FwdConfig& c, dim3 grid, dim3 block, cudaStream_t st)
 {
@@ -1031,6 +1094,8 @@ inline cudaError_t launch_fwd_ka(const FwdParams& p, const FwdConfig& c, int G, 
 {
     dim3 grid(chunks, c.jchunks, G), block(c.JW * c.lanes * c.NS + 32);   // + the producer warp
     if (c.KA != 2) return cudaErrorInvalidValue;
+    if (c.lanes == 2 && c.depth == 8)   // 32-image records, 16 per lane: nearest only (bilinear is bound by shared-memory loads, see fwd_config_wide)
+        return INTERP == CTR_NEAREST ? launch_fwd_one<16, CTR_NEAREST, EPI, 2, 0>(p, c, grid, block, st) : cudaErrorInvalidValue;
     if (c.lanes == 4 && c.depth == 8 && c.reuse && INTERP == CTR_BILINEAR) return launch_fwd_one<8, INTERP, EPI, 4, 1>(p, c, grid, block, st);
     if (c.lanes == 4 && c.depth == 8) return launch_fwd_one<8, INTERP, EPI, 4, 0>(p, c, grid, block, st);   // 32-image records
     if (c.lanes == 4) return launch_fwd_one<kFwdNB, INTERP, EPI, 4, 0>(p, c, grid, block, st);             // 16-image records

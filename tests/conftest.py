@@ -44,6 +44,7 @@ def emu():
     L.emu_forward_depth.argtypes = L.emu_forward.argtypes
     L.emu_forward_rec32.argtypes = L.emu_forward.argtypes
     L.emu_forward_rec32_plain.argtypes = L.emu_forward.argtypes
+    L.emu_forward_wide.argtypes = [f32p, i, i, i, i, i, i, i, f32p, i, i, i, i, f32p]
     L.emu_adjoint.argtypes = [f32p, i, i, i, i, i, i, i, f32p, i, i, i, i, i, i, f32p]
     L.emu_make_transforms.argtypes = [f64p, i, i, i, f32p]
     L.emu_invert_transforms.argtypes = [f32p, i, f32p]

@@ -79,13 +79,13 @@ void forward_impl(const float* img, int B, int X, int Y, int H, int W, int padx,
                 CtrRayState s;
                 ctr_ray_begin(r, cg, j, H, s);
                 float acc[NBL] = {};
-                const int swz = (NBL == 8) ? (j & 1) * 4 : 0;
+                const int swz = (NBL == 16) ? (j & 3) * 4 : (NBL == 8) ? (j & 1) * 4 : 0;
                 for (int k = 0; k < K; ++k) {
                     // the strip buffer the TMA bulk copy would have filled: rows [kR, kR+R+1)
                     const int rows = std::min(R + 1, cg.Vp - k * R);
                     std::vector<float> strip((size_t)(R + 1) * cg.Up * REC, -1e30f);  // poison what is not loaded
                     std::memcpy(strip.data(), pkg + (size_t)k * R * cg.Up * REC, sizeof(float) * rows * cg.Up * REC);
-                    if (REUSE && NBL == 8 && INTERP == CTR_BILINEAR)   // the windowed shape's march for 8-image lanes
+                    if (REUSE && NBL >= 8 && INTERP == CTR_BILINEAR)   // the windowed shape's march for 8/16-image lanes
                         ctr_march_reuse<NBL, REC>(strip.data() + gsub * NBL, cg.Up, (float)((k + 1) * R + cg.offv),
                                                   k * R + cg.offv, cg.offu, r, s, acc, swz);
                     else
@@ -93,7 +93,7 @@ void forward_impl(const float* img, int B, int X, int Y, int H, int W, int padx,
                                                     k * R + cg.offv, cg.offu, r, s, acc, swz);
                 }
                 for (int n = 0; n < NBL; ++n) {
-                    const int b = (g * DEPTH + gsub) * NBL + (n ^ swz);
+                    const int b = (g * DEPTH + gsub) * NBL + ctr_img_of_reg<NBL>(n, swz);
                     if (b < B) sino[((size_t)b * A + r.angle) * W + j] = acc[n];
                 }
             }
@@ -160,23 +160,25 @@ int forward_window_impl(const float* img, int B, int X, int Y, int H, int W, int
                         for (int jj = 0; jj < nb; ++jj)
                             for (int gsub = 0; gsub < DEPTH; ++gsub) {
                                 CtrRayState s = st[(size_t)q * nb + jj];   // the DEPTH lanes of a ray march identically
-                                if (NBL == 8 && INTERP == CTR_BILINEAR)
+                                if (NBL >= 8 && INTERP == CTR_BILINEAR)
                                     ctr_march_reuse<NBL, REC>(strip.data() + gsub * NBL, Us, (float)((k + 1) * R + cg.offv),
                                                               k * R + cg.offv, cg.offu + c0, rays[ch.first + q], s,
-                                                              &acc[((size_t)q * nb + jj) * REC + gsub * NBL], (jj & 1) * 4);
+                                                              &acc[((size_t)q * nb + jj) * REC + gsub * NBL],
+                                                              (NBL == 16) ? (jj & 3) * 4 : (jj & 1) * 4);
                                 else
                                     ctr_march<NBL, INTERP, REC>(strip.data() + gsub * NBL, Us, (float)((k + 1) * R + cg.offv),
                                                                 k * R + cg.offv, cg.offu + c0, rays[ch.first + q], s,
                                                                 &acc[((size_t)q * nb + jj) * REC + gsub * NBL],
-                                                                (NBL == 8) ? (jj & 1) * 4 : 0);
+                                                                (NBL == 16) ? (jj & 3) * 4 : (NBL == 8) ? (jj & 1) * 4 : 0);
                                 if (gsub == DEPTH - 1) st[(size_t)q * nb + jj] = s;
                             }
                 }
                 for (int q = 0; q < ch.cnt; ++q)
                     for (int jj = 0; jj < nb; ++jj)
                         for (int n = 0; n < REC; ++n) {
-                            // register n of lane n / NBL holds image n ^ swz of that lane's block
-                            const int b = g * REC + (n ^ ((NBL == 8) ? (jj & 1) * 4 : 0));
+                            // register n % NBL of lane n / NBL holds image ctr_img_of_reg(n % NBL, swz) of that lane's block
+                            const int swz = (NBL == 16) ? (jj & 3) * 4 : (NBL == 8) ? (jj & 1) * 4 : 0;
+                            const int b = g * REC + (n / NBL) * NBL + ctr_img_of_reg<NBL>(n % NBL, swz);
                             if (b < B) sino[((size_t)b * A + rays[ch.first + q].angle) * W + z * JW + jj] = acc[((size_t)q * nb + jj) * REC + n];
                         }
             }
@@ -284,6 +286,21 @@ int emu_forward_window32(const float* img, int B, int X, int Y, int H, int W, in
 {
     if (interp == CTR_NEAREST) return forward_window_impl<CTR_NEAREST, 4, 8>(img, B, X, Y, H, W, padx, pady, t, A, JW, NA, Rmax, budget, sino);
     return forward_window_impl<CTR_BILINEAR, 4, 8>(img, B, X, Y, H, W, padx, pady, t, A, JW, NA, Rmax, budget, sino);
+}
+
+// 32-image records, two lanes per ray x 16 images with rotated loads (ctr_fwd_kernel<16, 2, ., ., 2>)
+void emu_forward_wide(const float* img, int B, int X, int Y, int H, int W, int padx, int pady, const float* t, int A,
+                      int interp, int R, int reuse, float* sino)
+{
+    if (interp == CTR_NEAREST) forward_impl<CTR_NEAREST, 2, 16>(img, B, X, Y, H, W, padx, pady, t, A, R, sino);
+    else if (reuse) forward_impl<CTR_BILINEAR, 2, 16, true>(img, B, X, Y, H, W, padx, pady, t, A, R, sino);
+    else forward_impl<CTR_BILINEAR, 2, 16, false>(img, B, X, Y, H, W, padx, pady, t, A, R, sino);
+}
+int emu_forward_window_wide(const float* img, int B, int X, int Y, int H, int W, int padx, int pady, const float* t, int A,
+                            int interp, int JW, int NA, int Rmax, int budget, float* sino)
+{
+    if (interp == CTR_NEAREST) return forward_window_impl<CTR_NEAREST, 2, 16>(img, B, X, Y, H, W, padx, pady, t, A, JW, NA, Rmax, budget, sino);
+    return forward_window_impl<CTR_BILINEAR, 2, 16>(img, B, X, Y, H, W, padx, pady, t, A, JW, NA, Rmax, budget, sino);
 }
 
 // column-windowed depth-first strips (16-image records)

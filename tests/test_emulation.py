@@ -25,6 +25,7 @@ CASES = [
     (2, 20, 33, 17, False, 3, 32, 16, 44),
     (4, 64, 64, 24, True, 8, 32, 16, 44),
     (1, 96, 96, 16, True, 32, 32, 16, 44),
+    (41, 12, 10, 7, True, 4, 32, 8, 44),                # two 32-image records: every register slot of the swizzled / rotated lanes
 ]
 
 
@@ -55,6 +56,10 @@ def test_emulated_kernels_match_oracle(emu, orc, B, X, Y, A, pad, R, TW, TH, win
         emu.emu_forward_rec32_plain(P(img), B, X, Y, H, W, padx, pady, P(t), A, interp, R, P(s32p))
         assert np.array_equal(s32p, sd), "32-image records (plain march) differ from 16-image records"
         np.testing.assert_array_equal(sd, s)
+        for reuse in (0, 1):
+            sw = np.full_like(sd, np.nan)
+            emu.emu_forward_wide(P(img), B, X, Y, H, W, padx, pady, P(t), A, interp, R, reuse, P(sw))
+            assert np.array_equal(sw, sd), "32-image records (two lanes per ray, rotated 16-image loads) differ from 16-image records"
         g = np.full((B, X, Y), np.nan, np.float32)
         emu.emu_adjoint(P(y), B, X, Y, H, W, padx, pady, P(t), A, interp, 0, TW, TH, win, P(g))
         assert rel_l2(g, orc.adjoint_exact(y, th, X, Y, pad, interp)) <= 1e-6
@@ -105,6 +110,9 @@ def test_emulated_kernels_property(emu, orc, B, X, Y, pad, R, th, seed):
         emu.emu_forward_rec32_plain(P(img), B, X, Y, H, W, padx, pady, P(t), A, interp, R, P(s32p))
         assert np.array_equal(s32p, sd), "32-image records (plain march) differ from 16-image records"
         np.testing.assert_array_equal(sd, s)
+        sw = np.full_like(sd, np.nan)
+        emu.emu_forward_wide(P(img), B, X, Y, H, W, padx, pady, P(t), A, interp, R, 1, P(sw))
+        assert np.array_equal(sw, sd), "32-image records (two lanes per ray, rotated 16-image loads) differ from 16-image records"
         for mode, table, fn in ((0, t, orc.adjoint_exact), (1, ti, orc.adjoint_tf)):
             g = np.full((B, X, Y), np.nan, np.float32)
             emu.emu_adjoint(P(y), B, X, Y, H, W, padx, pady, P(table), A, interp, mode, 32, 8, 40, P(g))
@@ -121,6 +129,7 @@ WIN_CASES = [
     (2, 80, 48, 20, False, 24, 2, 5, 50000, "even"),
     (2, 64, 64, 11, True, 24, 2, 8, 80000, "random"),       # far-apart angles in one CTA: wide or whole-row windows
     (17, 40, 40, 16, True, 16, 4, 7, 30000, "even"),        # two 16-image records, second one ragged
+    (37, 24, 24, 12, True, 8, 4, 5, 12000, "even"),         # two 32-image records, second one ragged
 ]
 
 
@@ -131,10 +140,10 @@ def test_emulated_windowed_forward_matches_oracle(emu, orc, B, X, Y, A, pad, JW,
     img = rng.random((B, X, Y), dtype=np.float32)
     H, W, padx, pady = orc.frame_of(X, Y, pad)
     t = orc.make_transforms(th, H, W)
-    emu.emu_forward_window.restype = emu.emu_forward_window32.restype = ctypes.c_int
+    emu.emu_forward_window.restype = emu.emu_forward_window32.restype = emu.emu_forward_window_wide.restype = ctypes.c_int
     for interp in (0, 1):
         want = orc.forward(img, th, pad, interp)
-        for fn, bud in ((emu.emu_forward_window, budget), (emu.emu_forward_window32, 2 * budget)):
+        for fn, bud in ((emu.emu_forward_window, budget), (emu.emu_forward_window32, 2 * budget), (emu.emu_forward_window_wide, 2 * budget)):
             s = np.full((B, A, W), np.nan, np.float32)
             nwin = fn(P(img), B, X, Y, H, W, padx, pady, P(t), A, interp, JW, NA, Rmax, bud, P(s))
             assert nwin >= 0, "shape did not fit the budget / rays not covered"

@@ -240,6 +240,23 @@ def test_full_size_forward_matches_oracle(cp, orc, name, B, X, A, interp):
     assert rel_l2(got, orc.forward(img, th, True, IID[interp])) <= TOL
 
 
+@pytest.mark.parametrize("interp", INTERPS)
+def test_c4_angle_block_forward_matches_oracle(cp, orc, interp):
+    """16 neighbouring angles of configs[3]'s 720 (two blocks, one per ray class) x 40 images (a full and a ragged
+    32-image record): the production CTA shapes of C4 with every angle slot filled -- 8-image lanes + reuse march for
+    bilinear, two lanes per ray x 16 images with rotated loads (8 angle slots) for nearest."""
+    from ct_pvae_b200 import _lib
+    rng = np.random.default_rng(33)
+    X, B = 512, 40
+    th = np.concatenate([_theta(720)[100:108], _theta(720)[300:308]])
+    desc = _lib.get_plan(np.asarray(th, np.float64), X, X, True, 0).describe(B)
+    assert "images_per_record=32 windowed=1" in desc and "nearest: images_per_lane=16" in desc, desc
+    img = rng.random((B, X, X), dtype=np.float32)
+    got = cp.project_tf_fast(torch.from_numpy(img).cuda().unsqueeze(-1), th, pad=True, dim=2, integrate_vae=True,
+                             interpolation=interp)[..., 0].cpu().numpy()
+    assert rel_l2(got, orc.forward(img, th, True, IID[interp])) <= TOL
+
+
 @pytest.mark.parametrize("mode", ["exact", "tf_compat"])
 @pytest.mark.parametrize("interp", INTERPS)
 @pytest.mark.parametrize("name,B,X,A", FULL)

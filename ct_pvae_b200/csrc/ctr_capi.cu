@@ -120,6 +120,11 @@ struct ctr_fbp_plan {
     int A = 0, P = 0, x_size = 0, y_size = 0;
     double* d_cs = nullptr;   // [A][2]
     float* d_h = nullptr;     // [P] spatial kernel
+    // ramp filter: the kernel vanishes at every even offset but 0 -> half the taps (ctr_fbp_filter_sparse_kernel)
+    int sparse = 0;
+    float h0 = 0.f;
+    float* d_hs = nullptr;    // [1 + P + kFiltBPTMax] odd taps, doubled
+    int smem_optin = 0;
     int fused_cl = 0, fused_ab = 0;   // cluster size / angle batch of the single-kernel path (0: image too large for it)
     int use_fused = 0;                // ctr_fbp_plan_set_fused
 };
@@ -672,20 +677,37 @@ int ctr_fbp_plan_create(const double* theta, int A, int P, int x_size, int y_siz
     ctr_filter_to_spatial(fr, fi, P, hd.data());
     std::vector<float> hf(P);
     for (int k = 0; k < P; ++k) hf[k] = (float)hd[k];
+    // "ramp" (and the identity filter): real(ifft(filter)) is zero at the even offsets 2, 4, ... up to the rounding of
+    // the transform (measured 3e-17 relative); those taps are dropped and the row filter does half the work
+    std::vector<float> hs;
+    if (P % 2 == 0) {
+        double hmax = 0.0, emax = 0.0;
+        for (int k = 0; k < P; ++k) hmax = std::max(hmax, std::fabs(hd[k]));
+        for (int k = 2; k < P; k += 2) emax = std::max(emax, std::fabs(hd[k]));
+        if (emax <= 1e-12 * hmax) {
+            p->sparse = 1;
+            p->h0 = hf[0];
+            hs.assign((size_t)1 + P + ctr::kFiltBPTMax, 0.f);
+            for (int i = 0; i < P + ctr::kFiltBPTMax; ++i) hs[1 + i] = hf[(2 * i + 1) % P];
+        }
+    }
     DeviceGuard guard(device);
     if (!guard.ok) { int rc = fail_cuda(guard.err, "cudaSetDevice"); delete p; return rc; }
     {
         int smem_optin = 0;
         if (cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) == cudaSuccess)
             ctr::fbp_fused_shape(x_size, y_size, P, smem_optin - 1024, p->fused_cl, p->fused_ab);
+        p->smem_optin = smem_optin;
     }
     cudaError_t e;
     if ((e = cudaMalloc(&p->d_cs, cs.size() * sizeof(double))) != cudaSuccess ||
         (e = cudaMalloc(&p->d_h, hf.size() * sizeof(float))) != cudaSuccess ||
         (e = cudaMemcpy(p->d_cs, cs.data(), cs.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess ||
-        (e = cudaMemcpy(p->d_h, hf.data(), hf.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess) {
+        (e = cudaMemcpy(p->d_h, hf.data(), hf.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (p->sparse && ((e = cudaMalloc(&p->d_hs, hs.size() * sizeof(float))) != cudaSuccess ||
+                       (e = cudaMemcpy(p->d_hs, hs.data(), hs.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess))) {
         int rc = fail_cuda(e, "ctr_fbp_plan_create: table upload");
-        cudaFree(p->d_cs); cudaFree(p->d_h);
+        cudaFree(p->d_cs); cudaFree(p->d_h); cudaFree(p->d_hs);
         delete p;
         return rc;
     }
@@ -697,7 +719,7 @@ int ctr_fbp_plan_destroy(ctr_fbp_plan* p)
 {
     if (!p) return CTR_OK;
     DeviceGuard guard(p->device);
-    cudaFree(p->d_cs); cudaFree(p->d_h);
+    cudaFree(p->d_cs); cudaFree(p->d_h); cudaFree(p->d_hs);
     delete p;
     return CTR_OK;
 }
@@ -732,6 +754,7 @@ static int fbp_impl(const ctr_fbp_plan* p, const float* sino, int A, int A_total
         // single kernel: the filtered rows stay in (distributed) shared memory
         ctr::FbpFusedParams fp{};
         fp.sino = sino; fp.h = p->d_h; fp.cs = p->d_cs; fp.out = recon;
+        fp.hs = p->d_hs; fp.h0 = p->h0; fp.sparse = p->sparse;
         fp.B = B; fp.A = p->A; fp.P = p->P; fp.X = p->x_size; fp.Y = p->y_size; fp.AB = p->fused_ab;
         fp.scale = (float)(M_PI / (2.0 * (double)A_total));
         if (xg) fp.xg = *xg; else fp.xg.nranks = 1;
@@ -741,21 +764,27 @@ static int fbp_impl(const ctr_fbp_plan* p, const float* sino, int A, int A_total
         return CTR_OK;
     }
     const int NBb = ctr::bp_nb_for_batch(B, CTR_ADJ_FBP, p->x_size, p->y_size);
-    const int G = (B + NBb - 1) / NBb;
+    const int NBf = NBb >= 16 ? 16 : 8;                                    // images per row-filter CTA
+    const int G = (B + NBf - 1) / NBf;
     float* spk = (float*)ws;
     {
-        const size_t smem = ((size_t)p->P * (NBb + 2) + 1) * sizeof(float);
-        const int pairs = (p->P + 1) / 2;                                  // two adjacent bins per thread
-        dim3 grid(p->A, G), block(std::min(256, (pairs + 31) / 32 * 32));
         ProfScope prof(CTR_K_FBP_FILTER, st);
-        if (NBb == 16) {
-            CTR_CUDA(cudaFuncSetAttribute(ctr::ctr_fbp_filter_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            ctr::ctr_fbp_filter_kernel<16><<<grid, block, smem, st>>>(sino, p->d_h, B, p->A, p->P, spk);
-        } else if (NBb == 8) {
-            CTR_CUDA(cudaFuncSetAttribute(ctr::ctr_fbp_filter_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            ctr::ctr_fbp_filter_kernel<8><<<grid, block, smem, st>>>(sino, p->d_h, B, p->A, p->P, spk);
+        if (p->sparse) {
+            const cudaError_t e = (NBf == 16)
+                ? ctr::launch_fbp_filter_sparse<16>(sino, p->d_hs, p->h0, B, p->A, p->P, p->smem_optin, NBb, spk, st)
+                : ctr::launch_fbp_filter_sparse<8>(sino, p->d_hs, p->h0, B, p->A, p->P, p->smem_optin, NBb, spk, st);
+            if (e != cudaSuccess) return fail_cuda(e, "ctr_fbp_filter_sparse_kernel launch");
         } else {
-            return fail(CTR_EUNSUPPORTED, "ctr_fbp: unexpected image group size");
+            const size_t smem = ((size_t)p->P * (NBf + 2) + 1) * sizeof(float);
+            const int pairs = (p->P + 1) / 2;                              // two adjacent bins per thread
+            dim3 grid(p->A, G), block(std::min(256, (pairs + 31) / 32 * 32));
+            if (NBf == 16) {
+                CTR_CUDA(cudaFuncSetAttribute(ctr::ctr_fbp_filter_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                ctr::ctr_fbp_filter_kernel<16><<<grid, block, smem, st>>>(sino, p->d_h, B, p->A, p->P, NBb, spk);
+            } else {
+                CTR_CUDA(cudaFuncSetAttribute(ctr::ctr_fbp_filter_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                ctr::ctr_fbp_filter_kernel<8><<<grid, block, smem, st>>>(sino, p->d_h, B, p->A, p->P, NBb, spk);
+            }
         }
         ctr::launch_counter()++;
         CTR_CUDA(cudaGetLastError());

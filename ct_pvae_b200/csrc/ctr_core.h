@@ -496,28 +496,56 @@ CTR_HD void ctr_adj_tf(const float* ti, int H, int W, float px, float py,
     }
 }
 
-// Back-projection stage of iradon (ctvae/fbp_tensorflow.py:52-71): geometry in
-// float64 like the reference, interpolation weights applied in float32.
-//   cs[0]=cos(theta), cs[1]=sin(theta); xpr = row - x_size/2, ypr = col - y_size/2.
-// tfp's constant_extension clamps the fractional index to [0, P-1], so the halo
-// bins of the packed row (packed index = j + 1) are never read here.
-template <int NB>
-CTR_HD void ctr_adj_fbp(const double* cs, int P, double xpr, double ypr,
-                        const float* __restrict__ ywin, int pstride, int jbase_p, float* __restrict__ acc)
+// The two taps of a linear interpolation along the detector: bins base, base + 1 of the staged window.
+struct CtrTap2 {
+    int base;
+    float w0, w1;
+};
+
+// Taps of one pixel for iradon's back-projection (ctvae/fbp_tensorflow.py:52-71): geometry in float64 like the
+// reference, interpolation weights in float32.
+//   cs[0]=cos(theta), cs[1]=sin(theta); xpr = row - x_size/2, ypr = col - y_size/2;
+//   idx = t + P/2 is the fractional bin ((t - x_ref_min)/(x_ref_max - x_ref_min)*(P-1) for the reference's grid).
+// tfp's constant extension clamps idx to [0, P-1] and takes bins (below, below+1) with below <= P-2: idx < 0 gives
+// bins (0, 1) with alpha 0, idx >= P-1 bins (P-2, P-1) with alpha 1 -- applied here to the integer floor and the
+// float32 weight, which is the same thing.  floor() on the device is the 1.5*2^52 trick on the FP64 add pipe (the
+// integer lands in the low word): no FRND / F2I / I2F on the quarter-rate conversion unit (r2: the gather's loop had
+// five of those per pixel-angle).
+CTR_HD CtrTap2 ctr_tap_fbp(const double* cs, int P, double half_p, double xpr, double ypr, int jbase_p)   // half_p = 0.5 * P
 {
     const double tt = ypr * cs[0] - xpr * cs[1];
-    double idx = tt + 0.5 * (double)P;   // (t - x_ref_min)/(x_ref_max - x_ref_min)*(P-1)
-    idx = fmin(fmax(idx, 0.0), (double)(P - 1));
-    double below = floor(idx);
-    double above = fmin(below + 1.0, (double)(P - 1));
-    below = fmax(above - 1.0, 0.0);
-    const float alpha = (float)(idx - below);
+    const double idx = tt + half_p;
+#if defined(__CUDA_ARCH__)
+    const double tm = __dadd_rd(idx, 6755399441055744.0);     // exact floor for |idx| < 2^31
+    int bi = __double2loint(tm);
+    const double below = tm - 6755399441055744.0;
+#else
+    const double below = floor(idx);
+    int bi = (int)below;
+#endif
+    float alpha = (float)(idx - below);
+    if (bi < 0) { bi = 0; alpha = 0.f; }
+    if (bi > P - 2) { bi = P - 2; alpha = 1.f; }
+    if (P < 2) { bi = 0; alpha = 0.f; }                        // a one-bin detector: both taps are bin 0
+    CtrTap2 t;
+    t.base = bi + 1 - jbase_p;
+    t.w0 = 1.f - alpha;
+    t.w1 = alpha;
+    return t;
+}
+
+// Back-projection stage of iradon for one pixel: the two taps of ctr_tap_fbp.  The halo bins of the packed row
+// (packed index = j + 1) are never read here.
+template <int NB>
+CTR_HD void ctr_adj_fbp(const double* cs, int P, double half_p, double xpr, double ypr,
+                        const float* __restrict__ ywin, int pstride, int jbase_p, float* __restrict__ acc)
+{
+    const CtrTap2 t = ctr_tap_fbp(cs, P, half_p, xpr, ypr, jbase_p);
     float yb[NB], ya[NB];
-    ctr_ld_bins<NB>(ywin, pstride, (int)below + 1 - jbase_p, yb);
-    ctr_ld_bins<NB>(ywin, pstride, (int)above + 1 - jbase_p, ya);
-    const float beta = 1.f - alpha;
+    ctr_ld_bins<NB>(ywin, pstride, t.base, yb);
+    ctr_ld_bins<NB>(ywin, pstride, t.base + 1, ya);
 #pragma unroll
-    for (int q = 0; q < NB; ++q) acc[q] = fmaf(alpha, ya[q], fmaf(beta, yb[q], acc[q]));
+    for (int q = 0; q < NB; ++q) acc[q] = fmaf(t.w1, ya[q], fmaf(t.w0, yb[q], acc[q]));
 }
 
 // Measurement log-likelihood of one ray-sum (ctvae/helper_functions.py:359-368):

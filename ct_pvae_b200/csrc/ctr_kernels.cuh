@@ -502,7 +502,7 @@ __global__ void __launch_bounds__(kBpTW * (TH + 1), MINB) ctr_bp_kernel(const Bp
     const int nbatch = (p.A + AB - 1) / AB;
     const float px = (float)(c + p.pady), py = (float)(r + p.padx);
     // FBP pixel coordinates (fbp_tensorflow.py:52-53): x' = row - x_size/2, y' = col - y_size/2
-    const double xpr = (double)r - 0.5 * (double)p.X, ypr = (double)c - 0.5 * (double)p.Y;
+    const double xpr = (double)r - 0.5 * (double)p.X, ypr = (double)c - 0.5 * (double)p.Y, half_w = 0.5 * (double)p.W;
 
     if (tid == 0) {
         mbar_init(&full[0], AB);
@@ -582,7 +582,7 @@ __global__ void __launch_bounds__(kBpTW * (TH + 1), MINB) ctr_bp_kernel(const Bp
             const float* ywin = wins + (size_t)(s * AB + k) * NBP * pstride;
             const int start = jb[s * AB + k];
             if (MODE == CTR_ADJ_FBP) {
-                ctr_adj_fbp<NB>(&css[(s * AB + k) * 2], p.W, xpr, ypr, ywin, pstride, start, acc);
+                ctr_adj_fbp<NB>(&css[(s * AB + k) * 2], p.W, half_w, xpr, ypr, ywin, pstride, start, acc);
             } else {
                 float t[8];
 #pragma unroll
@@ -703,9 +703,19 @@ __global__ void __launch_bounds__(512) ctr_xchg_sum_kernel(const XchgParams p)
 // 72 of its 256 threads had no bin at P = 184: 0.48 -> see DESIGN.md section 4).  k ascending, fmaf(h, s, acc): the
 // same sums, bit for bit, as the fused kernel's filter stage.
 // Output goes straight into the plane-layout sinogram pack K3b reads.
+
+// Row (angle a) of the NB images of filter group g inside a pack whose image groups hold nbg >= NB images (the gather
+// may take 32 images per thread while the filter works on 16): [nbg-group][A][nbg/4 planes][P+2][4].
+template <int NB>
+__device__ __forceinline__ float* filt_dst_row(float* spk, int g, int a, int A, int P, int nbg)
+{
+    const int first = g * NB, grp = first / nbg, plane0 = (first - grp * nbg) / 4;
+    return spk + (((size_t)grp * A + a) * (nbg / 4) + plane0) * (size_t)(P + 2) * 4;
+}
+
 template <int NB>
 __global__ void __launch_bounds__(256) ctr_fbp_filter_kernel(const float* __restrict__ sino, const float* __restrict__ h,
-                                                             int B, int A, int P, float* __restrict__ spk)
+                                                             int B, int A, int P, int nbg, float* __restrict__ spk)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* s = reinterpret_cast<float*>(smem_raw);   // [P][NB]
@@ -718,7 +728,7 @@ __global__ void __launch_bounds__(256) ctr_fbp_filter_kernel(const float* __rest
     }
     for (int m = threadIdx.x; m <= 2 * P; m += blockDim.x) h2[m] = (m < 2 * P) ? __ldg(h + (m >= P ? m - P : m)) : 0.f;
     __syncthreads();
-    float* dst_row = spk + ((size_t)g * A + a) * (NB / 4) * (size_t)(P + 2) * 4;
+    float* dst_row = filt_dst_row<NB>(spk, g, a, A, P, nbg);
     for (int n0 = 2 * threadIdx.x; n0 < P; n0 += 2 * blockDim.x) {
         float a0[NB], a1[NB];
 #pragma unroll
@@ -750,6 +760,156 @@ __global__ void __launch_bounds__(256) ctr_fbp_filter_kernel(const float* __rest
     }
 }
 
+// ---- K3a', the ramp filter.  real(ifft(ramp)) is zero at every even offset except 0 (P even: the detector of
+// pad_phantom always is), so an output bin of parity pn only needs the input bins of the OTHER parity plus its own
+// bin times h[0]: half the multiply-adds of the dense loop above.  The row is staged de-interleaved by parity,
+// s[par][P/2][NB]; a thread owns BPT outputs of ONE parity (n = 2(a0+q)+pn) and a warp is parity-uniform, so per input
+// bin the whole warp reads the same NB values (broadcast LDS.128) and every thread slides its window of odd taps
+// along by one register (one new LDS.32 per step): BPT*NB FFMA per NB/4 + 1 loads.
+//   hs      [1 + P + kFiltBPTMax] odd taps, doubled and shifted by one: hs[1 + i] = h[(2i + 1) mod P], i < P
+//   sum     k ascending over the other parity, fmaf(h, s, acc), then fmaf(h[0], s[n], acc): the fused kernel's filter
+//           stage calls the same routine, so the two paths stay bit-identical.
+constexpr int kFiltBPTMax = 4;
+template <int NBQ, int BPT>
+__device__ __forceinline__ void ctr_filter_sparse_taps(const float* __restrict__ so, const float* __restrict__ ss, int sstride,
+                                                       const float* __restrict__ hs, float h0, int Ph, int a0, int pn,
+                                                       float (&acc)[BPT][NBQ])
+{
+    const float* hp = hs + 1 + (a0 - (1 - pn) + Ph);   // tap of output a0 at k2 = 0; output q uses hp[q - k2]
+    float hr[BPT];
+#pragma unroll
+    for (int q = 0; q < BPT; ++q) {
+        hr[q] = hp[q];
+#pragma unroll
+        for (int n = 0; n < NBQ; ++n) acc[q][n] = 0.f;
+    }
+    for (int k2 = 0; k2 < Ph; ++k2) {
+        float sv[NBQ];
+        ctr_ldv<NBQ>(so + (size_t)k2 * sstride, sv);
+#pragma unroll
+        for (int q = 0; q < BPT; ++q)
+#pragma unroll
+            for (int n = 0; n < NBQ; ++n) acc[q][n] = fmaf(hr[q], sv[n], acc[q][n]);
+#pragma unroll
+        for (int q = BPT - 1; q > 0; --q) hr[q] = hr[q - 1];
+        hr[0] = hp[-k2 - 1];                           // hs[0] is the pad the last step reads
+    }
+#pragma unroll
+    for (int q = 0; q < BPT; ++q) {
+        if (a0 + q >= Ph) continue;
+        float sv[NBQ];
+        ctr_ldv<NBQ>(ss + (size_t)(a0 + q) * sstride, sv);
+#pragma unroll
+        for (int n = 0; n < NBQ; ++n) acc[q][n] = fmaf(h0, sv[n], acc[q][n]);
+    }
+}
+
+// grid (ceil(A / AP), G), block = AP rows x 2 parities x wper warps (<= 256 threads).
+template <int NB, int BPT>
+__global__ void __launch_bounds__(256) ctr_fbp_filter_sparse_kernel(const float* __restrict__ sino, const float* __restrict__ hs,
+                                                                    float h0, int B, int A, int P, int wper, int AP,
+                                                                    int nbg, float* __restrict__ spk)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int Ph = P / 2;
+    float* s = reinterpret_cast<float*>(smem_raw);            // [AP][2][Ph][NB]
+    float* hsm = s + (size_t)AP * P * NB;                      // [1 + P + kFiltBPTMax]
+    const int a_lo = blockIdx.x * AP, g = blockIdx.y, tid = threadIdx.x;
+    // stage the AP rows of the NB images: lanes = (2 neighbouring quads of bins) x (16 images) -- a full 32-byte sector
+    // per image row and warp load, and shared-memory stores with at most 2-way bank conflicts
+    if ((P & 3) == 0 && (reinterpret_cast<uintptr_t>(sino) & 15) == 0) {
+        const int Pq = P / 4;
+        for (int idx = tid; idx < AP * Pq * NB; idx += blockDim.x) {
+            const int n = idx % NB, kq = (idx / NB) % Pq, row = idx / (NB * Pq);
+            const int b = g * NB + n, a = a_lo + row;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (b < B && a < A) v = __ldg(reinterpret_cast<const float4*>(sino + ((size_t)b * A + a) * P) + kq);
+            float* d = s + (size_t)row * P * NB + (size_t)(2 * kq) * NB + n;     // bins 4kq, 4kq+2 -> even[2kq], even[2kq+1]
+            d[0] = v.x; d[NB] = v.z;
+            d[(size_t)Ph * NB] = v.y; d[(size_t)Ph * NB + NB] = v.w;             // bins 4kq+1, 4kq+3 -> odd[2kq], odd[2kq+1]
+        }
+    } else {
+        for (int idx = tid; idx < AP * P * NB; idx += blockDim.x) {
+            const int n = idx % NB, k = (idx / NB) % P, row = idx / (NB * P);
+            const int b = g * NB + n, a = a_lo + row;
+            s[(size_t)row * P * NB + ((size_t)(k & 1) * Ph + (k >> 1)) * NB + n] =
+                (b < B && a < A) ? __ldg(sino + ((size_t)b * A + a) * P + k) : 0.f;
+        }
+    }
+    for (int m = tid; m < 1 + P + kFiltBPTMax; m += blockDim.x) hsm[m] = __ldg(hs + m);
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31;
+    const int row = warp / (2 * wper), pn = (warp / wper) & 1, a0 = ((warp % wper) * 32 + lane) * BPT;
+    const int a = a_lo + row;
+    if (row >= AP || a >= A) return;
+    float* dst_row = filt_dst_row<NB>(spk, g, a, A, P, nbg);
+    if (a0 < Ph) {
+        const float* srow = s + (size_t)row * P * NB;
+        float acc[BPT][NB];
+        ctr_filter_sparse_taps<NB, BPT>(srow + (size_t)(1 - pn) * Ph * NB, srow + (size_t)pn * Ph * NB, NB, hsm, h0, Ph, a0, pn, acc);
+#pragma unroll
+        for (int q = 0; q < BPT; ++q) {
+            if (a0 + q >= Ph) continue;
+            const int n0 = 2 * (a0 + q) + pn;
+#pragma unroll
+            for (int h = 0; h < NB / 4; ++h)
+                *reinterpret_cast<float4*>(dst_row + ((size_t)h * (P + 2) + n0 + 1) * 4) =
+                    make_float4(acc[q][4 * h], acc[q][4 * h + 1], acc[q][4 * h + 2], acc[q][4 * h + 3]);
+        }
+    }
+    if ((warp % (2 * wper)) == 0 && lane < 2 * (NB / 4)) {  // halo bins (never read by the FBP gather; keep them defined)
+        const int h = lane >> 1;
+        *reinterpret_cast<float4*>(dst_row + ((size_t)h * (P + 2) + ((lane & 1) ? P + 1 : 0)) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+// launch shape of the ramp filter: outputs per thread (fewest idle lanes, then fewest accumulators), warps per parity,
+// rows per CTA (as many as fit 256 threads and half the shared memory)
+struct FiltShape { int bpt, wper, ap; size_t smem; };
+inline FiltShape fbp_filter_sparse_shape(int P, int NB, int A, int smem_optin)
+{
+    FiltShape f{2, 1, 1, 0};
+    const int Ph = P / 2;
+    int best = 1 << 30;
+    for (int bpt : {3, 2, 4}) {
+        if (bpt * NB > 48) continue;                                  // accumulators per thread
+        const int tasks = (Ph + bpt - 1) / bpt, wp = (tasks + 31) / 32;
+        if (2 * wp * 32 > 256) continue;
+        const int idle = wp * 32 * bpt - Ph;
+        if (idle < best) { best = idle; f.bpt = bpt; f.wper = wp; }
+    }
+    auto bytes = [&](int ap) { return ((size_t)ap * P * NB + 1 + P + kFiltBPTMax) * sizeof(float); };
+    f.ap = 256 / (2 * f.wper * 32);
+    if (f.ap < 1) f.ap = 1;
+    while (f.ap > 1 && (bytes(f.ap) > (size_t)smem_optin / 2 || f.ap > A)) --f.ap;
+    f.smem = bytes(f.ap);
+    return f;
+}
+
+template <int NB>
+inline cudaError_t launch_fbp_filter_sparse(const float* sino, const float* hs, float h0, int B, int A, int P, int smem_optin,
+                                            int nbg, float* spk, cudaStream_t st)
+{
+    const FiltShape f = fbp_filter_sparse_shape(P, NB, A, smem_optin);
+    const int G = (B + NB - 1) / NB;
+    dim3 grid((A + f.ap - 1) / f.ap, G), block(f.ap * 2 * f.wper * 32);
+    cudaError_t e = cudaSuccess;
+#define CTR_FILT_CASE(BPT)                                                                                                     \
+    case BPT:                                                                                                                  \
+        e = cudaFuncSetAttribute(ctr_fbp_filter_sparse_kernel<NB, BPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f.smem); \
+        if (e != cudaSuccess) return e;                                                                                        \
+        ctr_fbp_filter_sparse_kernel<NB, BPT><<<grid, block, f.smem, st>>>(sino, hs, h0, B, A, P, f.wper, f.ap, nbg, spk);          \
+        break;
+    switch (f.bpt) {
+        CTR_FILT_CASE(2)
+        CTR_FILT_CASE(3)
+        CTR_FILT_CASE(4)
+        default: return cudaErrorInvalidValue;
+    }
+#undef CTR_FILT_CASE
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------ K3 fused FBP
 // iradon in ONE kernel (fbp_tensorflow.py:49-74): the circular row filter runs in shared memory and its output never
 // leaves the chip.  A thread-block CLUSTER of CL CTAs serves one group of 16 sinograms:
@@ -766,6 +926,9 @@ constexpr int kFusedNB = 16, kFusedPPT = 4, kFusedThreads = 512, kFusedPxPerCta 
 struct FbpFusedParams {
     const float* sino;     // [B][A][P]
     const float* h;        // [P] spatial kernel real(ifft(filter_1d))
+    const float* hs;       // ramp filter (sparse != 0): the odd taps, doubled (see ctr_filter_sparse_taps), and h[0]
+    float h0;
+    int sparse;
     const double* cs;      // [A][2] cos / sin(theta)
     float* out;            // [B][X][Y]
     int B, A, P, X, Y;
@@ -791,7 +954,7 @@ __device__ __forceinline__ void st_cluster_f4(const void* local, uint32_t rank, 
 __host__ __device__ inline size_t fbp_fused_smem(int P, int AB, int CL)
 {
     const int quads = (AB * (kFusedNB / 4) + CL - 1) / CL;                  // row quads a CTA filters per batch
-    return 2ull * AB * (kFusedNB / 4) * P * 16 + (size_t)quads * P * 16 + 2ull * P * 4 + 16;
+    return 2ull * AB * (kFusedNB / 4) * P * 16 + (size_t)quads * P * 16 + 2ull * P * 4 + 16 + 4 * (1 + kFiltBPTMax);
 }
 
 __global__ void __launch_bounds__(kFusedThreads, 1) ctr_fbp_fused_kernel(const FbpFusedParams p)
@@ -805,8 +968,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1) ctr_fbp_fused_kernel(const F
     float* filt = reinterpret_cast<float*>(smem_raw);                        // [2][AB][NBP][P][4]
     const int stage_floats = AB * NBP * P * 4;
     float* raw = filt + 2 * stage_floats;                                    // [quads][P][4]
-    float* h2 = raw + quads * P * 4;                                         // [2P]
-    for (int m = tid; m < 2 * P; m += kFusedThreads) h2[m] = __ldg(p.h + (m >= P ? m - P : m));
+    float* h2 = raw + quads * P * 4;                                         // [2P], or [1 + P + kFiltBPTMax] odd taps (ramp)
+    if (p.sparse) for (int m = tid; m < 1 + P + kFiltBPTMax; m += kFusedThreads) h2[m] = __ldg(p.hs + m);
+    else for (int m = tid; m < 2 * P; m += kFusedThreads) h2[m] = __ldg(p.h + (m >= P ? m - P : m));
+    const int Ph = P / 2, nbp = (Ph + 1) / 2;                                // ramp: pair tasks per parity
 
     // this thread's pixels (consecutive lanes = consecutive pixels of a row: neighbouring bins in the gather)
     const int npix = p.X * p.Y, per = (npix + CL - 1) / CL;
@@ -823,18 +988,37 @@ __global__ void __launch_bounds__(kFusedThreads, 1) ctr_fbp_fused_kernel(const F
         for (int n = 0; n < NB; ++n) acc[i][n] = 0.f;
     }
     const int nbatch = (p.A + AB - 1) / AB;
+    const double half_p = 0.5 * (double)P;
     const int nb2 = (P + 1) / 2;                                             // filter tasks per quad: 2 bins each
 
     auto filter_batch = [&](int b) {
         float* dst = filt + (b & 1) * stage_floats;
         // raw rows of this CTA's quads: quad t = (angle k = t / NBP, plane h = t % NBP), t = q + CL * ql
+        // (ramp filter: de-interleaved by bin parity, [ql][parity][P/2][4])
         for (int idx = tid; idx < quads * 4 * P; idx += kFusedThreads) {
             const int kk = idx % P, n4 = (idx / P) & 3, ql = idx / (4 * P);
             const int t = q + CL * ql, k = t / NBP, hpl = t - k * NBP;
             const int a = b * AB + k, bimg = g * NB + 4 * hpl + n4;
-            raw[(ql * P + kk) * 4 + n4] = (t < AB * NBP && a < p.A && bimg < p.B) ? __ldg(p.sino + ((size_t)bimg * p.A + a) * P + kk) : 0.f;
+            const int slot = p.sparse ? (kk & 1) * Ph + (kk >> 1) : kk;
+            raw[(ql * P + slot) * 4 + n4] = (t < AB * NBP && a < p.A && bimg < p.B) ? __ldg(p.sino + ((size_t)bimg * p.A + a) * P + kk) : 0.f;
         }
         __syncthreads();
+        if (p.sparse) {
+            for (int task = tid; task < quads * 2 * nbp; task += kFusedThreads) {
+                const int ql = task / (2 * nbp), rem = task - ql * 2 * nbp, pn = rem / nbp, a0 = (rem - pn * nbp) * 2;
+                const int t = q + CL * ql, k = t / NBP, hpl = t - k * NBP;
+                if (t >= AB * NBP || b * AB + k >= p.A) continue;
+                const float* sq = raw + (size_t)ql * P * 4;
+                float acc[2][4];
+                ctr_filter_sparse_taps<4, 2>(sq + (size_t)(1 - pn) * Ph * 4, sq + (size_t)pn * Ph * 4, 4, h2, p.h0, Ph, a0, pn, acc);
+                float* d0 = dst + ((size_t)(k * NBP + hpl) * P + 2 * a0 + pn) * 4;
+                for (int r = 0; r < CL; ++r) {
+                    st_cluster_f4(d0, (uint32_t)r, make_float4(acc[0][0], acc[0][1], acc[0][2], acc[0][3]));
+                    if (a0 + 1 < Ph) st_cluster_f4(d0 + 8, (uint32_t)r, make_float4(acc[1][0], acc[1][1], acc[1][2], acc[1][3]));
+                }
+            }
+            return;
+        }
         for (int task = tid; task < quads * nb2; task += kFusedThreads) {
             const int ql = task / nb2, n0 = (task - ql * nb2) * 2;
             const int t = q + CL * ql, k = t / NBP, hpl = t - k * NBP;
@@ -872,7 +1056,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) ctr_fbp_fused_kernel(const F
             cs[1] = __ldg(p.cs + 2 * (b * AB + k) + 1);
             const float* ywin = src + (size_t)k * NBP * P * 4;
 #pragma unroll
-            for (int i = 0; i < PPT; ++i) ctr_adj_fbp<NB>(cs, P, xpr[i], ypr[i], ywin, P * 4, 1, acc[i]);
+            for (int i = 0; i < PPT; ++i) ctr_adj_fbp<NB>(cs, P, half_p, xpr[i], ypr[i], ywin, P * 4, 1, acc[i]);
         }
         cluster_sync_all();                            // F(b+1) has landed everywhere; BP(b) has finished everywhere
     }
@@ -1120,11 +1304,11 @@ inline size_t bp_smem_bytes(int win, int NB, int AB)
 inline int bp_nb_for_batch(int B, int mode, int X = 0, int Y = 0)
 {
     if (B <= 8) return 8;
-    // FBP stays at 16: with 32 the gather gains 5 % but the row filter (64 accumulators per thread) loses 38 %
-    // (r2, 1000 x 128^2 x 180: 1.31 vs 1.20 ms per pass; 64 x 512^2 x 720: no change)
-    if (B < 24 || mode == CTR_ADJ_FBP) return 16;
+    if (B < 24) return 16;
     const long long ctas32 = (X > 0 && Y > 0) ? (long long)((Y + kBpTW - 1) / kBpTW) * ((X + 7) / 8) * ((B + 31) / 32) : -1;
-    if (mode == CTR_ADJ_TF)   // 2-tap gather: 32 images only pay on grids of several waves (C4 3.15 -> 2.90 ms; C2 unchanged)
+    // 2-tap gathers (TF-compat gradient, FBP): 32 images only pay on grids of several waves (TF-compat C4 3.15 -> 2.90 ms,
+    // C2 unchanged).  The FBP row filter always works on 16 images and writes into the gather's groups (filt_dst_row).
+    if (mode == CTR_ADJ_TF || mode == CTR_ADJ_FBP)
         return ctas32 >= 1024 ? 32 : 16;
     if (ctas32 >= 0 && ctas32 < 148) return 16;
     return 32;

@@ -124,7 +124,6 @@ struct ctr_fbp_plan {
     int sparse = 0;
     float h0 = 0.f;
     float* d_hs = nullptr;    // [1 + P + kFiltBPTMax] odd taps, doubled
-    int smem_optin = 0;
     int fused_cl = 0, fused_ab = 0;   // cluster size / angle batch of the single-kernel path (0: image too large for it)
     int use_fused = 0;                // ctr_fbp_plan_set_fused
 };
@@ -697,7 +696,6 @@ int ctr_fbp_plan_create(const double* theta, int A, int P, int x_size, int y_siz
         int smem_optin = 0;
         if (cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) == cudaSuccess)
             ctr::fbp_fused_shape(x_size, y_size, P, smem_optin - 1024, p->fused_cl, p->fused_ab);
-        p->smem_optin = smem_optin;
     }
     cudaError_t e;
     if ((e = cudaMalloc(&p->d_cs, cs.size() * sizeof(double))) != cudaSuccess ||
@@ -771,8 +769,8 @@ static int fbp_impl(const ctr_fbp_plan* p, const float* sino, int A, int A_total
         ProfScope prof(CTR_K_FBP_FILTER, st);
         if (p->sparse) {
             const cudaError_t e = (NBf == 16)
-                ? ctr::launch_fbp_filter_sparse<16>(sino, p->d_hs, p->h0, B, p->A, p->P, p->smem_optin, NBb, spk, st)
-                : ctr::launch_fbp_filter_sparse<8>(sino, p->d_hs, p->h0, B, p->A, p->P, p->smem_optin, NBb, spk, st);
+                ? ctr::launch_fbp_filter_sparse<16>(sino, p->d_hs, p->h0, B, p->A, p->P, NBb, spk, st)
+                : ctr::launch_fbp_filter_sparse<8>(sino, p->d_hs, p->h0, B, p->A, p->P, NBb, spk, st);
             if (e != cudaSuccess) return fail_cuda(e, "ctr_fbp_filter_sparse_kernel launch");
         } else {
             const size_t smem = ((size_t)p->P * (NBf + 2) + 1) * sizeof(float);

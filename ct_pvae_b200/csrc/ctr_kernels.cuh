@@ -804,49 +804,47 @@ __device__ __forceinline__ void ctr_filter_sparse_taps(const float* __restrict__
     }
 }
 
-// grid (ceil(A / AP), G), block = AP rows x 2 parities x wper warps (<= 256 threads).
+// grid (A, G), block = 2 parities x wper warps (<= 256 threads): one sinogram row of NB images per CTA.  (Several rows
+// per CTA were measured and lost -- C5, 1000 x 180 rows of 184 bins: 4 rows 0.265 ms, 2 rows 0.228, 1 row 0.208: small
+// CTAs overlap one CTA's global loads with another's multiply-adds.)
 template <int NB, int BPT>
 __global__ void __launch_bounds__(256) ctr_fbp_filter_sparse_kernel(const float* __restrict__ sino, const float* __restrict__ hs,
-                                                                    float h0, int B, int A, int P, int wper, int AP,
-                                                                    int nbg, float* __restrict__ spk)
+                                                                    float h0, int B, int A, int P, int wper, int nbg,
+                                                                    float* __restrict__ spk)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int Ph = P / 2;
-    float* s = reinterpret_cast<float*>(smem_raw);            // [AP][2][Ph][NB]
-    float* hsm = s + (size_t)AP * P * NB;                      // [1 + P + kFiltBPTMax]
-    const int a_lo = blockIdx.x * AP, g = blockIdx.y, tid = threadIdx.x;
-    // stage the AP rows of the NB images: lanes = (2 neighbouring quads of bins) x (16 images) -- a full 32-byte sector
+    float* s = reinterpret_cast<float*>(smem_raw);            // [2][Ph][NB]
+    float* hsm = s + (size_t)P * NB;                           // [1 + P + kFiltBPTMax]
+    const int a = blockIdx.x, g = blockIdx.y, tid = threadIdx.x;
+    // stage the row of the NB images: lanes = (2 neighbouring quads of bins) x (16 images) -- a full 32-byte sector
     // per image row and warp load, and shared-memory stores with at most 2-way bank conflicts
     if ((P & 3) == 0 && (reinterpret_cast<uintptr_t>(sino) & 15) == 0) {
         const int Pq = P / 4;
-        for (int idx = tid; idx < AP * Pq * NB; idx += blockDim.x) {
-            const int n = idx % NB, kq = (idx / NB) % Pq, row = idx / (NB * Pq);
-            const int b = g * NB + n, a = a_lo + row;
+        for (int idx = tid; idx < Pq * NB; idx += blockDim.x) {
+            const int n = idx % NB, kq = idx / NB;
+            const int b = g * NB + n;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (b < B && a < A) v = __ldg(reinterpret_cast<const float4*>(sino + ((size_t)b * A + a) * P) + kq);
-            float* d = s + (size_t)row * P * NB + (size_t)(2 * kq) * NB + n;     // bins 4kq, 4kq+2 -> even[2kq], even[2kq+1]
+            if (b < B) v = __ldg(reinterpret_cast<const float4*>(sino + ((size_t)b * A + a) * P) + kq);
+            float* d = s + (size_t)(2 * kq) * NB + n;                            // bins 4kq, 4kq+2 -> even[2kq], even[2kq+1]
             d[0] = v.x; d[NB] = v.z;
             d[(size_t)Ph * NB] = v.y; d[(size_t)Ph * NB + NB] = v.w;             // bins 4kq+1, 4kq+3 -> odd[2kq], odd[2kq+1]
         }
     } else {
-        for (int idx = tid; idx < AP * P * NB; idx += blockDim.x) {
-            const int n = idx % NB, k = (idx / NB) % P, row = idx / (NB * P);
-            const int b = g * NB + n, a = a_lo + row;
-            s[(size_t)row * P * NB + ((size_t)(k & 1) * Ph + (k >> 1)) * NB + n] =
-                (b < B && a < A) ? __ldg(sino + ((size_t)b * A + a) * P + k) : 0.f;
+        for (int idx = tid; idx < P * NB; idx += blockDim.x) {
+            const int n = idx % NB, k = idx / NB;
+            const int b = g * NB + n;
+            s[((size_t)(k & 1) * Ph + (k >> 1)) * NB + n] = (b < B) ? __ldg(sino + ((size_t)b * A + a) * P + k) : 0.f;
         }
     }
     for (int m = tid; m < 1 + P + kFiltBPTMax; m += blockDim.x) hsm[m] = __ldg(hs + m);
     __syncthreads();
     const int warp = tid >> 5, lane = tid & 31;
-    const int row = warp / (2 * wper), pn = (warp / wper) & 1, a0 = ((warp % wper) * 32 + lane) * BPT;
-    const int a = a_lo + row;
-    if (row >= AP || a >= A) return;
+    const int pn = warp / wper, a0 = ((warp % wper) * 32 + lane) * BPT;
     float* dst_row = filt_dst_row<NB>(spk, g, a, A, P, nbg);
     if (a0 < Ph) {
-        const float* srow = s + (size_t)row * P * NB;
         float acc[BPT][NB];
-        ctr_filter_sparse_taps<NB, BPT>(srow + (size_t)(1 - pn) * Ph * NB, srow + (size_t)pn * Ph * NB, NB, hsm, h0, Ph, a0, pn, acc);
+        ctr_filter_sparse_taps<NB, BPT>(s + (size_t)(1 - pn) * Ph * NB, s + (size_t)pn * Ph * NB, NB, hsm, h0, Ph, a0, pn, acc);
 #pragma unroll
         for (int q = 0; q < BPT; ++q) {
             if (a0 + q >= Ph) continue;
@@ -857,18 +855,17 @@ __global__ void __launch_bounds__(256) ctr_fbp_filter_sparse_kernel(const float*
                     make_float4(acc[q][4 * h], acc[q][4 * h + 1], acc[q][4 * h + 2], acc[q][4 * h + 3]);
         }
     }
-    if ((warp % (2 * wper)) == 0 && lane < 2 * (NB / 4)) {  // halo bins (never read by the FBP gather; keep them defined)
+    if (warp == 0 && lane < 2 * (NB / 4)) {  // halo bins (never read by the FBP gather; keep them defined)
         const int h = lane >> 1;
         *reinterpret_cast<float4*>(dst_row + ((size_t)h * (P + 2) + ((lane & 1) ? P + 1 : 0)) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
 
-// launch shape of the ramp filter: outputs per thread (fewest idle lanes, then fewest accumulators), warps per parity,
-// rows per CTA (as many as fit 256 threads and half the shared memory)
-struct FiltShape { int bpt, wper, ap; size_t smem; };
-inline FiltShape fbp_filter_sparse_shape(int P, int NB, int A, int smem_optin)
+// launch shape of the ramp filter: outputs per thread (fewest idle lanes, then fewest accumulators) and warps per parity
+struct FiltShape { int bpt, wper; size_t smem; };
+inline FiltShape fbp_filter_sparse_shape(int P, int NB)
 {
-    FiltShape f{2, 1, 1, 0};
+    FiltShape f{2, 1, 0};
     const int Ph = P / 2;
     int best = 1 << 30;
     for (int bpt : {3, 2, 4}) {
@@ -878,27 +875,23 @@ inline FiltShape fbp_filter_sparse_shape(int P, int NB, int A, int smem_optin)
         const int idle = wp * 32 * bpt - Ph;
         if (idle < best) { best = idle; f.bpt = bpt; f.wper = wp; }
     }
-    auto bytes = [&](int ap) { return ((size_t)ap * P * NB + 1 + P + kFiltBPTMax) * sizeof(float); };
-    f.ap = 256 / (2 * f.wper * 32);
-    if (f.ap < 1) f.ap = 1;
-    while (f.ap > 1 && (bytes(f.ap) > (size_t)smem_optin / 2 || f.ap > A)) --f.ap;
-    f.smem = bytes(f.ap);
+    f.smem = ((size_t)P * NB + 1 + P + kFiltBPTMax) * sizeof(float);
     return f;
 }
 
 template <int NB>
-inline cudaError_t launch_fbp_filter_sparse(const float* sino, const float* hs, float h0, int B, int A, int P, int smem_optin,
-                                            int nbg, float* spk, cudaStream_t st)
+inline cudaError_t launch_fbp_filter_sparse(const float* sino, const float* hs, float h0, int B, int A, int P, int nbg, float* spk,
+                                            cudaStream_t st)
 {
-    const FiltShape f = fbp_filter_sparse_shape(P, NB, A, smem_optin);
+    const FiltShape f = fbp_filter_sparse_shape(P, NB);
     const int G = (B + NB - 1) / NB;
-    dim3 grid((A + f.ap - 1) / f.ap, G), block(f.ap * 2 * f.wper * 32);
+    dim3 grid(A, G), block(2 * f.wper * 32);
     cudaError_t e = cudaSuccess;
 #define CTR_FILT_CASE(BPT)                                                                                                     \
     case BPT:                                                                                                                  \
         e = cudaFuncSetAttribute(ctr_fbp_filter_sparse_kernel<NB, BPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f.smem); \
         if (e != cudaSuccess) return e;                                                                                        \
-        ctr_fbp_filter_sparse_kernel<NB, BPT><<<grid, block, f.smem, st>>>(sino, hs, h0, B, A, P, f.wper, f.ap, nbg, spk);          \
+        ctr_fbp_filter_sparse_kernel<NB, BPT><<<grid, block, f.smem, st>>>(sino, hs, h0, B, A, P, f.wper, nbg, spk);           \
         break;
     switch (f.bpt) {
         CTR_FILT_CASE(2)

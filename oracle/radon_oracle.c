@@ -5,7 +5,7 @@
  * execute this file; it is the checker for tests/, __graft_entry__.smoke() and
  * the cpu_baseline / --impl reference legs of bench.py.
  *
- * PARITY UNPINNED: the reference (vganapati/CT_PVAE) ships no tests, golden
+ * PARITY PARTLY PINNED: the reference (vganapati/CT_PVAE) ships no tests, golden
  * vectors or fixtures for this path, and its arithmetic lives in third-party
  * packages that are neither vendored nor installable here:
  *   tensorflow-addons==0.17.1  tfa.image.rotate / angles_to_projective_transforms
@@ -17,7 +17,12 @@
  *   ctvae/forward_functions.py:49-78   project_tf_low_mem   -> orc_forward with interp=1
  *   ctvae/main_ct_vae.py:471-481       tape.gradient        -> orc_adjoint_tf (TF's registered gradient)
  *   (north_star)                       exact transpose      -> orc_adjoint_exact
- * Known answers that do pin it (tests/test_oracle.py): the toy dataset's closed
+ * The rotation is pinned by the known-answer vectors of tensorflow-addons' OWN test
+ * suite (transform_ops_test.py::test_rotate_even / test_rotate_odd / test_bilinear,
+ * transcribed in tests/test_tfa_known_answers.py): nearest exactly, bilinear to the
+ * 1e-3 that test asserts.  Still UNPINNED: last-ulp behaviour of the bilinear kernel,
+ * TF's registered gradient, tfp's interp_regular_1d_grid.
+ * Further known answers (tests/test_oracle.py): the toy dataset's closed
  * form sinograms (scripts/images_to_sinograms.py:54-59), theta=0 column sums,
  * mass conservation, and an independent bilinear implementation
  * (torch grid_sample, align_corners=True, zeros padding).

@@ -4,11 +4,14 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline /
 ``--impl reference`` legs may import this module.  Nothing under ``ct_pvae_b200/``
 does, and the product path has no CPU fallback.
 
-PARITY UNPINNED: the reference ships no tests or golden vectors for this path and
+PARITY PARTLY PINNED: the reference ships no tests or golden vectors for this path and
 TensorFlow / tensorflow-addons / tensorflow-probability are not installable here, so
 the third-party arithmetic (tfa 0.17.1 ``rotate``, TF 2.8.1
 ``ImageProjectiveTransformV3`` and its gradient, tfp 0.14 ``interp_regular_1d_grid``)
-is restated from their published algorithms.  What pins it: the toy dataset's closed
+is restated from their published algorithms.  The rotation is pinned by tensorflow-addons'
+own known-answer tests (``test_rotate_even`` / ``test_rotate_odd`` / ``test_bilinear``, transcribed in
+``tests/test_tfa_known_answers.py``): nearest exactly, bilinear to that test's 1e-3; TF's gradient and
+tfp's interpolation stay UNPINNED.  Further anchors: the toy dataset's closed
 form sinograms (reference ``scripts/images_to_sinograms.py:54-59``), theta=0 column
 sums, mass conservation, the explicit sparse matrix, and an independent bilinear
 implementation (``torch.nn.functional.grid_sample``) -- see ``tests/test_oracle.py``.

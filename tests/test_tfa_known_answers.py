@@ -91,8 +91,11 @@ def test_oracle_projector_reproduces_the_known_answers(orc, name, image, angles,
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,image,angles,want,interp,atol", CASES, ids=[c[0] for c in CASES])
-def test_cuda_projector_reproduces_the_known_answers(cp, name, image, angles, want, interp, atol):
+def test_cuda_projector_reproduces_the_known_answers(name, image, angles, want, interp, atol):
     import torch
+
+    import ct_pvae_b200 as cp
+    assert torch.cuda.is_available()
     theta = -angles.astype(np.float64)
     x = torch.from_numpy(image[None, :, :, None]).cuda()
     got = cp.project_tf_fast(x, theta, pad=False, dim=2, integrate_vae=True, interpolation=interp)[0, ..., 0].cpu().numpy()

@@ -495,7 +495,11 @@ def smem_rooflines(rec, wl, A_loc, clocks):
     B, X = wl["B"], wl["X"]
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
     peak, src = measured_smem_peak(sm_mhz)
-    out = {"peak_GBs": peak, "peak_source": src}
+    out = {"peak_GBs": peak, "peak_source": src,
+           "note": "achieved = ALGORITHMIC shared-memory bytes (forward: 16 B per in-support bilinear sample-image, adjoint: 12 B per "
+                   "update-image) / kernel time.  The forward's vertical-reuse march actually loads ~13 B per sample-image on "
+                   "windowed shapes, so its pipe utilisation by ncu is lower than frac (C4: 77 %, profiles/r2_ncu_fwd_c4_summary.txt); "
+                   "the adjoint's loads equal the algorithmic bytes (ncu 92.6 %)."}
     fwd = rec["kernels"].get("ctr_fwd_kernel", {}).get("ms_per_launch")
     adj = rec["kernels"].get("ctr_bp_kernel<exact>", {}).get("ms_per_launch")
     if fwd:

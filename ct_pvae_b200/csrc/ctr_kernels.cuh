@@ -8,8 +8,10 @@
 //                               the fused measurement log-likelihood epilogue (helper_functions.py:355-368)
 //   K2  ctr_bp_kernel<EXACT>    pixel-driven gather adjoint, the exact transpose of K1 (no atomics)
 //   K2' ctr_bp_kernel<TF>       TensorFlow's registered gradient of the projector graph
-//   K3a ctr_fbp_filter_kernel   circular row filter in shared memory (fbp_tensorflow.py:49-50)
+//   K3a ctr_fbp_filter_kernel   circular row filter in shared memory (fbp_tensorflow.py:49-50); the ramp filter's
+//       ctr_fbp_filter_sparse_kernel  kernel vanishes at the even offsets: odd taps only, parity-split rows
 //   K3b ctr_bp_kernel<FBP>      linear-interpolating back-projection of iradon (fbp_tensorflow.py:52-74)
+//   K3  ctr_fbp_fused_kernel    iradon as one thread-block-cluster kernel (opt-in)
 //
 // Data movement: image strips (K1) and sinogram bin windows (K2/K3b) are staged in
 // shared memory by the TMA engine with 1-D bulk copies (cp.async.bulk, SASS UBLKCP)
@@ -19,9 +21,10 @@
 // 16-byte aligned range in HBM (whole packed rows, or -- wide detectors -- the column
 // window of every row that the CTA's rays cross) and so that one 128-bit shared-memory
 // load serves 4 images: the per-sample geometry (coordinates, floor, weights, address)
-// is computed once per 4 or 8 (K1) or 16-32 (K2) images.  K1's big-batch shape reads
+// is computed once per 4, 8 or 16 (K1) or 16-32 (K2) images.  K1's big-batch shape reads
 // 32-image records with parity-swizzled 8-image lanes (conflict-free quarter-warps) and,
-// with tall windowed strips, keeps the previous sample's bottom row in registers.
+// with tall windowed strips, keeps the previous sample's bottom row in registers; the
+// nearest-neighbour projector reads them with two lanes per ray x 16 images (rotated loads).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

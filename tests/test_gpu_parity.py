@@ -276,8 +276,12 @@ def test_full_size_adjoint_matches_oracle(cp, orc, name, B, X, A, interp, mode):
 
 def test_fbp_matches_oracle(cp, orc):
     rng = np.random.default_rng(6)
+    # ramp / None: odd-tap row filter (P = 256 with 5 images: four outputs per thread, 8-image groups; P = 184 with 40
+    # images: three outputs per thread; 500 images: 16-image filter groups inside the gather's 32-image groups, last one ragged)
     for (B, A, P, xs, ys, name) in [(3, 20, 46, 30, 30, "ramp"), (9, 45, 184, 128, 128, "hann"),
-                                    (2, 12, 50, 33, 21, None), (1, 7, 24, 16, 16, "shepp-logan")]:
+                                    (2, 12, 50, 33, 21, None), (1, 7, 24, 16, 16, "shepp-logan"),
+                                    (5, 9, 256, 179, 179, "ramp"), (40, 11, 184, 128, 128, "ramp"),
+                                    (500, 4, 184, 128, 128, "ramp")]:   # >= 1024 gather CTAs: 32 images per gather thread
         th = _theta(A)
         sino = rng.random((B, A, P))
         filt = orc.get_fourier_filter(P, name)

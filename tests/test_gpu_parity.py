@@ -294,6 +294,23 @@ def test_fbp_matches_oracle(cp, orc):
         cp.iradon(torch.zeros((1, 5, 16), device="cuda"), _theta(4), 8, 8, np.ones(16))
 
 
+@pytest.mark.parametrize("seed", range(10))
+def test_fbp_random_shapes(cp, orc, seed):
+    """iradon on random detector widths (even and odd: odd-tap and dense row filters, float4 and scalar staging), batch
+    sizes (8 / 16-image filter groups, ragged), image sizes and angle sets, every filter, against the float64 oracle."""
+    rng = np.random.default_rng(700 + seed)
+    B, A = int(rng.integers(1, 45)), int(rng.integers(1, 25))
+    xs, ys = int(rng.integers(2, 120)), int(rng.integers(2, 120))
+    P = int(rng.integers(2, 200)) if seed % 3 == 0 else cp.num_proj_pix(xs, ys)   # any width, or the reference's own
+    name = ["ramp", None, "hann", "ramp", "shepp-logan", "ramp", "cosine", "ramp", "hamming", "ramp"][seed] if P % 2 == 0 else None
+    th = rng.uniform(-4, 4, A) if seed % 2 else _theta(A)
+    sino = rng.random((B, A, P))
+    filt = orc.get_fourier_filter(P, name) if P % 2 == 0 else np.ones(P)   # skimage's filters need an even size
+    want = orc.iradon(sino, th, xs, ys, filt)
+    got = cp.iradon(torch.from_numpy(sino).cuda(), th, xs, ys, filt).cpu().numpy()
+    assert rel_l2(got, want) <= TOL, (B, A, P, xs, ys, name)
+
+
 @pytest.mark.parametrize("B,A,X,Y", [(3, 20, 30, 30), (9, 45, 128, 128), (2, 12, 33, 21), (20, 13, 64, 64), (17, 9, 90, 90),
                                      (5, 7, 128, 100), (33, 24, 47, 45)])
 def test_fused_fbp_is_one_kernel_and_matches_the_two_kernel_path(cp, orc, B, A, X, Y):

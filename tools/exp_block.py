@@ -21,4 +21,4 @@ for N in (8, 4, 2, 1):
             ts.append(a.elapsed_time(b))
         tot.append(float(np.median(ts)))
         if r == 0: desc = plan.describe(B)
-    print(f"NS={os.environ.get('CTR_EXP_NS','-')} N={N}: fwd per rank " + " ".join(f"{t:.3f}" for t in tot) + f"  max {max(tot):.3f} sum {sum(tot):.3f}   {desc[:110]}", flush=True)
+    print(f"N={N}: fwd per rank " + " ".join(f"{t:.3f}" for t in tot) + f"  max {max(tot):.3f} sum {sum(tot):.3f}   {desc[:110]}", flush=True)

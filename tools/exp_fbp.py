@@ -17,5 +17,5 @@ for (B, X, A) in [(1000, 128, 180), (64, 512, 720), (32, 128, 180)]:
     for _ in range(5): o = ops.fbp(y, plan)
     torch.cuda.synchronize()
     prof = _lib.profile_read(); _lib.profile_enable(False)
-    print(f"DENSE={os.environ.get('CTR_EXP_DENSE','-')} B={B} X={X} A={A} P={P}: " +
+    print(f"B={B} X={X} A={A} P={P}: " +
           "  ".join(f"{k} {v[0] / v[1]:.3f} ms" for k, v in prof.items()) + f"  sum {float(o.double().sum()):.9e} crc {zlib.crc32(o.cpu().numpy().tobytes()):08x}", flush=True)

@@ -19,4 +19,4 @@ for (B, X, A) in shapes:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); o = ops.radon_forward(img, plan, iid); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
         res.append((min(ts), zlib.crc32(o.cpu().numpy().tobytes())))
-    print(f"EXP={os.environ.get('CTR_EXP_WIDE','-')} B={B} X={X} A={A}: bilinear {res[0][0]:.3f} ms crc {res[0][1]:08x}  nearest {res[1][0]:.3f} ms crc {res[1][1]:08x}  {plan.describe(B)}", flush=True)
+    print(f"B={B} X={X} A={A}: bilinear {res[0][0]:.3f} ms crc {res[0][1]:08x}  nearest {res[1][0]:.3f} ms crc {res[1][1]:08x}  {plan.describe(B)}", flush=True)

@@ -13,4 +13,4 @@ for (B, X, A) in [(64, 512, 720), (256, 128, 180), (32, 128, 180)]:
     for _ in range(5):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); o = ops.radon_adjoint(y, plan, 1, 1); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
-    print(f"TFPAIR={os.environ.get('CTR_EXP_TFPAIR','-')} B={B} X={X} A={A}: tf_compat bilinear {min(ts):.3f} ms crc {zlib.crc32(o.cpu().numpy().tobytes()):08x}", flush=True)
+    print(f"B={B} X={X} A={A}: tf_compat bilinear {min(ts):.3f} ms crc {zlib.crc32(o.cpu().numpy().tobytes()):08x}", flush=True)

@@ -264,7 +264,8 @@ def run_reference(args, wl):
         "impl": "reference", "metric": "FBP Gpixel-angle updates/s" if fbp else METRIC, "value": value, "unit": unit,
         "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": tot / args.steps * 1e3, "higher_is_better": True,
-        "scaling": "strong" if (args.gpus > 1 and args.shard == "angle") else "weak",
+        # the N = 1 point belongs to the curve the N > 1 runs of the same command line continue (angle-sharded: total work fixed)
+        "scaling": "strong" if args.shard == "angle" else "weak",
         "vs_baseline": None, "dtype": "f64" if fbp else "f32",
         "data": "synthetic foam (unit disk, random circular pores), random cotangents",
         "config": {"workload": wl["name"], "interpolation": INTERP,
@@ -678,7 +679,10 @@ def run_batch(args, ctx, wl):
         extra.update(others)
         line = {
             "metric": METRIC, "value": rec["value"], "unit": UNIT, "n_gpus": ctx.world, "steps": args.steps, "warmup": warm,
-            "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": rec["ms_per_step"], "higher_is_better": True,
+            # N = 1 is the first point of the curve the same command line continues under torchrun: angle-sharded by default
+            # (total work fixed: strong), batch-sharded with --shard batch (work per GPU fixed: weak)
+            "scaling": "strong" if (ctx.world == 1 and args.shard == "angle") else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic foam (unit disk, random circular pores), random cotangents",
             "config": {"workload": wl["name"], "interpolation": INTERP, "adjoint": "exact", "B_per_gpu": B, "X": X, "Y": X,
                        "A": A, "P": P, "sharding": "batch" if ctx.world > 1 else "none (one GPU)",
